@@ -1,0 +1,174 @@
+/*
+ * nimrud_b200.h -- C ABI of the B200-native multiscale neighborhood eigenfeature path.
+ *
+ * The reference (grayhem/nimrud) is pure Python and has no FFI of its own: its boundary for this
+ * path is the Python call signature of nimrud/minimal/multiscale.py.  Every entry point below names
+ * the reference interface it replaces (file:line relative to the reference tree).  INTEGRATION.md
+ * shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - all array arguments are DEVICE pointers unless the name ends in `_host`; row-major, C order.
+ *   - point clouds are (n,3); `dtype` is NBR_F32 or NBR_F64.  float32 inputs are promoted to float64
+ *     exactly, so both dtypes describe the same points when the values are float32-representable.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  calls are
+ *     stream-ordered and return without synchronising unless stated.
+ *   - every function returns NBR_OK (0) or an error code; nbr_last_error() gives the message of the
+ *     last failure on the calling thread.
+ *   - scratch memory comes from the stream-ordered CUDA pool (cudaMallocAsync); the caller owns
+ *     every input and output buffer.
+ */
+#ifndef NIMRUD_B200_H
+#define NIMRUD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NBR_OK 0
+#define NBR_ERR_INVALID 1        /* bad argument                                                  */
+#define NBR_ERR_TOO_FEW_POINTS 2 /* reference: ValueError, utils/geometry.py:34-35                */
+#define NBR_ERR_ADDRESS_BITS 3   /* reference: ValueError, utils/geometry.py:59-60 (> 64 bits)    */
+#define NBR_ERR_CUDA 4
+#define NBR_ERR_UNSUPPORTED 5
+#define NBR_ERR_OUT_OF_BOUNDS 6  /* reference: ValueError, utils/geometry.py:96-97                */
+
+#define NBR_F32 0
+#define NBR_F64 1
+
+/* descriptor_mask bits for the feature kernels.  0 = the reference's 4 columns per scale
+ * [population, centroid distance, l_max/sum, l_mid/sum] (minimal/features.py:21-57).
+ * NBR_DESC_EXTENDED appends 12 columns per scale (extension, not in the reference):
+ * linearity, planarity, sphericity, omnivariance, anisotropy, eigenentropy, change of curvature,
+ * verticality, normal x, y, z (nz >= 0), sum of eigenvalues (covariance trace, ddof = 1). */
+#define NBR_DESC_REFERENCE 0
+#define NBR_DESC_EXTENDED 1
+#define NBR_COLS_REFERENCE 4
+#define NBR_COLS_EXTENDED 16
+
+const char *nbr_last_error(void);
+int nbr_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * voxel grid (replaces VoxelFilter.__init__ / _calculate_shift, utils/geometry.py:23-62)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct nbr_grid {
+    double min_corner[3];  /* points.min(0) - e/2            geometry.py:37 */
+    double max_corner[3];  /* points.max(0) + e/2            geometry.py:38 */
+    double edge;
+    int32_t widths[3];     /* ceil(log2(span/e)) per axis    geometry.py:55 */
+    int32_t shifts[3];     /* bit offset of each axis in the packed address; shifts[0] = 0 */
+    int32_t ndim;          /* 2 or 3 (2: z is ignored, width 0) */
+    int32_t reserved;
+} nbr_grid;
+
+/* min and max of an (n, ndim<=3) cloud -> 6 doubles on the DEVICE (lo[3], hi[3]); unused axes 0. */
+int nbr_bbox(const void *xyz, int dtype, int64_t n, int ndim, double *lohi_dev, void *stream);
+
+/* HOST helper: grid parameters from a bounding box.  NBR_ERR_ADDRESS_BITS if more than 64 bits. */
+int nbr_grid_from_bbox(const double lo[3], const double hi[3], double edge, int ndim, nbr_grid *out);
+
+/* ------------------------------------------------------------------------------------------------
+ * spatial index primitives
+ * ---------------------------------------------------------------------------------------------- */
+/* VoxelFilter.coordinate_to_address, geometry.py:103-116.  *oob_dev (device int32, may be NULL) is
+ * set non-zero if a point lies outside [min_corner, max_corner] (geometry.py:94-97). */
+int nbr_voxel_addresses(const void *xyz, int dtype, int64_t n, const nbr_grid *grid,
+                        int64_t *addresses, int32_t *oob_dev, void *stream);
+
+/* ascending LSD radix sort of 64-bit keys on bits [begin_bit, end_bit); result in `keys`.
+ * `tmp` holds n keys.  replaces the sort inside np.unique, geometry.py:150. */
+int nbr_sort_u64(uint64_t *keys, uint64_t *tmp, int64_t n, int begin_bit, int end_bit, void *stream);
+
+/* same, carrying a 32-bit payload (stable). */
+int nbr_sort_pairs_u64_u32(uint64_t *keys, uint64_t *keys_tmp, uint32_t *vals, uint32_t *vals_tmp,
+                           int64_t n, int begin_bit, int end_bit, void *stream);
+
+/* dedup of a sorted key array (the other half of np.unique).  out may alias nothing; *n_out_dev is
+ * a device int64. */
+int nbr_unique_u64(const uint64_t *sorted, int64_t n, uint64_t *out, int64_t *n_out_dev, void *stream);
+
+/* VoxelFilter.address_to_coordinate, geometry.py:120-138: (k*e + min_corner) + e*0.5 -> (n,ndim) f64 */
+int nbr_voxel_centres(const int64_t *addresses, int64_t n, const nbr_grid *grid, double *xyz_out,
+                      void *stream);
+
+/* exclusive prefix sum (the cell-offset scan). */
+int nbr_exclusive_scan_u32(const uint32_t *in, uint32_t *out, int64_t n, void *stream);
+int nbr_exclusive_scan_i64(const int64_t *in, int64_t *out, int64_t n, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * lattice index: the voxel-filtered search cloud of one edge length, as occupancy bit bricks
+ * (replaces VoxelFilter.unique_voxels + cKDTree(search_voxels), minimal/multiscale.py:75-87)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct nbr_lattice nbr_lattice;
+
+#define NBR_LATTICE_INDEXED 1 /* also keep the sorted unique addresses (np.unique order), so that
+                                 neighbor INDICES can be reported; needs the radix sort */
+
+int nbr_lattice_create(nbr_lattice **out, const void *search_xyz, int dtype, int64_t n_search,
+                       const nbr_grid *grid, int flags, void *stream);
+void nbr_lattice_destroy(nbr_lattice *lattice);
+/* synchronises the stream; n_voxels = number of unique voxels (== len(np.unique(addresses))). */
+int nbr_lattice_info(const nbr_lattice *lattice, int64_t *n_voxels, int64_t *n_bricks);
+/* sorted unique addresses and/or their centres (either pointer may be NULL); INDEXED lattices only. */
+int nbr_lattice_export(const nbr_lattice *lattice, int64_t *addresses, double *centres, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * queries
+ * ---------------------------------------------------------------------------------------------- */
+/* fused radius query + covariance + eigensolve + feature emission for the scales that share this
+ * lattice's edge (replaces minimal/multiscale.py:94-122 and minimal/features.py:14-57).
+ * for radius j, row i, writes cols [col_offset + j*C, col_offset + (j+1)*C) of out, C = 4 or 16 by
+ * descriptor_mask; out has `out_row_stride` elements per row and dtype out_dtype.
+ * algorithm: 0 = automatic, 1 = exact per-candidate kernel, 2 = row-interval kernel. */
+int nbr_radius_features(const nbr_lattice *lattice, const void *query_xyz, int dtype, int64_t n_query,
+                        const double *radii_host, int32_t n_radii, void *out, int out_dtype,
+                        int64_t out_row_stride, int32_t col_offset, int32_t descriptor_mask,
+                        int32_t algorithm, void *stream);
+
+/* neighbor index sets in CSR form (parity path; replaces query_ball_tree, minimal/multiscale.py:103).
+ * indices are positions in the sorted unique address array, ascending within each query.
+ * pass 1: indices == NULL, fills offsets[n_query+1] (device int64).  pass 2: fills indices. */
+int nbr_radius_sets(const nbr_lattice *lattice, const void *query_xyz, int dtype, int64_t n_query,
+                    double radius, int64_t *offsets, int32_t *indices, void *stream);
+
+/* k nearest voxels, total order (squared distance as float64, index).  no reference counterpart
+ * (extension).  idx_out (n_query,k) int32 padded with -1, d2_out (n_query,k) f64 padded
+ * with +inf; either may be NULL.  if feats_out is non-NULL also writes the 4 (or 16) feature
+ * columns for each k in ks_host (ascending, ks[n_k-1] == k). */
+int nbr_knn(const nbr_lattice *lattice, const void *query_xyz, int dtype, int64_t n_query, int32_t k,
+            int32_t *idx_out, double *d2_out, const int32_t *ks_host, int32_t n_k, void *feats_out,
+            int out_dtype, int64_t out_row_stride, int32_t col_offset, int32_t descriptor_mask,
+            void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * whole path
+ * ---------------------------------------------------------------------------------------------- */
+/* process_single_core, minimal/multiscale.py:27-67: out is (n_query, C*n_scales), scale-major.
+ * global_lohi_host: optional 6 doubles (lo, hi) of the search cloud's bounding box to anchor the
+ * lattices (multi-GPU: the all-reduced box); NULL = computed from `search`.
+ * n_voxels_host: optional int64[n_scales] receiving the unique-voxel count per scale (forces a
+ * stream synchronise). */
+int nbr_multiscale_features(const void *query_xyz, int q_dtype, int64_t n_query, const void *search_xyz,
+                            int s_dtype, int64_t n_search, const double *edges_host,
+                            const double *radii_host, int32_t n_scales, void *out, int out_dtype,
+                            int32_t descriptor_mask, const double *global_lohi_host,
+                            int64_t *n_voxels_host, void *stream);
+
+/* same with HOST buffers: copies the clouds in, runs, copies the features out; synchronous.
+ * this is the call the reference-facing Python shim makes for numpy arguments. */
+int nbr_multiscale_features_host(const void *query_host, int q_dtype, int64_t n_query,
+                                 const void *search_host, int s_dtype, int64_t n_search,
+                                 const double *edges_host, const double *radii_host, int32_t n_scales,
+                                 void *out_host, int out_dtype, int32_t descriptor_mask,
+                                 int64_t *n_voxels_host);
+
+/* counters for tests and benches: number of kernels this library has launched in this process. */
+int64_t nbr_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NIMRUD_B200_H */

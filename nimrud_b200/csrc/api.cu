@@ -1,0 +1,242 @@
+// api.cu -- C ABI glue: errors, scratch memory, the radius-feature dispatcher and the whole-path
+// drivers that stand in for process_single_core (nimrud/minimal/multiscale.py:27-67).
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "lattice.cuh"
+
+namespace nbr {
+
+static thread_local std::string g_error;
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const std::string &msg) { g_error = msg; }
+
+int fail(int code, const std::string &msg)
+{
+    g_error = msg;
+    return code;
+}
+
+int Scratch::alloc(size_t bytes, cudaStream_t s)
+{
+    release();
+    stream = s;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMallocAsync(&ptr, bytes, s);
+    if (e != cudaSuccess) {
+        ptr = nullptr;
+        return fail(NBR_ERR_CUDA, std::string("cudaMallocAsync(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+    }
+    return NBR_OK;
+}
+
+void Scratch::release()
+{
+    if (ptr) cudaFreeAsync(ptr, stream);
+    ptr = nullptr;
+}
+
+int device_sm_count()
+{
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+            sms = 148;
+        // keep freed scratch in the pool: the path allocates the same sizes on every call
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
+    return sms;
+}
+
+int radius_features_exact(const Lattice *lat, const void *query, int dtype, int64_t nq, const double *radii, int nr,
+                          void *out, int out_dtype, int64_t row_stride, int col_offset, int descriptor_mask,
+                          cudaStream_t stream);
+int radius_features_rows(const Lattice *lat, const void *query, int dtype, int64_t nq, const double *radii, int nr,
+                         void *out, int out_dtype, int64_t row_stride, int col_offset, int descriptor_mask,
+                         cudaStream_t stream, bool *handled);
+int radius_sets(const Lattice *lat, const void *query, int dtype, int64_t nq, double radius, int64_t *offsets,
+                int32_t *indices, cudaStream_t stream);
+
+static int check_cloud_dtype(int dtype, const char *who)
+{
+    if (dtype != NBR_F32 && dtype != NBR_F64) return fail(NBR_ERR_INVALID, std::string(who) + ": dtype must be NBR_F32 or NBR_F64");
+    return NBR_OK;
+}
+
+int radius_features(const Lattice *lat, const void *query, int dtype, int64_t nq, const double *radii, int nr,
+                    void *out, int out_dtype, int64_t row_stride, int col_offset, int descriptor_mask, int algorithm,
+                    cudaStream_t stream)
+{
+    if (lat->grid.ndim != 3) return fail(NBR_ERR_INVALID, "radius_features: the feature path is 3-D only");
+    for (int k = 0; k < nr; ++k)
+        if (!(radii[k] >= 0)) return fail(NBR_ERR_INVALID, "radius_features: radii must be >= 0");
+    if (algorithm != 1) {
+        bool handled = false;
+        NBR_TRY(radius_features_rows(lat, query, dtype, nq, radii, nr, out, out_dtype, row_stride, col_offset,
+                                     descriptor_mask, stream, &handled));
+        if (handled) return NBR_OK;
+        if (algorithm == 2) return fail(NBR_ERR_UNSUPPORTED, "radius_features: row-interval kernel does not cover this r/e");
+    }
+    return radius_features_exact(lat, query, dtype, nq, radii, nr, out, out_dtype, row_stride, col_offset,
+                                 descriptor_mask, stream);
+}
+
+// groups scales by edge length, builds one lattice per distinct edge and runs the fused kernel once
+// per group (all radii of the group in one pass over each query's neighborhood).
+int multiscale_features(const void *query, int q_dtype, int64_t nq, const void *search, int s_dtype, int64_t ns,
+                        const double *edges, const double *radii, int n_scales, void *out, int out_dtype,
+                        int descriptor_mask, const double *global_lohi, int64_t *n_voxels_host, cudaStream_t stream)
+{
+    NBR_TRY(check_cloud_dtype(q_dtype, "multiscale_features"));
+    NBR_TRY(check_cloud_dtype(s_dtype, "multiscale_features"));
+    if (out_dtype != NBR_F32 && out_dtype != NBR_F64) return fail(NBR_ERR_INVALID, "multiscale_features: bad out_dtype");
+    if (n_scales < 0 || nq < 0) return fail(NBR_ERR_INVALID, "multiscale_features: negative size");
+    if (ns < 2) return fail(NBR_ERR_TOO_FEW_POINTS, "need at least 2 points to define a voxel grid");
+    if (n_scales == 0 || nq == 0) return NBR_OK;
+    if (!query || !search || !edges || !radii || !out) return fail(NBR_ERR_INVALID, "multiscale_features: null argument");
+
+    double lohi[6];
+    if (global_lohi) {
+        std::copy(global_lohi, global_lohi + 6, lohi);
+    } else {
+        Scratch box;
+        NBR_TRY(box.alloc(sizeof(double) * 6, stream));
+        NBR_TRY(bbox(search, s_dtype, ns, 3, box.as<double>(), stream));
+        NBR_CUDA(cudaMemcpyAsync(lohi, box.ptr, sizeof(lohi), cudaMemcpyDeviceToHost, stream));
+        NBR_CUDA(cudaStreamSynchronize(stream));
+    }
+
+    const int ncol = (descriptor_mask & NBR_DESC_EXTENDED) ? NBR_COLS_EXTENDED : NBR_COLS_REFERENCE;
+    const int64_t row_stride = (int64_t)ncol * n_scales;
+    std::vector<char> done(n_scales, 0);
+    std::vector<Lattice *> lattices;
+    std::vector<std::pair<Lattice *, int>> voxel_of_scale;   // lattice, scale
+    int rc = NBR_OK;
+    for (int s = 0; s < n_scales && rc == NBR_OK; ++s) {
+        if (done[s]) continue;
+        nbr_grid grid;
+        rc = grid_from_bbox(lohi, lohi + 3, edges[s], 3, &grid);
+        if (rc) break;
+        Lattice *lat = nullptr;
+        rc = lattice_create(&lat, search, s_dtype, ns, &grid, 0, stream);
+        if (rc) break;
+        lattices.push_back(lat);
+        // scales sharing this edge form runs of consecutive columns where possible
+        int t = s;
+        while (t < n_scales && rc == NBR_OK) {
+            if (done[t] || edges[t] != edges[s]) { ++t; continue; }
+            int u = t;
+            std::vector<double> group;
+            while (u < n_scales && !done[u] && edges[u] == edges[s]) {
+                group.push_back(radii[u]);
+                done[u] = 1;
+                voxel_of_scale.push_back({lat, u});
+                ++u;
+            }
+            rc = radius_features(lat, query, q_dtype, nq, group.data(), (int)group.size(), out, out_dtype, row_stride,
+                                 t * ncol, descriptor_mask, 0, stream);
+            t = u;
+        }
+    }
+    if (rc == NBR_OK && n_voxels_host) {
+        for (auto &p : voxel_of_scale) {
+            int64_t nv = 0;
+            rc = lattice_counts(p.first, &nv, nullptr);
+            if (rc) break;
+            n_voxels_host[p.second] = nv;
+        }
+    }
+    for (Lattice *l : lattices) delete l;
+    return rc;
+}
+
+}  // namespace nbr
+
+using namespace nbr;
+
+extern "C" const char *nbr_last_error(void) { return g_error.c_str(); }
+extern "C" int nbr_version(void) { return 100; }
+extern "C" int64_t nbr_kernel_launches(void) { return g_launches.load(); }
+
+extern "C" int nbr_radius_features(const nbr_lattice *lattice, const void *query_xyz, int dtype, int64_t n_query,
+                                   const double *radii_host, int32_t n_radii, void *out, int out_dtype,
+                                   int64_t out_row_stride, int32_t col_offset, int32_t descriptor_mask,
+                                   int32_t algorithm, void *stream)
+{
+    if (!lattice || !query_xyz || !radii_host || !out) return fail(NBR_ERR_INVALID, "nbr_radius_features: null argument");
+    NBR_TRY(check_cloud_dtype(dtype, "nbr_radius_features"));
+    if (out_dtype != NBR_F32 && out_dtype != NBR_F64) return fail(NBR_ERR_INVALID, "nbr_radius_features: bad out_dtype");
+    return radius_features(reinterpret_cast<const Lattice *>(lattice), query_xyz, dtype, n_query, radii_host, n_radii, out,
+                           out_dtype, out_row_stride, col_offset, descriptor_mask, algorithm, (cudaStream_t)stream);
+}
+
+extern "C" int nbr_radius_sets(const nbr_lattice *lattice, const void *query_xyz, int dtype, int64_t n_query,
+                               double radius, int64_t *offsets, int32_t *indices, void *stream)
+{
+    if (!lattice || !query_xyz || !offsets) return fail(NBR_ERR_INVALID, "nbr_radius_sets: null argument");
+    NBR_TRY(check_cloud_dtype(dtype, "nbr_radius_sets"));
+    return radius_sets(reinterpret_cast<const Lattice *>(lattice), query_xyz, dtype, n_query, radius, offsets, indices,
+                       (cudaStream_t)stream);
+}
+
+extern "C" int nbr_multiscale_features(const void *query_xyz, int q_dtype, int64_t n_query, const void *search_xyz,
+                                       int s_dtype, int64_t n_search, const double *edges_host,
+                                       const double *radii_host, int32_t n_scales, void *out, int out_dtype,
+                                       int32_t descriptor_mask, const double *global_lohi_host,
+                                       int64_t *n_voxels_host, void *stream)
+{
+    return multiscale_features(query_xyz, q_dtype, n_query, search_xyz, s_dtype, n_search, edges_host, radii_host,
+                               n_scales, out, out_dtype, descriptor_mask, global_lohi_host, n_voxels_host,
+                               (cudaStream_t)stream);
+}
+
+static size_t elem_size(int dtype) { return dtype == NBR_F32 ? 4 : 8; }
+
+extern "C" int nbr_multiscale_features_host(const void *query_host, int q_dtype, int64_t n_query,
+                                            const void *search_host, int s_dtype, int64_t n_search,
+                                            const double *edges_host, const double *radii_host, int32_t n_scales,
+                                            void *out_host, int out_dtype, int32_t descriptor_mask,
+                                            int64_t *n_voxels_host)
+{
+    NBR_TRY(check_cloud_dtype(q_dtype, "nbr_multiscale_features_host"));
+    NBR_TRY(check_cloud_dtype(s_dtype, "nbr_multiscale_features_host"));
+    if (out_dtype != NBR_F32 && out_dtype != NBR_F64) return fail(NBR_ERR_INVALID, "nbr_multiscale_features_host: bad out_dtype");
+    if (n_search < 2) return fail(NBR_ERR_TOO_FEW_POINTS, "need at least 2 points to define a voxel grid");
+    if (n_query <= 0 || n_scales <= 0) return NBR_OK;
+    if (!query_host || !search_host || !out_host) return fail(NBR_ERR_INVALID, "nbr_multiscale_features_host: null argument");
+    cudaStream_t stream;
+    NBR_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    const int ncol = (descriptor_mask & NBR_DESC_EXTENDED) ? NBR_COLS_EXTENDED : NBR_COLS_REFERENCE;
+    const size_t qbytes = (size_t)n_query * 3 * elem_size(q_dtype);
+    const size_t sbytes = (size_t)n_search * 3 * elem_size(s_dtype);
+    const size_t obytes = (size_t)n_query * ncol * n_scales * elem_size(out_dtype);
+    const bool same = query_host == search_host && q_dtype == s_dtype && n_query == n_search;
+    int rc = NBR_OK;
+    {
+        Scratch q, s, o;
+        rc = s.alloc(sbytes, stream);
+        if (!rc && !same) rc = q.alloc(qbytes, stream);
+        if (!rc) rc = o.alloc(obytes, stream);
+        cudaError_t e = cudaSuccess;
+        if (!rc) e = cudaMemcpyAsync(s.ptr, search_host, sbytes, cudaMemcpyHostToDevice, stream);
+        if (!rc && e == cudaSuccess && !same) e = cudaMemcpyAsync(q.ptr, query_host, qbytes, cudaMemcpyHostToDevice, stream);
+        if (!rc && e == cudaSuccess)
+            rc = multiscale_features(same ? s.ptr : q.ptr, q_dtype, n_query, s.ptr, s_dtype, n_search, edges_host,
+                                     radii_host, n_scales, o.ptr, out_dtype, descriptor_mask, nullptr, n_voxels_host,
+                                     stream);
+        if (!rc && e == cudaSuccess) e = cudaMemcpyAsync(out_host, o.ptr, obytes, cudaMemcpyDeviceToHost, stream);
+        if (!rc && e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (!rc && e != cudaSuccess) rc = fail(NBR_ERR_CUDA, std::string("host path: ") + cudaGetErrorString(e));
+    }
+    cudaStreamSynchronize(stream);
+    cudaStreamDestroy(stream);
+    return rc;
+}

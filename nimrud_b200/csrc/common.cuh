@@ -1,0 +1,126 @@
+// common.cuh -- shared host/device helpers for the nimrud_b200 CUDA library (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/nimrud_b200.h"
+
+namespace nbr {
+
+// ------------------------------------------------------------------------------------------------
+// errors, launch counter
+// ------------------------------------------------------------------------------------------------
+void set_error(const std::string &msg);
+int fail(int code, const std::string &msg);
+extern std::atomic<int64_t> g_launches;
+
+#define NBR_CUDA(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return ::nbr::fail(NBR_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+#define NBR_TRY(expr)                  \
+    do {                               \
+        int _rc = (expr);              \
+        if (_rc != NBR_OK) return _rc; \
+    } while (0)
+
+// count + check a kernel launch
+#define NBR_LAUNCHED()                                                                        \
+    do {                                                                                      \
+        ::nbr::g_launches.fetch_add(1, std::memory_order_relaxed);                            \
+        cudaError_t _e = cudaGetLastError();                                                  \
+        if (_e != cudaSuccess)                                                                \
+            return ::nbr::fail(NBR_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(_e)); \
+    } while (0)
+
+// stream-ordered scratch buffer (RAII; freed on the same stream)
+struct Scratch {
+    void *ptr = nullptr;
+    cudaStream_t stream = nullptr;
+    Scratch() {}
+    Scratch(const Scratch &) = delete;
+    Scratch &operator=(const Scratch &) = delete;
+    ~Scratch() { release(); }
+    int alloc(size_t bytes, cudaStream_t s);
+    void release();
+    template <typename T>
+    T *as() const { return reinterpret_cast<T *>(ptr); }
+};
+
+int device_sm_count();
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ------------------------------------------------------------------------------------------------
+// device-side grid description (copied by value into kernels)
+// ------------------------------------------------------------------------------------------------
+struct GridDev {
+    double minc[3];
+    double edge;
+    int32_t widths[3];
+    int32_t shifts[3];
+    int32_t ncell[3];   // number of addressable cells actually spanned by the bounding box
+    int32_t ndim;
+};
+
+// brick geometry: 32 (x) * 8 (y) * 4 (z) cells = 32 words of 32 bits = 128 bytes
+constexpr int BRICK_X = 32, BRICK_Y = 8, BRICK_Z = 4, BRICK_WORDS = 32;
+constexpr int BRICK_YS = 3, BRICK_ZS = 2, BRICK_XS = 5;
+
+struct LatticeDev {
+    GridDev g;
+    int32_t nbx, nby, nbz;        // directory dimensions (bricks)
+    const uint32_t *dir;          // [nbz][nby][nbx] -> slot; 0 = empty (slot 0 is an all-zero brick)
+    const uint32_t *pool;         // [slots][32] occupancy words; word = (z&3)*8 + (y&7), bit = x&31
+    const uint32_t *rowbase;      // [slots][32] index (np.unique order) of the first voxel of the row; or NULL
+};
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------------
+// exact float64 arithmetic of the reference (no fma contraction anywhere on these paths)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double load_coord(const void *xyz, int dtype, int64_t i, int ndim, int a)
+{
+    if (a >= ndim) return 0.0;
+    return dtype == NBR_F32 ? (double)reinterpret_cast<const float *>(xyz)[i * ndim + a]
+                            : reinterpret_cast<const double *>(xyz)[i * ndim + a];
+}
+
+// floor((p - min_corner) / e)  -- utils/geometry.py:107
+__device__ __forceinline__ double cell_coord_f(double p, double minc, double edge)
+{
+    return floor(__ddiv_rn(__dsub_rn(p, minc), edge));
+}
+
+// (k*e + min_corner) + e*0.5 -- utils/geometry.py:137
+__device__ __forceinline__ double cell_centre(int64_t k, double minc, double edge)
+{
+    return __dadd_rn(__dadd_rn(__dmul_rn((double)k, edge), minc), __dmul_rn(edge, 0.5));
+}
+
+// one squared coordinate difference; the membership sum is ((dx2 + dy2) + dz2) <= r2
+__device__ __forceinline__ double sqdiff(double q, double c)
+{
+    double d = __dsub_rn(q, c);
+    return __dmul_rn(d, d);
+}
+
+__device__ __forceinline__ uint32_t lanemask_lt()
+{
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+#endif
+
+}  // namespace nbr

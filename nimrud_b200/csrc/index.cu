@@ -1,0 +1,491 @@
+// index.cu -- the spatial index: voxel grid parameters, packed addresses, unique voxels, centres, and
+// the occupancy bit-brick lattice that the query kernels read.
+//
+// reference: nimrud/utils/geometry.py:16-154 (VoxelFilter) and the search_voxels/cKDTree build of
+// nimrud/minimal/multiscale.py:75-87.
+#include <math.h>
+
+#include "common.cuh"
+#include "lattice.cuh"
+#include "scan.cuh"
+
+namespace nbr {
+
+int sort_keys(uint64_t *keys, uint64_t *tmp, int64_t n, int begin_bit, int end_bit, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------
+// bounding box
+// ------------------------------------------------------------------------------------------------
+constexpr int BBOX_THREADS = 256;
+
+__device__ __forceinline__ double warp_min(double v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// partial[block][6]
+__global__ void __launch_bounds__(BBOX_THREADS)
+bbox_partial_kernel(const void *__restrict__ xyz, int dtype, int64_t n, int ndim, double *__restrict__ partial)
+{
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    // flat coalesced sweep over the n*ndim scalars; axis = flat index mod ndim
+    const int64_t total = n * ndim;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        double v = dtype == NBR_F32 ? (double)reinterpret_cast<const float *>(xyz)[i]
+                                    : reinterpret_cast<const double *>(xyz)[i];
+        int a = (int)(i % ndim);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (a == k) { lo[k] = fmin(lo[k], v); hi[k] = fmax(hi[k], v); }
+    }
+    __shared__ double s[BBOX_THREADS / 32][6];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double a = warp_min(lo[k]), b = warp_max(hi[k]);
+        if (lane == 0) { s[warp][k] = a; s[warp][3 + k] = b; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double r = s[0][threadIdx.x];
+        for (int w = 1; w < BBOX_THREADS / 32; ++w)
+            r = threadIdx.x < 3 ? fmin(r, s[w][threadIdx.x]) : fmax(r, s[w][threadIdx.x]);
+        partial[blockIdx.x * 6 + threadIdx.x] = r;
+    }
+}
+
+__global__ void bbox_final_kernel(const double *__restrict__ partial, int blocks, int ndim, double *__restrict__ out)
+{
+    const int k = threadIdx.x;
+    if (k >= 6) return;
+    double r = partial[k];
+    for (int b = 1; b < blocks; ++b) r = k < 3 ? fmin(r, partial[b * 6 + k]) : fmax(r, partial[b * 6 + k]);
+    if ((k % 3) >= ndim) r = 0.0;
+    out[k] = r;
+}
+
+int bbox(const void *xyz, int dtype, int64_t n, int ndim, double *lohi_dev, cudaStream_t stream)
+{
+    if (n < 1) return fail(NBR_ERR_TOO_FEW_POINTS, "need at least 1 point for a bounding box");
+    int blocks = (int)std::min<int64_t>(ceil_div(n * ndim, BBOX_THREADS * 8), device_sm_count() * 4);
+    if (blocks < 1) blocks = 1;
+    Scratch partial;
+    NBR_TRY(partial.alloc(sizeof(double) * 6 * blocks, stream));
+    bbox_partial_kernel<<<blocks, BBOX_THREADS, 0, stream>>>(xyz, dtype, n, ndim, partial.as<double>());
+    NBR_LAUNCHED();
+    bbox_final_kernel<<<1, 32, 0, stream>>>(partial.as<double>(), blocks, ndim, lohi_dev);
+    NBR_LAUNCHED();
+    return NBR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// grid parameters (host)   utils/geometry.py:37-62
+// ------------------------------------------------------------------------------------------------
+int grid_from_bbox(const double lo[3], const double hi[3], double edge, int ndim, nbr_grid *out)
+{
+    if (!(edge > 0) || (ndim != 2 && ndim != 3)) return fail(NBR_ERR_INVALID, "grid: edge must be > 0, ndim 2 or 3");
+    memset(out, 0, sizeof(*out));
+    out->edge = edge;
+    out->ndim = ndim;
+    double total = 0;
+    int shift = 0;
+    for (int a = 0; a < 3; ++a) {
+        if (a >= ndim) { out->widths[a] = 0; out->shifts[a] = shift; continue; }
+        out->min_corner[a] = lo[a] - edge / 2;
+        out->max_corner[a] = hi[a] + edge / 2;
+        double span = out->max_corner[a] - out->min_corner[a];
+        double w = ceil(log2(span / edge));
+        if (!(w >= 0)) w = 0;     // degenerate (span <= e): the reference breaks here (int("0b")), we use 0 bits
+        total += w;
+        out->widths[a] = (int32_t)w;
+        out->shifts[a] = shift;
+        shift += (int32_t)w;
+    }
+    if (total > 64) return fail(NBR_ERR_ADDRESS_BITS, "edge length is too small to address this space");
+    return NBR_OK;
+}
+
+int grid_to_dev(const nbr_grid *g, GridDev *d)
+{
+    for (int a = 0; a < 3; ++a) {
+        d->minc[a] = g->min_corner[a];
+        d->widths[a] = g->widths[a];
+        d->shifts[a] = g->shifts[a];
+        double cells = a < g->ndim ? floor((g->max_corner[a] - g->min_corner[a]) / g->edge) + 1.0 : 1.0;
+        if (cells > 2147483000.0) return fail(NBR_ERR_UNSUPPORTED, "more than 2^31 cells along one axis");
+        d->ncell[a] = (int32_t)cells;
+    }
+    d->edge = g->edge;
+    d->ndim = g->ndim;
+    return NBR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// addresses / centres      utils/geometry.py:103-138
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+address_kernel(const void *__restrict__ xyz, int dtype, int64_t n, GridDev g, double maxc0, double maxc1, double maxc2,
+               int64_t *__restrict__ addr, int32_t *__restrict__ oob)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double maxc[3] = {maxc0, maxc1, maxc2};
+    int64_t a64 = 0;
+    bool bad = false;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        if (a < g.ndim) {
+            double p = load_coord(xyz, dtype, i, g.ndim, a);
+            bad |= (p < g.minc[a]) | (p > maxc[a]);
+            int64_t k = (int64_t)cell_coord_f(p, g.minc[a], g.edge);
+            a64 += k << g.shifts[a];
+        }
+    }
+    addr[i] = a64;
+    if (bad && oob) *oob = 1;
+}
+
+__global__ void __launch_bounds__(256)
+centre_kernel(const int64_t *__restrict__ addr, int64_t n, GridDev g, double *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t k = addr[i];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        if (a < g.ndim) {
+            int64_t mask = g.widths[a] >= 64 ? -1ll : ((1ll << g.widths[a]) - 1);
+            int64_t c = (k >> g.shifts[a]) & mask;
+            out[i * g.ndim + a] = cell_centre(c, g.minc[a], g.edge);
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
+// unique of a sorted array
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+head_flag_kernel(const uint64_t *__restrict__ keys, int64_t n, uint32_t *__restrict__ flags)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256)
+compact_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ slots, int64_t n,
+               uint64_t *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t s = slots[i];
+    if (s) out[s - 1] = keys[i];
+}
+
+__global__ void widen_count_kernel(const uint32_t *c, int64_t *out) { *out = (int64_t)*c; }
+
+int unique_sorted(const uint64_t *sorted, int64_t n, uint64_t *out, int64_t *n_out_dev, cudaStream_t stream)
+{
+    if (n <= 0) {
+        NBR_CUDA(cudaMemsetAsync(n_out_dev, 0, sizeof(int64_t), stream));
+        return NBR_OK;
+    }
+    Scratch flags, count;
+    NBR_TRY(flags.alloc(sizeof(uint32_t) * n, stream));
+    NBR_TRY(count.alloc(sizeof(uint32_t), stream));
+    const unsigned blocks = (unsigned)ceil_div(n, 256);
+    head_flag_kernel<<<blocks, 256, 0, stream>>>(sorted, n, flags.as<uint32_t>());
+    NBR_LAUNCHED();
+    NBR_TRY(flags_to_slots(flags.as<uint32_t>(), n, count.as<uint32_t>(), stream));
+    compact_kernel<<<blocks, 256, 0, stream>>>(sorted, flags.as<uint32_t>(), n, out);
+    NBR_LAUNCHED();
+    widen_count_kernel<<<1, 1, 0, stream>>>(count.as<uint32_t>(), n_out_dev);
+    NBR_LAUNCHED();
+    return NBR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// lattice (bit bricks)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void point_cell(const void *xyz, int dtype, int64_t i, const GridDev &g, int c[3])
+{
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        int v = 0;
+        if (a < g.ndim) {
+            double p = load_coord(xyz, dtype, i, g.ndim, a);
+            double k = cell_coord_f(p, g.minc[a], g.edge);
+            // search points lie inside the box by construction; clamp defends against a caller-supplied
+            // (global) box that does not contain them.
+            k = fmin(fmax(k, 0.0), (double)(g.ncell[a] - 1));
+            v = (int)k;
+        }
+        c[a] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+brick_mark_kernel(const void *__restrict__ xyz, int dtype, int64_t n, GridDev g, int nbx, int nby,
+                  uint32_t *__restrict__ dir)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int c[3];
+    point_cell(xyz, dtype, i, g, c);
+    const int64_t b = ((int64_t)(c[2] >> BRICK_ZS) * nby + (c[1] >> BRICK_YS)) * nbx + (c[0] >> BRICK_XS);
+    if (dir[b] == 0) dir[b] = 1;   // benign race: every writer stores 1
+}
+
+__global__ void __launch_bounds__(256)
+pool_zero_kernel(uint32_t *__restrict__ pool, const uint32_t *__restrict__ n_bricks)
+{
+    const int64_t words = ((int64_t)*n_bricks + 1) * BRICK_WORDS;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (int64_t)gridDim.x * blockDim.x)
+        pool[i] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+brick_fill_kernel(const void *__restrict__ xyz, int dtype, int64_t n, GridDev g, int nbx, int nby,
+                  const uint32_t *__restrict__ dir, uint32_t *__restrict__ pool)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int c[3];
+    point_cell(xyz, dtype, i, g, c);
+    const int64_t b = ((int64_t)(c[2] >> BRICK_ZS) * nby + (c[1] >> BRICK_YS)) * nbx + (c[0] >> BRICK_XS);
+    const uint32_t slot = dir[b];
+    const int word = ((c[2] & (BRICK_Z - 1)) << BRICK_YS) | (c[1] & (BRICK_Y - 1));
+    const uint32_t bit = 1u << (c[0] & 31);
+    uint32_t *w = pool + (int64_t)slot * BRICK_WORDS + word;
+    if ((*w & bit) == 0) atomicOr(w, bit);
+}
+
+// number of occupied voxels = popcount of the pool
+__global__ void __launch_bounds__(256)
+pool_count_kernel(const uint32_t *__restrict__ pool, const uint32_t *__restrict__ n_bricks,
+                  unsigned long long *__restrict__ total)
+{
+    const int64_t words = ((int64_t)*n_bricks + 1) * BRICK_WORDS;
+    unsigned long long acc = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (int64_t)gridDim.x * blockDim.x)
+        acc += __popc(pool[i]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(total, acc);
+}
+
+// for every sorted unique address that starts a (brick,row) word: rowbase[slot][word] = its rank
+__global__ void __launch_bounds__(256)
+rowbase_kernel(const uint64_t *__restrict__ ukeys, const int64_t *__restrict__ n_unique, GridDev g, int nbx,
+               int nby, const uint32_t *__restrict__ dir, uint32_t *__restrict__ rowbase)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *n_unique) return;
+    int c[3], p[3];
+    const uint64_t k = ukeys[i];
+    const uint64_t kp = i ? ukeys[i - 1] : 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        uint64_t mask = g.widths[a] >= 64 ? ~0ull : ((1ull << g.widths[a]) - 1);
+        c[a] = (int)((k >> g.shifts[a]) & mask);
+        p[a] = (int)((kp >> g.shifts[a]) & mask);
+    }
+    const bool head = i == 0 || c[2] != p[2] || c[1] != p[1] || (c[0] >> BRICK_XS) != (p[0] >> BRICK_XS);
+    if (!head) return;
+    const int64_t b = ((int64_t)(c[2] >> BRICK_ZS) * nby + (c[1] >> BRICK_YS)) * nbx + (c[0] >> BRICK_XS);
+    const int word = ((c[2] & (BRICK_Z - 1)) << BRICK_YS) | (c[1] & (BRICK_Y - 1));
+    rowbase[(int64_t)dir[b] * BRICK_WORDS + word] = (uint32_t)i;
+}
+
+Lattice::~Lattice()
+{
+    // buffers were allocated stream-ordered; free them the same way
+    if (dir) cudaFreeAsync(dir, stream);
+    if (pool) cudaFreeAsync(pool, stream);
+    if (rowbase) cudaFreeAsync(rowbase, stream);
+    if (ukeys) cudaFreeAsync(ukeys, stream);
+    if (counters) cudaFreeAsync(counters, stream);
+}
+
+LatticeDev Lattice::dev() const
+{
+    LatticeDev d;
+    d.g = gdev;
+    d.nbx = nbx; d.nby = nby; d.nbz = nbz;
+    d.dir = dir; d.pool = pool; d.rowbase = rowbase;
+    return d;
+}
+
+int lattice_create(Lattice **out, const void *xyz, int dtype, int64_t n, const nbr_grid *grid, int flags,
+                   cudaStream_t stream)
+{
+    if (!out || !xyz || !grid) return fail(NBR_ERR_INVALID, "lattice_create: null argument");
+    if (dtype != NBR_F32 && dtype != NBR_F64) return fail(NBR_ERR_INVALID, "lattice_create: bad dtype");
+    if (n < 1) return fail(NBR_ERR_TOO_FEW_POINTS, "lattice_create: empty search cloud");
+    if (n >= (int64_t)1 << 31) return fail(NBR_ERR_UNSUPPORTED, "lattice_create: more than 2^31 search points");
+    Lattice *L = new Lattice();
+    L->stream = stream;
+    L->grid = *grid;
+    L->n_search = n;
+    int rc = grid_to_dev(grid, &L->gdev);
+    if (rc) { delete L; return rc; }
+    L->nbx = (L->gdev.ncell[0] + BRICK_X - 1) / BRICK_X;
+    L->nby = (L->gdev.ncell[1] + BRICK_Y - 1) / BRICK_Y;
+    L->nbz = (L->gdev.ncell[2] + BRICK_Z - 1) / BRICK_Z;
+    const double dir_entries = (double)L->nbx * L->nby * L->nbz;
+    if (dir_entries > 3.0e9) {
+        delete L;
+        return fail(NBR_ERR_UNSUPPORTED, "brick directory would exceed 12 GB; extent / edge too large");
+    }
+    L->n_dir = (int64_t)L->nbx * L->nby * L->nbz;
+    L->pool_slots = std::min<int64_t>(n, L->n_dir) + 1;
+
+#define L_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { delete L; \
+        return fail(NBR_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
+#define L_TRY(expr) do { int _rc = (expr); if (_rc) { delete L; return _rc; } } while (0)
+#define L_LAUNCHED() do { g_launches.fetch_add(1, std::memory_order_relaxed); cudaError_t _e = cudaGetLastError(); \
+        if (_e != cudaSuccess) { delete L; return fail(NBR_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(_e)); } } while (0)
+
+    L_CUDA(cudaMallocAsync(&L->dir, sizeof(uint32_t) * L->n_dir, stream));
+    L_CUDA(cudaMallocAsync(&L->pool, sizeof(uint32_t) * BRICK_WORDS * L->pool_slots, stream));
+    L_CUDA(cudaMallocAsync(&L->counters, 64, stream));
+    L_CUDA(cudaMemsetAsync(L->dir, 0, sizeof(uint32_t) * L->n_dir, stream));
+    L_CUDA(cudaMemsetAsync(L->counters, 0, 64, stream));
+    uint32_t *n_bricks_dev = reinterpret_cast<uint32_t *>(L->counters);
+    unsigned long long *n_vox_dev = reinterpret_cast<unsigned long long *>(L->counters + 8);
+    int64_t *n_unique_dev = reinterpret_cast<int64_t *>(L->counters + 16);
+
+    const unsigned blocks = (unsigned)ceil_div(n, 256);
+    const int sweep_blocks = device_sm_count() * 8;
+    brick_mark_kernel<<<blocks, 256, 0, stream>>>(xyz, dtype, n, L->gdev, L->nbx, L->nby, L->dir);
+    L_LAUNCHED();
+    L_TRY(flags_to_slots(L->dir, L->n_dir, n_bricks_dev, stream));
+    pool_zero_kernel<<<sweep_blocks, 256, 0, stream>>>(L->pool, n_bricks_dev);
+    L_LAUNCHED();
+    brick_fill_kernel<<<blocks, 256, 0, stream>>>(xyz, dtype, n, L->gdev, L->nbx, L->nby, L->dir, L->pool);
+    L_LAUNCHED();
+    pool_count_kernel<<<sweep_blocks, 256, 0, stream>>>(L->pool, n_bricks_dev, n_vox_dev);
+    L_LAUNCHED();
+
+    if (flags & NBR_LATTICE_INDEXED) {
+        // np.unique order: sort the packed addresses, dedup, remember the rank of each row head
+        Scratch addr, tmp;
+        L_TRY(addr.alloc(sizeof(uint64_t) * n, stream));
+        L_TRY(tmp.alloc(sizeof(uint64_t) * n, stream));
+        L_CUDA(cudaMallocAsync(&L->ukeys, sizeof(uint64_t) * n, stream));
+        L_CUDA(cudaMallocAsync(&L->rowbase, sizeof(uint32_t) * BRICK_WORDS * L->pool_slots, stream));
+        address_kernel<<<blocks, 256, 0, stream>>>(xyz, dtype, n, L->gdev, grid->max_corner[0], grid->max_corner[1],
+                                                   grid->max_corner[2], addr.as<int64_t>(), nullptr);
+        L_LAUNCHED();
+        const int bits = grid->widths[0] + grid->widths[1] + grid->widths[2];
+        L_TRY(sort_keys(addr.as<uint64_t>(), tmp.as<uint64_t>(), n, 0, bits, stream));
+        L_TRY(unique_sorted(addr.as<uint64_t>(), n, L->ukeys, n_unique_dev, stream));
+        rowbase_kernel<<<blocks, 256, 0, stream>>>(L->ukeys, n_unique_dev, L->gdev, L->nbx, L->nby, L->dir, L->rowbase);
+        L_LAUNCHED();
+        L->indexed = true;
+    }
+    *out = L;
+    return NBR_OK;
+#undef L_CUDA
+#undef L_TRY
+#undef L_LAUNCHED
+}
+
+int lattice_counts(const Lattice *L, int64_t *n_voxels, int64_t *n_bricks)
+{
+    unsigned char host[64];
+    NBR_CUDA(cudaMemcpyAsync(host, L->counters, 64, cudaMemcpyDeviceToHost, L->stream));
+    NBR_CUDA(cudaStreamSynchronize(L->stream));
+    if (n_bricks) *n_bricks = (int64_t) * reinterpret_cast<uint32_t *>(host);
+    if (n_voxels) *n_voxels = (int64_t) * reinterpret_cast<unsigned long long *>(host + 8);
+    return NBR_OK;
+}
+
+}  // namespace nbr
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+using namespace nbr;
+
+extern "C" int nbr_bbox(const void *xyz, int dtype, int64_t n, int ndim, double *lohi_dev, void *stream)
+{
+    if (!xyz || !lohi_dev || (ndim != 2 && ndim != 3)) return fail(NBR_ERR_INVALID, "nbr_bbox: bad argument");
+    return bbox(xyz, dtype, n, ndim, lohi_dev, (cudaStream_t)stream);
+}
+
+extern "C" int nbr_grid_from_bbox(const double lo[3], const double hi[3], double edge, int ndim, nbr_grid *out)
+{
+    if (!lo || !hi || !out) return fail(NBR_ERR_INVALID, "nbr_grid_from_bbox: null argument");
+    return grid_from_bbox(lo, hi, edge, ndim, out);
+}
+
+extern "C" int nbr_voxel_addresses(const void *xyz, int dtype, int64_t n, const nbr_grid *grid, int64_t *addresses,
+                                   int32_t *oob_dev, void *stream)
+{
+    if (!xyz || !grid || !addresses) return fail(NBR_ERR_INVALID, "nbr_voxel_addresses: null argument");
+    if (n <= 0) return NBR_OK;
+    GridDev g;
+    NBR_TRY(grid_to_dev(grid, &g));
+    if (oob_dev) NBR_CUDA(cudaMemsetAsync(oob_dev, 0, sizeof(int32_t), (cudaStream_t)stream));
+    address_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        xyz, dtype, n, g, grid->max_corner[0], grid->max_corner[1], grid->max_corner[2], addresses, oob_dev);
+    NBR_LAUNCHED();
+    return NBR_OK;
+}
+
+extern "C" int nbr_unique_u64(const uint64_t *sorted, int64_t n, uint64_t *out, int64_t *n_out_dev, void *stream)
+{
+    if (!sorted || !out || !n_out_dev) return fail(NBR_ERR_INVALID, "nbr_unique_u64: null argument");
+    return unique_sorted(sorted, n, out, n_out_dev, (cudaStream_t)stream);
+}
+
+extern "C" int nbr_voxel_centres(const int64_t *addresses, int64_t n, const nbr_grid *grid, double *xyz_out, void *stream)
+{
+    if (!addresses || !grid || !xyz_out) return fail(NBR_ERR_INVALID, "nbr_voxel_centres: null argument");
+    if (n <= 0) return NBR_OK;
+    GridDev g;
+    NBR_TRY(grid_to_dev(grid, &g));
+    centre_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(addresses, n, g, xyz_out);
+    NBR_LAUNCHED();
+    return NBR_OK;
+}
+
+extern "C" int nbr_lattice_create(nbr_lattice **out, const void *search_xyz, int dtype, int64_t n_search,
+                                  const nbr_grid *grid, int flags, void *stream)
+{
+    return lattice_create(reinterpret_cast<Lattice **>(out), search_xyz, dtype, n_search, grid, flags,
+                          (cudaStream_t)stream);
+}
+
+extern "C" void nbr_lattice_destroy(nbr_lattice *lattice) { delete reinterpret_cast<Lattice *>(lattice); }
+
+extern "C" int nbr_lattice_info(const nbr_lattice *lattice, int64_t *n_voxels, int64_t *n_bricks)
+{
+    if (!lattice) return fail(NBR_ERR_INVALID, "nbr_lattice_info: null lattice");
+    return lattice_counts(reinterpret_cast<const Lattice *>(lattice), n_voxels, n_bricks);
+}
+
+extern "C" int nbr_lattice_export(const nbr_lattice *lattice, int64_t *addresses, double *centres, void *stream)
+{
+    const Lattice *L = reinterpret_cast<const Lattice *>(lattice);
+    if (!L) return fail(NBR_ERR_INVALID, "nbr_lattice_export: null lattice");
+    if (!L->indexed) return fail(NBR_ERR_INVALID, "nbr_lattice_export: lattice was built without NBR_LATTICE_INDEXED");
+    int64_t nv = 0;
+    NBR_TRY(lattice_counts(L, &nv, nullptr));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (addresses) NBR_CUDA(cudaMemcpyAsync(addresses, L->ukeys, sizeof(int64_t) * nv, cudaMemcpyDeviceToDevice, s));
+    if (centres && nv) {
+        centre_kernel<<<(unsigned)ceil_div(nv, 256), 256, 0, s>>>(reinterpret_cast<const int64_t *>(L->ukeys), nv,
+                                                                L->gdev, centres);
+        NBR_LAUNCHED();
+    }
+    return NBR_OK;
+}

@@ -1,0 +1,279 @@
+"""
+multiscale operator processing pipeline -- B200 drop-in for `nimrud.minimal.multiscale`
+(reference: nimrud/minimal/multiscale.py).
+
+features are generated for points in the query cloud, using geometry from the search cloud.
+all undefined features are represented by zeros (reference: multiscale.py:4-5).
+
+`process_single_core` / `one_scale_single_core` keep the reference's names, argument order and
+output layout: (Nq, 4*S) float64, column 4*s+j = feature j of scale s, features
+[population, centroid distance, l_max/sum, l_mid/sum].
+
+numpy arrays in -> numpy array out (host buffers through nbr_multiscale_features_host);
+CUDA torch tensors in -> CUDA torch tensor out (nbr_multiscale_features on the current stream).
+There is no CPU implementation in this package.
+"""
+import ctypes
+import time
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._util import device_cloud, host_cloud, is_torch, ptr, require_cuda, stream_ptr, validate_cloud
+from .geometry import cloud_bbox, grid_from_bbox
+
+# the reference's tunables (multiscale.py:18-24).  results never depended on them; the CUDA path
+# has no leaf size and no query chunking, they are kept so that code that sets them still imports.
+LEAFSIZE = 300
+QUERY_CHUNK_SIZE = 1000
+VERBOSITY_INTERVAL = 100
+
+_TORCH_OUT = {np.float64: torch.float64, np.float32: torch.float32}
+
+
+def _out_code(out_dtype):
+    dt = np.dtype(out_dtype)
+    if dt == np.float64:
+        return np.float64, _lib.F64
+    if dt == np.float32:
+        return np.float32, _lib.F32
+    raise ValueError("out_dtype must be float32 or float64")
+
+
+def _ncol(descriptors):
+    if descriptors in ("reference", 0, None):
+        return 4, _lib.DESC_REFERENCE
+    if descriptors in ("extended", 1):
+        return 16, _lib.DESC_EXTENDED
+    raise ValueError("descriptors must be 'reference' or 'extended'")
+
+
+def _check_inputs(query_cloud, search_cloud):
+    # reference: VoxelFilter.__init__ on the search cloud (utils/geometry.py:30-35); scipy rejects
+    # a query cloud whose width differs from the tree's.
+    if search_cloud.ndim != 2:
+        raise ValueError("wrong point cloud array shape")
+    if search_cloud.shape[1] not in (2, 3):
+        raise ValueError("only 2D and 3D spaces supported")
+    if search_cloud.shape[0] < 2:
+        raise ValueError("need at least 2 points to define a voxel grid")
+    if search_cloud.shape[1] != 3:
+        raise ValueError("the eigenfeature path needs 3D clouds")
+    validate_cloud(query_cloud, "query_cloud")
+
+
+def process_single_core(query_cloud, search_cloud, edge_lengths, radii, verbose=False,
+                        out_dtype=np.float64, descriptors="reference", return_voxel_counts=False):
+    """
+    compute features at multiple scales. returns an array of feature vectors aligned with the query
+    cloud.  (reference: multiscale.py:27-67)
+
+    extras beyond the reference signature (keyword only in spirit, defaults = reference behaviour):
+      out_dtype            float64 (drop-in) or float32
+      descriptors          "reference" (4 columns per scale) or "extended" (16 columns per scale)
+      return_voxel_counts  also return the number of unique search voxels per scale
+    """
+    assert(len(edge_lengths) == len(radii)), \
+        "edge_lengths and radii should be equal-length sequences."
+    _check_inputs(query_cloud, search_cloud)
+    require_cuda()
+    np_out, out_code = _out_code(out_dtype)
+    ncol, mask = _ncol(descriptors)
+    n_scales = len(radii)
+    nq = int(query_cloud.shape[0])
+    ns = int(search_cloud.shape[0])
+    edges_arr, edges_p = _lib.f64_array(list(edge_lengths))
+    radii_arr, radii_p = _lib.f64_array(list(radii))
+    counts = np.zeros(max(n_scales, 1), dtype=np.int64)
+    counts_p = counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)) if (return_voxel_counts or verbose) else None
+    start = time.perf_counter()
+
+    if is_torch(query_cloud) and query_cloud.is_cuda:
+        q, qc = device_cloud(query_cloud)
+        if search_cloud is query_cloud:
+            s, sc = q, qc
+        else:
+            s, sc = device_cloud(search_cloud, q.device)
+        out = torch.zeros((nq, ncol * n_scales), dtype=_TORCH_OUT[np_out], device=q.device)
+        with torch.cuda.device(q.device):
+            _lib.check(_lib.lib().nbr_multiscale_features(
+                ptr(q), qc, nq, ptr(s), sc, ns, edges_p, radii_p, n_scales, ptr(out), out_code, mask, None,
+                counts_p, stream_ptr(q.device)))
+    else:
+        q, qc = host_cloud(query_cloud.cpu().numpy() if is_torch(query_cloud) else query_cloud)
+        if search_cloud is query_cloud:
+            s, sc = q, qc
+        else:
+            s, sc = host_cloud(search_cloud.cpu().numpy() if is_torch(search_cloud) else search_cloud)
+        out = np.zeros((nq, ncol * n_scales), dtype=np_out)
+        _lib.check(_lib.lib().nbr_multiscale_features_host(
+            ctypes.c_void_p(q.ctypes.data), qc, nq, ctypes.c_void_p(s.ctypes.data), sc, ns, edges_p, radii_p,
+            n_scales, ctypes.c_void_p(out.ctypes.data), out_code, mask, counts_p))
+        if is_torch(query_cloud):
+            out = torch.from_numpy(out)
+
+    if verbose:
+        if is_torch(out) and out.is_cuda:
+            torch.cuda.synchronize(out.device)
+        elapsed = time.perf_counter() - start
+        for e, r, c in zip(edges_arr, radii_arr, counts):
+            print("queried {} points against a search space of {} voxels".format(nq, int(c)))
+            print("using a voxel edge length of {} and radius of {}".format(e, r))
+        print("===============================")
+        print("calculating all scales took {}s".format(np.around(elapsed, 3)))
+        print("final rate of {} points per second".format(np.around(nq / max(elapsed, 1e-12), 3)))
+    if return_voxel_counts:
+        return out, counts[:n_scales].copy()
+    return out
+
+
+def one_scale_single_core(query_cloud, search_cloud, edge_length, radius, verbose=False, **kwargs):
+    """
+    generate a 4d feature vector representing one analysis scale.  (reference: multiscale.py:70-123)
+    """
+    return process_single_core(query_cloud, search_cloud, [edge_length], [radius], verbose=verbose, **kwargs)
+
+
+# --------------------------------------------------------------------------------------------------
+# the pieces, for callers that keep an index around (and for the parity tests)
+# --------------------------------------------------------------------------------------------------
+
+class LatticeIndex(object):
+    """
+    the voxel-filtered search cloud of one edge length on the GPU (what the reference builds at
+    multiscale.py:75-87: VoxelFilter.unique_voxels + cKDTree), as occupancy bit bricks.
+
+    indexed=True additionally keeps the sorted unique addresses so neighbor INDICES (positions in
+    np.unique order, as cKDTree reports them) can be returned.
+    """
+
+    def __init__(self, search_cloud, edge_length, indexed=False, bbox=None):
+        if search_cloud.ndim != 2:
+            raise ValueError("wrong point cloud array shape")
+        if search_cloud.shape[1] != 3:
+            raise ValueError("only 3D search clouds can be indexed")
+        if search_cloud.shape[0] < 2:
+            raise ValueError("need at least 2 points to define a voxel grid")
+        require_cuda()
+        self._search, self._code = device_cloud(search_cloud)
+        self.device = self._search.device
+        self.edge_length = edge_length
+        lo, hi = bbox if bbox is not None else cloud_bbox(self._search, self._code)
+        self.grid = grid_from_bbox(lo, hi, edge_length, 3)
+        self.indexed = bool(indexed)
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().nbr_lattice_create(
+                ctypes.byref(handle), ptr(self._search), self._code, self._search.shape[0], ctypes.byref(self.grid),
+                _lib.LATTICE_INDEXED if indexed else 0, stream_ptr(self.device)))
+        self._handle = handle
+        self._counts = None
+
+    def close(self):
+        if getattr(self, "_handle", None):
+            _lib.lib().nbr_lattice_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _info(self):
+        if self._counts is None:
+            nv, nb = ctypes.c_int64(), ctypes.c_int64()
+            _lib.check(_lib.lib().nbr_lattice_info(self._handle, ctypes.byref(nv), ctypes.byref(nb)))
+            self._counts = (nv.value, nb.value)
+        return self._counts
+
+    @property
+    def n_voxels(self):
+        return self._info()[0]
+
+    @property
+    def n_bricks(self):
+        return self._info()[1]
+
+    def addresses_and_centres(self):
+        """(sorted unique addresses int64 (Nv,), centres float64 (Nv,3)) as CUDA tensors."""
+        nv = self.n_voxels
+        addr = torch.empty(nv, dtype=torch.int64, device=self.device)
+        cen = torch.empty((nv, 3), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().nbr_lattice_export(self._handle, ptr(addr), ptr(cen), stream_ptr(self.device)))
+        return addr, cen
+
+    def radius_features(self, query_cloud, radii, out_dtype=np.float64, descriptors="reference", algorithm=0):
+        """(Nq, C*len(radii)) features for several radii sharing this lattice's edge; CUDA tensor."""
+        validate_cloud(query_cloud, "query_cloud")
+        np_out, out_code = _out_code(out_dtype)
+        ncol, mask = _ncol(descriptors)
+        q, qc = device_cloud(query_cloud, self.device)
+        radii_arr, radii_p = _lib.f64_array(list(radii))
+        out = torch.zeros((q.shape[0], ncol * len(radii_arr)), dtype=_TORCH_OUT[np_out], device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().nbr_radius_features(
+                self._handle, ptr(q), qc, q.shape[0], radii_p, len(radii_arr), ptr(out), out_code, out.shape[1], 0,
+                mask, int(algorithm), stream_ptr(self.device)))
+        return out
+
+    def radius_sets(self, query_cloud, radius):
+        """CSR neighbor index sets (offsets int64 (Nq+1,), indices int32) -- what query_ball_tree returns."""
+        validate_cloud(query_cloud, "query_cloud")
+        q, qc = device_cloud(query_cloud, self.device)
+        nq = q.shape[0]
+        offsets = torch.zeros(nq + 1, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            s = stream_ptr(self.device)
+            _lib.check(_lib.lib().nbr_radius_sets(self._handle, ptr(q), qc, nq, float(radius), ptr(offsets), None, s))
+            total = int(offsets[-1].item())
+            indices = torch.empty(max(total, 1), dtype=torch.int32, device=self.device)
+            _lib.check(_lib.lib().nbr_radius_sets(self._handle, ptr(q), qc, nq, float(radius), ptr(offsets),
+                                                  ptr(indices), s))
+        return offsets, indices[:total]
+
+    def knn(self, query_cloud, k, ks=None, out_dtype=np.float64, descriptors="reference"):
+        """
+        k nearest voxels per query in (squared distance, index) order.
+        returns (indices int32 (Nq,k), d2 float64 (Nq,k)[, features (Nq, C*len(ks))]).
+        """
+        validate_cloud(query_cloud, "query_cloud")
+        q, qc = device_cloud(query_cloud, self.device)
+        nq = q.shape[0]
+        idx = torch.empty((nq, k), dtype=torch.int32, device=self.device)
+        d2 = torch.empty((nq, k), dtype=torch.float64, device=self.device)
+        feats = None
+        np_out, out_code = _out_code(out_dtype)
+        ncol, mask = _ncol(descriptors)
+        ks_arr = None
+        if ks is not None:
+            ks_arr = np.ascontiguousarray(ks, dtype=np.int32)
+            if np.any(np.diff(ks_arr) <= 0) or ks_arr[-1] != k:
+                raise ValueError("ks must be ascending and end at k")
+            feats = torch.zeros((nq, ncol * len(ks_arr)), dtype=_TORCH_OUT[np_out], device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().nbr_knn(
+                self._handle, ptr(q), qc, nq, int(k), ptr(idx), ptr(d2),
+                ks_arr.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)) if ks_arr is not None else None,
+                len(ks_arr) if ks_arr is not None else 0, ptr(feats), out_code,
+                feats.shape[1] if feats is not None else 0, 0, mask, stream_ptr(self.device)))
+        return (idx, d2) if feats is None else (idx, d2, feats)
+
+
+def knn_features(query_cloud, search_cloud, edge_length, ks, out_dtype=np.float64, descriptors="reference"):
+    """
+    multiscale kNN features (extension; BASELINE config 3): the search cloud is voxel-filtered at
+    edge_length, and for each k in ks the reference's 4 columns are computed over the k nearest
+    voxels, ties broken by (distance, index).  (Nq, C*len(ks)); numpy in -> numpy out.
+    """
+    ks = sorted(int(k) for k in ks)
+    index = LatticeIndex(search_cloud, edge_length, indexed=True)
+    try:
+        _, _, feats = index.knn(query_cloud, ks[-1], ks=ks, out_dtype=out_dtype, descriptors=descriptors)
+    finally:
+        index.close()
+    if is_torch(query_cloud):
+        return feats if query_cloud.is_cuda else feats.cpu()
+    return feats.cpu().numpy()

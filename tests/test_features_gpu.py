@@ -1,0 +1,179 @@
+"""
+GPU parity of the fused radius-feature path against golden vectors produced by the reference, the
+oracle on seeded clouds, and size-independent properties.  all calls go through the C ABI.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_features_close, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["small", "urban", "degenerate"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_process_single_core_matches_reference(name, dtype):
+    from nimrud_b200 import multiscale
+    g = load_golden(name)
+    q, s = g["query"].astype(dtype), g["search"].astype(dtype)
+    out = multiscale.process_single_core(q, s, tuple(g["edges"]), tuple(g["radii"]))
+    assert isinstance(out, np.ndarray) and out.dtype == np.float64
+    assert out.shape == g["features"].shape
+    assert_features_close(out, g["features"], g["radii"])
+    # float32 output option
+    out32 = multiscale.process_single_core(q, s, tuple(g["edges"]), tuple(g["radii"]), out_dtype=np.float32)
+    assert out32.dtype == np.float32
+    assert np.array_equal(out32[:, 0::4], g["features"][:, 0::4])
+    assert np.allclose(out32, g["features"], rtol=1e-4, atol=1e-5)
+
+
+def test_one_scale_and_device_tensors():
+    from nimrud_b200 import multiscale
+    g = load_golden("small")
+    q = torch.from_numpy(g["query"]).cuda()
+    out = multiscale.one_scale_single_core(q, q, float(g["edges"][1]), float(g["radii"][1]))
+    assert out.is_cuda and out.shape == (len(g["query"]), 4) and out.dtype == torch.float64
+    assert_features_close(out.cpu().numpy(), g["features"][:, 4:8], g["radii"][1:2])
+
+
+def test_config1_subset_matches_reference():
+    from nimrud_b200 import multiscale, synth
+    g = load_golden("config1")
+    cloud = synth.uniform_box()
+    out, counts = multiscale.process_single_core(cloud[g["pick"]], cloud, tuple(g["edges"]), tuple(g["radii"]),
+                                                 return_voxel_counts=True)
+    assert np.array_equal(counts, g["n_voxels"])        # 94187 / 65061 / 15449
+    assert_features_close(out, g["features"], g["radii"])
+
+
+@pytest.mark.parametrize("name", ["small", "urban", "degenerate"])
+def test_radius_sets_bit_exact(name):
+    from nimrud_b200 import multiscale
+    g = load_golden(name)
+    q, s = g["query"], g["search"]
+    for i, (e, r) in enumerate(zip(g["edges"], g["radii"])):
+        index = multiscale.LatticeIndex(s, float(e), indexed=True)
+        assert index.n_voxels == len(g["s%d_addresses" % i])
+        addr, centres = index.addresses_and_centres()
+        assert np.array_equal(addr.cpu().numpy(), g["s%d_addresses" % i])
+        assert np.array_equal(centres.cpu().numpy(), g["s%d_centres" % i])
+        off, idx = index.radius_sets(q, float(r))
+        assert np.array_equal(off.cpu().numpy(), g["s%d_offsets" % i])
+        assert np.array_equal(idx.cpu().numpy(), g["s%d_indices" % i])
+        index.close()
+
+
+def test_exact_and_row_kernels_agree_with_each_other_and_the_oracle(c_oracle):
+    from nimrud_b200 import multiscale, synth
+    cloud = synth.urban_scene(300_000, seed=3).numpy()
+    q = cloud[::7]
+    for e, radii in ((0.2, (0.4, 0.6, 0.8, 1.0, 1.2)), (0.4, (1.2,)), (1.6, (4.8,))):
+        index = multiscale.LatticeIndex(cloud, e)
+        a = index.radius_features(q, radii, algorithm=1).cpu().numpy()
+        b = index.radius_features(q, radii, algorithm=0).cpu().numpy()
+        ref = c_oracle.process(q, cloud, [e] * len(radii), radii, threads=8)
+        assert_features_close(a, ref, radii)
+        assert_features_close(b, ref, radii)
+        index.close()
+
+
+def test_boundary_inclusive_and_lattice_aligned_queries(c_oracle):
+    # queries sitting exactly on voxel centres with r an exact multiple of e: distance == r ties
+    from nimrud_b200 import multiscale
+    rs = np.random.RandomState(0)
+    cells = rs.randint(0, 12, size=(4000, 3))
+    search = (cells * 0.5 + 0.25).astype(np.float32)
+    q = search[:500].copy()
+    for r in (0.5, 1.0, 1.5):
+        ref = c_oracle.process(q, search, [0.5], [r])
+        out = multiscale.process_single_core(q, search, [0.5], [r])
+        assert_features_close(out, ref, [r])
+
+
+def test_error_behaviour_matches_reference():
+    from nimrud_b200 import multiscale
+    pts = np.random.RandomState(0).rand(50, 3)
+    with pytest.raises(AssertionError):
+        multiscale.process_single_core(pts, pts, [0.1, 0.2], [0.5])
+    with pytest.raises(ValueError):
+        multiscale.process_single_core(pts, pts[:1], [0.1], [0.5])
+    with pytest.raises(ValueError):                      # > 64 address bits (utils/geometry.py:59-60)
+        multiscale.process_single_core(pts * 1e6, pts * 1e6, [1e-9], [0.5])
+    out = multiscale.process_single_core(pts[:0], pts, [0.1], [0.5])
+    assert out.shape == (0, 4)
+
+
+def test_query_sharding_invariance():
+    from nimrud_b200 import multiscale, synth
+    cloud = synth.urban_scene(200_000, seed=5).numpy()
+    e, r = (0.2, 0.8), (0.6, 2.4)
+    whole = multiscale.process_single_core(cloud, cloud, e, r)
+    parts = np.concatenate([multiscale.process_single_core(cloud[a:a + 50_000], cloud, e, r)
+                            for a in range(0, 200_000, 50_000)])
+    assert np.array_equal(whole, parts)
+
+
+def test_full_size_properties_10m():
+    # BASELINE config 2 at full size: size-independent properties instead of the oracle
+    from nimrud_b200 import multiscale, synth
+    cloud = synth.urban_scene(10_000_000, seed=20, device="cuda")
+    edges = (0.1, 0.2, 0.4, 0.8, 1.6)
+    radii = (0.3, 0.6, 1.2, 2.4, 4.8)
+    out = multiscale.process_single_core(cloud, cloud, edges, radii, out_dtype=np.float32)
+    assert out.shape == (10_000_000, 20)
+    assert torch.isfinite(out).all()
+    pop = out[:, 0::4]
+    assert (pop >= 1).all()                       # query == search: own voxel is always a neighbor
+    assert (pop == pop.round()).all()
+    l1, l2 = out[:, 2::4], out[:, 3::4]
+    assert (l1 >= l2 - 1e-6).all() and (l2 >= -1e-6).all() and (l1 + l2 <= 1 + 1e-5).all()
+    assert (l1 >= 1.0 / 3 - 1e-5).logical_or(pop < 2).all()
+    cen = out[:, 1::4]
+    assert (cen <= torch.tensor(radii, device="cuda") * (1 + 1e-5)).all()
+    # a random 20k subset against the same call on the subset (sharding invariance at full size)
+    pick = torch.randperm(10_000_000, device="cuda")[:20_000]
+    sub = multiscale.process_single_core(cloud[pick].contiguous(), cloud, edges, radii, out_dtype=np.float32)
+    assert torch.equal(sub, out[pick])
+
+
+def test_subset_of_10m_against_oracle(c_oracle):
+    from nimrud_b200 import multiscale, synth
+    cloud = synth.urban_scene(2_000_000, seed=20, device="cuda")
+    edges = (0.1, 0.2, 0.4, 0.8, 1.6)
+    radii = (0.3, 0.6, 1.2, 2.4, 4.8)
+    pick = torch.randperm(2_000_000, device="cuda")[:30_000]
+    out = multiscale.process_single_core(cloud[pick].contiguous(), cloud, edges, radii).cpu().numpy()
+    host = cloud.cpu().numpy()
+    ref = c_oracle.process(host[pick.cpu().numpy()], host, edges, radii, threads=8)
+    assert_features_close(out, ref, radii)
+
+
+def test_extended_descriptors_against_oracle():
+    from nimrud_b200 import multiscale
+    from oracle import nimrud_oracle as O
+    g = load_golden("small")
+    q = g["query"][:300]
+    s = g["search"]
+    e, r = float(g["edges"][1]), float(g["radii"][1])
+    out = multiscale.process_single_core(q, s, [e], [r], descriptors="extended")
+    assert out.shape == (300, 16)
+    assert_features_close(out[:, :4], g["features"][:300, 4:8], [r])
+    p = O.grid_params(s.astype(np.float64), e)
+    _, centres = O.unique_voxels(p, s.astype(np.float64))
+    off, idx = O.radius_sets(q.astype(np.float64), centres, r)
+    ext = O.rows_from_sets(q.astype(np.float64), centres, off, idx, row_fn=O.extended_row)
+    assert np.allclose(out[:, 4:12], ext[:, :8], rtol=1e-4, atol=1e-7)
+    assert np.allclose(out[:, 15], ext[:, 11], rtol=1e-6)
+    # normals: compare where the smallest eigenvalue is well separated
+    sep = (ext[:, 1] > 0.05)            # planarity = (e2-e3)/e1
+    dots = np.abs((out[sep, 12:15] * ext[sep, 8:11]).sum(1))
+    assert (dots > 1 - 1e-6).all()
+
+
+def test_launch_counter_moves():
+    from nimrud_b200 import _lib, multiscale
+    before = _lib.lib().nbr_kernel_launches()
+    pts = np.random.RandomState(0).rand(1000, 3).astype(np.float32)
+    multiscale.process_single_core(pts, pts, [0.1], [0.3])
+    assert _lib.lib().nbr_kernel_launches() > before
