@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""
+bench.py -- points*scales/sec of the multiscale eigenfeature path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--points P]
+
+One "step" = one pass of the whole hot path over the workload: bounding box, one lattice index per
+scale, fused radius query + covariance + eigensolve + feature emission for every query at every scale.
+Workload at N=1 = BASELINE.json configs[1]: 10M-point synthetic urban scene, 5 radius scales
+(edge 0.1..1.6, r = 3e), query cloud == search cloud.  N>1: one such tile per GPU (weak scaling),
+tiles side by side, lattices anchored on the all-reduced bounding box, halo exchange over NCCL.
+
+value      whole-job points*scales/s with the cloud resident in HBM (CUDA events, max over ranks)
+e2e        same through the reference-facing call with HOST buffers (pinned), H2D + D2H inside
+roofline   the dominant kernel (fused feature kernel) against the measured HBM peak
+cpu_baseline / --impl reference: the CPU port of the reference (oracle/nimrud_oracle.py, the same
+           per-neighborhood numpy calls the reference makes) on the box's host cores, bounded sample
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+EDGES = (0.1, 0.2, 0.4, 0.8, 1.6)
+RADII = (0.3, 0.6, 1.2, 2.4, 4.8)
+METRIC = "points_scales_per_sec"
+UNIT = "points*scales/s"
+FALLBACK_HBM_GBS = 6650.0
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md "clocks DURING the timed region")
+# --------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            parts = [p.strip() for p in row.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline
+# --------------------------------------------------------------------------------------------------
+def cpu_sample_cloud(points_target):
+    """a spatially contiguous tile of the config-2 scene plus its halo, generated on the CPU."""
+    import torch
+    from nimrud_b200 import synth
+    # a 2M-point scene at the config's density (about 224 m x 224 m) is enough to cut tiles from
+    scene = synth.urban_scene(2_000_000, seed=20, device="cpu").numpy()
+    halo = max(RADII) + max(EDGES) / 2
+    side = math.sqrt(points_target / 40.0)
+    lo = np.array([60.0, 60.0])
+    inside = np.all((scene[:, :2] >= lo) & (scene[:, :2] < lo + side), axis=1)
+    near = np.all((scene[:, :2] >= lo - halo) & (scene[:, :2] < lo + side + halo), axis=1)
+    return scene[inside].astype(np.float64), scene[near].astype(np.float64)
+
+
+def run_cpu_reference(steps, warmup, workers):
+    from oracle import nimrud_oracle as O
+    per_worker = 6000                                   # queries per worker per step (~10 s of CPU work)
+    query, search = cpu_sample_cloud(per_worker * workers)
+    query = query[:per_worker * workers]
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = O.process_parallel(query, search, EDGES, RADII, workers)
+        dt = time.perf_counter() - t0
+        assert out.shape == (len(query), 4 * len(RADII))
+        if it >= warmup:
+            times.append(dt)
+    total = sum(times)
+    value = len(query) * len(RADII) * len(times) / total
+    sample = "%d contiguous queries (tile of the 10M-scene generator) x %d scales against tile+halo (%d points), " \
+             "%d processes" % (len(query), len(RADII), len(search), workers)
+    return value, 1e3 * total / len(times), sample
+
+
+def reference_arm(args, rank):
+    if rank != 0:
+        return
+    workers = max(1, min(os.cpu_count() or 1, 64))
+    steps = max(1, min(args.steps, 3))
+    value, ms, sample = run_cpu_reference(steps, min(args.warmup, 1), workers)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.points, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(points, gpus):
+    return {"workload": "BASELINE configs[1]: %dM-point synthetic urban scene per GPU, 5 radius scales "
+                        "(edge 0.1/0.2/0.4/0.8/1.6 m, radius 3*edge), query == search" % (points // 1_000_000),
+            "points_per_gpu": points, "scales": len(RADII), "edges": list(EDGES), "radii": list(RADII),
+            "l2_policy": "inputs+outputs per step (920 MB) exceed the 126 MB L2; no explicit flush",
+            "parallelism": "spatial tiles, 1 per GPU" if gpus > 1 else "single GPU"}
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def gpu_arm(args, rank, world, local_rank):
+    import ctypes
+    import torch
+    from nimrud_b200 import _lib, multiscale, synth
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    lib = _lib.lib()
+    n = args.points
+    ns = len(RADII)
+    if world > 1:
+        from nimrud_b200 import distributed as nd
+        extent = math.sqrt(n / 40.0)
+        cols = 2 if world >= 2 else 1
+        origin = ((rank % cols) * extent, (rank // cols) * extent)
+        cloud = synth.urban_scene(n, seed=20 + rank, device=dev, origin=origin)
+    else:
+        cloud = synth.urban_scene(n, seed=20, device=dev)
+    out = torch.empty((n, 4 * ns), dtype=torch.float32, device=dev)
+    counts = np.zeros(ns, dtype=np.int64)
+
+    edges_arr, edges_p = _lib.f64_array(EDGES)
+    radii_arr, radii_p = _lib.f64_array(RADII)
+
+    def step(want_counts=False):
+        if world > 1:
+            return nd.process_tile(cloud, EDGES, RADII, out=out, gather=False)
+        cp = counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)) if want_counts else None
+        _lib.check(lib.nbr_multiscale_features(
+            ctypes.c_void_p(cloud.data_ptr()), _lib.F32, n, ctypes.c_void_p(cloud.data_ptr()), _lib.F32, n,
+            edges_p, radii_p, ns, ctypes.c_void_p(out.data_ptr()), _lib.F32, 0, None, cp,
+            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    step(want_counts=(world == 1))                       # voxel counts for the roofline's rho_s
+    torch.cuda.synchronize()
+
+    # ---- timed region: device-resident inputs
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    lib.nbr_timing_enable(1)
+    phases = (ctypes.c_double * 4)()
+    lib.nbr_timing_read(phases)                          # clear
+    launches0 = lib.nbr_kernel_launches()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = lib.nbr_kernel_launches() - launches0
+    lib.nbr_timing_read(phases)
+    lib.nbr_timing_enable(0)
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = world * n * ns / (ms_per_step * 1e-3)
+
+    # ---- e2e: host buffers (pinned), reference-facing host entry point, float64 output (drop-in)
+    e2e = None
+    if not args.no_e2e:
+        host_in = cloud.cpu().pin_memory()
+        e2e_steps = max(1, min(args.steps, 3))
+        results = {}
+        for label, tdt, code in (("f64", torch.float64, _lib.F64), ("f32", torch.float32, _lib.F32)):
+            host_out = torch.empty((n, 4 * ns), dtype=tdt).pin_memory()
+            def host_step():
+                _lib.check(lib.nbr_multiscale_features_host(
+                    ctypes.c_void_p(host_in.data_ptr()), _lib.F32, n, ctypes.c_void_p(host_in.data_ptr()), _lib.F32, n,
+                    edges_p, radii_p, ns, ctypes.c_void_p(host_out.data_ptr()), code, 0, None))
+            host_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                host_step()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if dist is not None:
+                t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            results[label] = (world * n * ns * e2e_steps / dt, host_out.numel() * host_out.element_size())
+            if label == "f64":
+                check = host_out[:4096].to(torch.float32)
+                assert torch.equal(check[:, 0::4], out[:4096, 0::4].cpu()), "e2e and device-resident results differ"
+            del host_out
+        e2e = {"value": results["f64"][0], "unit": UNIT, "h2d_bytes_per_step": int(host_in.numel() * 4),
+               "d2h_bytes_per_step": int(results["f64"][1]), "out_dtype": "float64 (drop-in default)",
+               "value_float32_out": results["f32"][0], "d2h_bytes_per_step_float32_out": int(results["f32"][1]),
+               "steps": e2e_steps, "timer": "host wall clock around the synchronous host-buffer call"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (fused feature kernels, all scales of one step)
+    peak, peak_src = hbm_peak()
+    feat_ms = phases[3] / args.steps
+    if world == 1:
+        rho = counts / float(n)
+    else:
+        rho = np.zeros(ns)
+    algo_bytes = float(sum(n * (28.0 + 12.0 * r) for r in rho)) if world == 1 else float(n * ns * 28.0)
+    achieved = algo_bytes / (feat_ms * 1e-3) / 1e9 if feat_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "fused radius query + covariance + eigen + features (all scales of a step)",
+                "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "algorithmic_bytes_per_step": algo_bytes, "kernel_ms_per_step": feat_ms,
+                "bytes_per_point_scale": "28 + 12*rho_s (SURVEY.md 8d); rho_s = unique voxels / queries = %s"
+                                         % [round(float(r), 4) for r in rho],
+                "phase_ms_per_step": {"bbox": phases[0] / args.steps, "index": phases[1] / args.steps,
+                                      "order": phases[2] / args.steps, "features": feat_ms}}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu:
+        workers = max(1, min(os.cpu_count() or 1, 64))
+        v, ms, sample = run_cpu_reference(1, 0, workers)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample,
+                        "ms": ms}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32 moments + f64 membership/eigen, f32 out", "data": "synthetic",
+        "config": workload_config(n, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "voxels_per_scale": [int(c) for c in counts] if world == 1 else None,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--points", type=int, default=10_000_000)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+    gpu_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -168,6 +168,14 @@ int nbr_multiscale_features_host(const void *query_host, int q_dtype, int64_t n_
 /* counters for tests and benches: number of kernels this library has launched in this process. */
 int64_t nbr_kernel_launches(void);
 
+/* optional device timing of the whole-path drivers, CUDA events on the launching stream.
+ * nbr_timing_read synchronises on the recorded events, writes the accumulated milliseconds of the
+ * NBR_TIMING_PHASES phases [bounding box, index build, query ordering, feature kernels] since the
+ * previous read, and clears them. */
+#define NBR_TIMING_PHASES 4
+void nbr_timing_enable(int on);
+int nbr_timing_read(double *ms_out);
+
 #ifdef __cplusplus
 }
 #endif

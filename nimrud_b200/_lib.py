@@ -30,6 +30,8 @@ SIGNATURES = {
     "nbr_last_error": (ctypes.c_char_p, []),
     "nbr_version": (ctypes.c_int, []),
     "nbr_kernel_launches": (c_i64, []),
+    "nbr_timing_enable": (None, [ctypes.c_int]),
+    "nbr_timing_read": (ctypes.c_int, [ctypes.POINTER(c_f64)]),
     "nbr_bbox": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, ctypes.c_int, c_vp, c_vp]),
     "nbr_grid_from_bbox": (ctypes.c_int, [ctypes.POINTER(c_f64), ctypes.POINTER(c_f64), c_f64, ctypes.c_int,
                                           ctypes.POINTER(Grid)]),

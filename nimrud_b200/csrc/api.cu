@@ -1,6 +1,7 @@
 // api.cu -- C ABI glue: errors, scratch memory, the radius-feature dispatcher and the whole-path
 // drivers that stand in for process_single_core (nimrud/minimal/multiscale.py:27-67).
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -56,6 +57,29 @@ int device_sm_count()
     return sms;
 }
 
+// ---------------------------------------------------------------------------------------------
+// phase timing
+// ---------------------------------------------------------------------------------------------
+static std::atomic<int> g_timing{0};
+static std::mutex g_timing_mutex;
+struct TimedSpan { int phase; cudaEvent_t start, stop; };
+static std::vector<TimedSpan> g_spans;
+
+PhaseTimer::PhaseTimer(int phase_, cudaStream_t stream_) : phase(phase_), stream(stream_)
+{
+    if (!g_timing.load(std::memory_order_relaxed)) return;
+    if (cudaEventCreate(&start) != cudaSuccess || cudaEventCreate(&stop) != cudaSuccess) { start = stop = nullptr; return; }
+    cudaEventRecord(start, stream);
+}
+
+PhaseTimer::~PhaseTimer()
+{
+    if (!start) return;
+    cudaEventRecord(stop, stream);
+    std::lock_guard<std::mutex> lock(g_timing_mutex);
+    g_spans.push_back({phase, start, stop});
+}
+
 int radius_features_exact(const Lattice *lat, const void *query, int dtype, int64_t nq, const double *radii, int nr,
                           void *out, int out_dtype, int64_t row_stride, int col_offset, int descriptor_mask,
                           cudaStream_t stream);
@@ -109,7 +133,10 @@ int multiscale_features(const void *query, int q_dtype, int64_t nq, const void *
     } else {
         Scratch box;
         NBR_TRY(box.alloc(sizeof(double) * 6, stream));
-        NBR_TRY(bbox(search, s_dtype, ns, 3, box.as<double>(), stream));
+        {
+            PhaseTimer t(PHASE_BBOX, stream);
+            NBR_TRY(bbox(search, s_dtype, ns, 3, box.as<double>(), stream));
+        }
         NBR_CUDA(cudaMemcpyAsync(lohi, box.ptr, sizeof(lohi), cudaMemcpyDeviceToHost, stream));
         NBR_CUDA(cudaStreamSynchronize(stream));
     }
@@ -126,7 +153,10 @@ int multiscale_features(const void *query, int q_dtype, int64_t nq, const void *
         rc = grid_from_bbox(lohi, lohi + 3, edges[s], 3, &grid);
         if (rc) break;
         Lattice *lat = nullptr;
-        rc = lattice_create(&lat, search, s_dtype, ns, &grid, 0, stream);
+        {
+            PhaseTimer t(PHASE_INDEX, stream);
+            rc = lattice_create(&lat, search, s_dtype, ns, &grid, 0, stream);
+        }
         if (rc) break;
         lattices.push_back(lat);
         // scales sharing this edge form runs of consecutive columns where possible
@@ -141,8 +171,11 @@ int multiscale_features(const void *query, int q_dtype, int64_t nq, const void *
                 voxel_of_scale.push_back({lat, u});
                 ++u;
             }
-            rc = radius_features(lat, query, q_dtype, nq, group.data(), (int)group.size(), out, out_dtype, row_stride,
-                                 t * ncol, descriptor_mask, 0, stream);
+            {
+                PhaseTimer tm(PHASE_FEATURES, stream);
+                rc = radius_features(lat, query, q_dtype, nq, group.data(), (int)group.size(), out, out_dtype,
+                                     row_stride, t * ncol, descriptor_mask, 0, stream);
+            }
             t = u;
         }
     }
@@ -165,6 +198,24 @@ using namespace nbr;
 extern "C" const char *nbr_last_error(void) { return g_error.c_str(); }
 extern "C" int nbr_version(void) { return 100; }
 extern "C" int64_t nbr_kernel_launches(void) { return g_launches.load(); }
+
+extern "C" void nbr_timing_enable(int on) { g_timing.store(on ? 1 : 0); }
+
+extern "C" int nbr_timing_read(double *ms_out)
+{
+    if (!ms_out) return fail(NBR_ERR_INVALID, "nbr_timing_read: null argument");
+    for (int i = 0; i < PHASE_COUNT; ++i) ms_out[i] = 0.0;
+    std::lock_guard<std::mutex> lock(g_timing_mutex);
+    for (auto &sp : g_spans) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(sp.stop) == cudaSuccess && cudaEventElapsedTime(&ms, sp.start, sp.stop) == cudaSuccess)
+            ms_out[sp.phase] += ms;
+        cudaEventDestroy(sp.start);
+        cudaEventDestroy(sp.stop);
+    }
+    g_spans.clear();
+    return NBR_OK;
+}
 
 extern "C" int nbr_radius_features(const nbr_lattice *lattice, const void *query_xyz, int dtype, int64_t n_query,
                                    const double *radii_host, int32_t n_radii, void *out, int out_dtype,

@@ -57,6 +57,16 @@ struct Scratch {
 
 int device_sm_count();
 
+// optional per-phase device timing (CUDA events on the launching stream); see nbr_timing_*
+enum Phase { PHASE_BBOX = 0, PHASE_INDEX = 1, PHASE_ORDER = 2, PHASE_FEATURES = 3, PHASE_COUNT = 4 };
+struct PhaseTimer {
+    int phase;
+    cudaStream_t stream;
+    cudaEvent_t start = nullptr, stop = nullptr;
+    PhaseTimer(int phase, cudaStream_t stream);
+    ~PhaseTimer();
+};
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ------------------------------------------------------------------------------------------------

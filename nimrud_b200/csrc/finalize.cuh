@@ -21,47 +21,105 @@ struct Moments {
 };
 
 #ifdef __CUDACC__
-// eigenvalues of a symmetric 3x3 with unit trace, descending.  trigonometric closed form in float64.
-__device__ __forceinline__ void eig3_unit_trace(const double a[6], double l[3])
+// eigenvalues (descending) of a symmetric positive semi-definite 3x3 with unit trace, and the unit
+// eigenvector of the smallest one.
+//
+// the trigonometric closed form alone loses half the digits on a (near-)double eigenvalue
+// (acos near +-1), which is the normal case here: lines give l2 = l3 = 0, flat patches l1 = l2.
+// so it is only used to pick the ISOLATED eigenvalue (largest if the half-determinant r >= 0,
+// smallest otherwise), which it gets to full precision; that eigenpair is deflated and the other two
+// come from the 2x2 block in the orthogonal complement through the cancellation-free
+// m +- hypot(.,.) form.  absolute error ~1e-16 on every eigenvalue, clusters included.
+__device__ __forceinline__ void sym_mul(const double a[6], const double x[3], double y[3])
+{
+    y[0] = a[0] * x[0] + a[1] * x[1] + a[2] * x[2];
+    y[1] = a[1] * x[0] + a[3] * x[1] + a[4] * x[2];
+    y[2] = a[2] * x[0] + a[4] * x[1] + a[5] * x[2];
+}
+
+__device__ __forceinline__ void eig3_unit_trace(const double a[6], double l[3], double normal[3])
 {
     const double q = 1.0 / 3.0;
+    normal[0] = 0.0; normal[1] = 0.0; normal[2] = 1.0;
     const double p1 = a[1] * a[1] + a[2] * a[2] + a[4] * a[4];
     const double d0 = a[0] - q, d1 = a[3] - q, d2 = a[5] - q;
     const double p2 = d0 * d0 + d1 * d1 + d2 * d2 + 2.0 * p1;
-    if (!(p2 > 1e-30)) { l[0] = l[1] = l[2] = q; return; }
+    if (!(p2 > 1e-28)) { l[0] = l[1] = l[2] = q; return; }
     const double p = sqrt(p2 / 6.0);
     const double ip = 1.0 / p;
     const double b0 = d0 * ip, b1 = a[1] * ip, b2 = a[2] * ip, b3 = d1 * ip, b4 = a[4] * ip, b5 = d2 * ip;
     double r = 0.5 * (b0 * (b3 * b5 - b4 * b4) - b1 * (b1 * b5 - b4 * b2) + b2 * (b1 * b4 - b3 * b2));
     r = fmin(1.0, fmax(-1.0, r));
     const double phi = acos(r) * (1.0 / 3.0);
-    const double e0 = q + 2.0 * p * cos(phi);
-    const double e2 = q + 2.0 * p * cos(phi + 2.0943951023931954923);
-    l[0] = e0;
-    l[2] = e2;
-    l[1] = 1.0 - e0 - e2;
-}
+    const bool top = r >= 0.0;          // true: the largest eigenvalue is the isolated one
+    double lam = top ? q + 2.0 * p * cos(phi) : q + 2.0 * p * cos(phi + 2.0943951023931954923);
 
-// unit eigenvector of the symmetric matrix `a` for eigenvalue lam (best conditioned cross product)
-__device__ __forceinline__ void eigvec3(const double a[6], double lam, double v[3])
-{
+    // eigenvector of the isolated eigenvalue: best-conditioned cross product of rows of (A - lam I)
     const double r0[3] = {a[0] - lam, a[1], a[2]};
     const double r1[3] = {a[1], a[3] - lam, a[4]};
     const double r2[3] = {a[2], a[4], a[5] - lam};
-    double c[3][3] = {
-        {r0[1] * r1[2] - r0[2] * r1[1], r0[2] * r1[0] - r0[0] * r1[2], r0[0] * r1[1] - r0[1] * r1[0]},
-        {r0[1] * r2[2] - r0[2] * r2[1], r0[2] * r2[0] - r0[0] * r2[2], r0[0] * r2[1] - r0[1] * r2[0]},
-        {r1[1] * r2[2] - r1[2] * r2[1], r1[2] * r2[0] - r1[0] * r2[2], r1[0] * r2[1] - r1[1] * r2[0]}};
-    int best = 0;
-    double bn = -1.0;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        double n2 = c[i][0] * c[i][0] + c[i][1] * c[i][1] + c[i][2] * c[i][2];
-        if (n2 > bn) { bn = n2; best = i; }
+    double c0[3] = {r0[1] * r1[2] - r0[2] * r1[1], r0[2] * r1[0] - r0[0] * r1[2], r0[0] * r1[1] - r0[1] * r1[0]};
+    double c1[3] = {r0[1] * r2[2] - r0[2] * r2[1], r0[2] * r2[0] - r0[0] * r2[2], r0[0] * r2[1] - r0[1] * r2[0]};
+    double c2[3] = {r1[1] * r2[2] - r1[2] * r2[1], r1[2] * r2[0] - r1[0] * r2[2], r1[0] * r2[1] - r1[1] * r2[0]};
+    const double n0 = c0[0] * c0[0] + c0[1] * c0[1] + c0[2] * c0[2];
+    const double n1 = c1[0] * c1[0] + c1[1] * c1[1] + c1[2] * c1[2];
+    const double n2 = c2[0] * c2[0] + c2[1] * c2[1] + c2[2] * c2[2];
+    double v[3], nn = n0;
+    v[0] = c0[0]; v[1] = c0[1]; v[2] = c0[2];
+    if (n1 > nn) { nn = n1; v[0] = c1[0]; v[1] = c1[1]; v[2] = c1[2]; }
+    if (n2 > nn) { nn = n2; v[0] = c2[0]; v[1] = c2[1]; v[2] = c2[2]; }
+    if (!(nn > 1e-60)) {
+        // (numerically) three equal eigenvalues: the closed form is as good as anything
+        const double e0 = q + 2.0 * p * cos(phi), e2 = q + 2.0 * p * cos(phi + 2.0943951023931954923);
+        l[0] = e0; l[2] = e2; l[1] = 1.0 - e0 - e2;
+        return;
     }
-    if (!(bn > 0.0)) { v[0] = 0; v[1] = 0; v[2] = 1; return; }
-    const double s = rsqrt(bn);
-    v[0] = c[best][0] * s; v[1] = c[best][1] * s; v[2] = c[best][2] * s;
+    const double inv = rsqrt(nn);
+    v[0] *= inv; v[1] *= inv; v[2] *= inv;
+    double av[3];
+    sym_mul(a, v, av);
+    lam = v[0] * av[0] + v[1] * av[1] + v[2] * av[2];           // Rayleigh quotient
+
+    // orthonormal basis of the complement
+    double u1[3], u2[3];
+    const double ax = fabs(v[0]), ay = fabs(v[1]), az = fabs(v[2]);
+    if (ax <= ay && ax <= az) { u1[0] = 0.0; u1[1] = -v[2]; u1[2] = v[1]; }
+    else if (ay <= az)        { u1[0] = v[2]; u1[1] = 0.0; u1[2] = -v[0]; }
+    else                      { u1[0] = -v[1]; u1[1] = v[0]; u1[2] = 0.0; }
+    const double iu = rsqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+    u1[0] *= iu; u1[1] *= iu; u1[2] *= iu;
+    u2[0] = v[1] * u1[2] - v[2] * u1[1];
+    u2[1] = v[2] * u1[0] - v[0] * u1[2];
+    u2[2] = v[0] * u1[1] - v[1] * u1[0];
+    double au1[3], au2[3];
+    sym_mul(a, u1, au1);
+    sym_mul(a, u2, au2);
+    const double m00 = u1[0] * au1[0] + u1[1] * au1[1] + u1[2] * au1[2];
+    const double m01 = u1[0] * au2[0] + u1[1] * au2[1] + u1[2] * au2[2];
+    const double m11 = u2[0] * au2[0] + u2[1] * au2[1] + u2[2] * au2[2];
+    const double mid = 0.5 * (m00 + m11);
+    const double hd = 0.5 * (m00 - m11);
+    const double rad = sqrt(hd * hd + m01 * m01);
+    const double hi = mid + rad, lo = mid - rad;
+    if (top) {
+        l[0] = lam; l[1] = hi; l[2] = lo;
+        // eigenvector of the 2x2 block for `lo`, mapped back
+        double w0 = m01, w1 = lo - m00;
+        if (fabs(lo - m11) > fabs(w1)) { w0 = lo - m11; w1 = m01; }
+        const double wn = w0 * w0 + w1 * w1;
+        if (wn > 0.0) {
+            const double iw = rsqrt(wn);
+            w0 *= iw; w1 *= iw;
+            normal[0] = w0 * u1[0] + w1 * u2[0];
+            normal[1] = w0 * u1[1] + w1 * u2[1];
+            normal[2] = w0 * u1[2] + w1 * u2[2];
+        } else {
+            normal[0] = u2[0]; normal[1] = u2[1]; normal[2] = u2[2];
+        }
+    } else {
+        l[0] = hi; l[1] = lo; l[2] = lam;
+        normal[0] = v[0]; normal[1] = v[1]; normal[2] = v[2];
+    }
 }
 
 // writes 4 (reference) or 16 (extended) columns at out[0..]
@@ -96,8 +154,8 @@ __device__ __forceinline__ void emit_features(const Moments &m, const double f[3
             const double it = 1.0 / tr;
 #pragma unroll
             for (int i = 0; i < 6; ++i) a[i] *= it;
-            double l[3];
-            eig3_unit_trace(a, l);
+            double l[3], v[3];
+            eig3_unit_trace(a, l, v);
             col[2] = l[0];
             col[3] = l[1];
             if ((descriptor_mask & NBR_DESC_EXTENDED) && m.n >= 3) {
@@ -114,8 +172,6 @@ __device__ __forceinline__ void emit_features(const Moments &m, const double f[3
                 if (e3 > 0) ent -= e3 * log(e3);
                 col[9] = ent;                          // eigenentropy
                 col[10] = e3;                          // change of curvature
-                double v[3];
-                eigvec3(a, l[2], v);
                 if (v[2] < 0 || (v[2] == 0 && (v[1] < 0 || (v[1] == 0 && v[0] < 0)))) {
                     v[0] = -v[0]; v[1] = -v[1]; v[2] = -v[2];
                 }

@@ -132,6 +132,7 @@ int sort_pairs(uint64_t *keys, uint64_t *keys_tmp, uint32_t *vals, uint32_t *val
 
 extern "C" int nbr_sort_u64(uint64_t *keys, uint64_t *tmp, int64_t n, int begin_bit, int end_bit, void *stream)
 {
+    if (n <= 1) return n < 0 ? nbr::fail(NBR_ERR_INVALID, "nbr_sort_u64: negative n") : NBR_OK;
     if (!keys || !tmp) return nbr::fail(NBR_ERR_INVALID, "nbr_sort_u64: null buffer");
     return nbr::sort_keys(keys, tmp, n, begin_bit, end_bit, (cudaStream_t)stream);
 }
@@ -139,6 +140,7 @@ extern "C" int nbr_sort_u64(uint64_t *keys, uint64_t *tmp, int64_t n, int begin_
 extern "C" int nbr_sort_pairs_u64_u32(uint64_t *keys, uint64_t *keys_tmp, uint32_t *vals, uint32_t *vals_tmp,
                                       int64_t n, int begin_bit, int end_bit, void *stream)
 {
+    if (n <= 1) return n < 0 ? nbr::fail(NBR_ERR_INVALID, "nbr_sort_pairs: negative n") : NBR_OK;
     if (!keys || !keys_tmp || !vals || !vals_tmp) return nbr::fail(NBR_ERR_INVALID, "nbr_sort_pairs: null buffer");
     return nbr::sort_pairs(keys, keys_tmp, vals, vals_tmp, n, begin_bit, end_bit, (cudaStream_t)stream);
 }
