@@ -83,9 +83,11 @@ PhaseTimer::~PhaseTimer()
 int radius_features_exact(const Lattice *lat, const void *query, int dtype, int64_t nq, const double *radii, int nr,
                           void *out, int out_dtype, int64_t row_stride, int col_offset, int descriptor_mask,
                           cudaStream_t stream);
-int radius_features_rows(const Lattice *lat, const void *query, int dtype, int64_t nq, const double *radii, int nr,
-                         void *out, int out_dtype, int64_t row_stride, int col_offset, int descriptor_mask,
-                         cudaStream_t stream, bool *handled);
+int radius_features_rows(const Lattice *lat, const void *query, int dtype, const uint32_t *perm, int64_t nq,
+                         const double *radii, int nr, void *out, int out_dtype, int64_t row_stride, int col_offset,
+                         int descriptor_mask, cudaStream_t stream, bool *handled);
+int morton_order(const void *xyz, int dtype, int64_t n, const double lohi[6], double cell, uint32_t *perm_out,
+                 cudaStream_t stream);
 int radius_sets(const Lattice *lat, const void *query, int dtype, int64_t nq, double radius, int64_t *offsets,
                 int32_t *indices, cudaStream_t stream);
 
@@ -95,16 +97,16 @@ static int check_cloud_dtype(int dtype, const char *who)
     return NBR_OK;
 }
 
-int radius_features(const Lattice *lat, const void *query, int dtype, int64_t nq, const double *radii, int nr,
-                    void *out, int out_dtype, int64_t row_stride, int col_offset, int descriptor_mask, int algorithm,
-                    cudaStream_t stream)
+int radius_features(const Lattice *lat, const void *query, int dtype, const uint32_t *perm, int64_t nq,
+                    const double *radii, int nr, void *out, int out_dtype, int64_t row_stride, int col_offset,
+                    int descriptor_mask, int algorithm, cudaStream_t stream)
 {
     if (lat->grid.ndim != 3) return fail(NBR_ERR_INVALID, "radius_features: the feature path is 3-D only");
     for (int k = 0; k < nr; ++k)
         if (!(radii[k] >= 0)) return fail(NBR_ERR_INVALID, "radius_features: radii must be >= 0");
     if (algorithm != 1) {
         bool handled = false;
-        NBR_TRY(radius_features_rows(lat, query, dtype, nq, radii, nr, out, out_dtype, row_stride, col_offset,
+        NBR_TRY(radius_features_rows(lat, query, dtype, perm, nq, radii, nr, out, out_dtype, row_stride, col_offset,
                                      descriptor_mask, stream, &handled));
         if (handled) return NBR_OK;
         if (algorithm == 2) return fail(NBR_ERR_UNSUPPORTED, "radius_features: row-interval kernel does not cover this r/e");
@@ -141,6 +143,27 @@ int multiscale_features(const void *query, int q_dtype, int64_t nq, const void *
         NBR_CUDA(cudaStreamSynchronize(stream));
     }
 
+    // processing order of the queries: Morton curve at 4 finest voxels per cell
+    Scratch perm;
+    NBR_TRY(perm.alloc(sizeof(uint32_t) * nq, stream));
+    {
+        PhaseTimer t(PHASE_ORDER, stream);
+        double qbox[6];
+        if (query == search && nq == ns && q_dtype == s_dtype && !global_lohi) {
+            std::copy(lohi, lohi + 6, qbox);
+        } else {
+            Scratch box;
+            NBR_TRY(box.alloc(sizeof(double) * 6, stream));
+            NBR_TRY(bbox(query, q_dtype, nq, 3, box.as<double>(), stream));
+            NBR_CUDA(cudaMemcpyAsync(qbox, box.ptr, sizeof(qbox), cudaMemcpyDeviceToHost, stream));
+            NBR_CUDA(cudaStreamSynchronize(stream));
+        }
+        double finest = edges[0];
+        for (int s = 1; s < n_scales; ++s) finest = std::min(finest, edges[s]);
+        if (!(finest > 0)) return fail(NBR_ERR_INVALID, "multiscale_features: edge lengths must be > 0");
+        NBR_TRY(morton_order(query, q_dtype, nq, qbox, 4.0 * finest, perm.as<uint32_t>(), stream));
+    }
+
     const int ncol = (descriptor_mask & NBR_DESC_EXTENDED) ? NBR_COLS_EXTENDED : NBR_COLS_REFERENCE;
     const int64_t row_stride = (int64_t)ncol * n_scales;
     std::vector<char> done(n_scales, 0);
@@ -173,8 +196,8 @@ int multiscale_features(const void *query, int q_dtype, int64_t nq, const void *
             }
             {
                 PhaseTimer tm(PHASE_FEATURES, stream);
-                rc = radius_features(lat, query, q_dtype, nq, group.data(), (int)group.size(), out, out_dtype,
-                                     row_stride, t * ncol, descriptor_mask, 0, stream);
+                rc = radius_features(lat, query, q_dtype, perm.as<uint32_t>(), nq, group.data(), (int)group.size(), out,
+                                     out_dtype, row_stride, t * ncol, descriptor_mask, 0, stream);
             }
             t = u;
         }
@@ -225,8 +248,9 @@ extern "C" int nbr_radius_features(const nbr_lattice *lattice, const void *query
     if (!lattice || !query_xyz || !radii_host || !out) return fail(NBR_ERR_INVALID, "nbr_radius_features: null argument");
     NBR_TRY(check_cloud_dtype(dtype, "nbr_radius_features"));
     if (out_dtype != NBR_F32 && out_dtype != NBR_F64) return fail(NBR_ERR_INVALID, "nbr_radius_features: bad out_dtype");
-    return radius_features(reinterpret_cast<const Lattice *>(lattice), query_xyz, dtype, n_query, radii_host, n_radii, out,
-                           out_dtype, out_row_stride, col_offset, descriptor_mask, algorithm, (cudaStream_t)stream);
+    return radius_features(reinterpret_cast<const Lattice *>(lattice), query_xyz, dtype, nullptr, n_query, radii_host,
+                           n_radii, out, out_dtype, out_row_stride, col_offset, descriptor_mask, algorithm,
+                           (cudaStream_t)stream);
 }
 
 extern "C" int nbr_radius_sets(const nbr_lattice *lattice, const void *query_xyz, int dtype, int64_t n_query,

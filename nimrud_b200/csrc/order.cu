@@ -1,0 +1,75 @@
+// order.cu -- spatially coherent processing order of the query cloud: Morton (Z-curve) keys at a
+// granularity of a few finest voxels, sorted with the hand-written radix sort.  consecutive queries
+// of the order are close in space at every scale, which is what lets one warp of the feature kernel
+// share a staged occupancy window.  results never depend on the order (each query is independent).
+#include "common.cuh"
+
+namespace nbr {
+
+int sort_pairs(uint64_t *keys, uint64_t *keys_tmp, uint32_t *vals, uint32_t *vals_tmp, int64_t n, int begin_bit,
+               int end_bit, cudaStream_t stream);
+
+struct MortonParam {
+    double lo[3];
+    double inv_cell;
+    int bits[3];
+    int levels;
+};
+
+__global__ void __launch_bounds__(256)
+morton_kernel(const void *__restrict__ xyz, int dtype, int64_t n, MortonParam P, uint64_t *__restrict__ keys,
+              uint32_t *__restrict__ vals)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t c[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        double v = (load_coord(xyz, dtype, i, 3, a) - P.lo[a]) * P.inv_cell;
+        const double top = (double)((1u << P.bits[a]) - 1u);
+        v = fmin(fmax(v, 0.0), top);
+        c[a] = (uint32_t)v;
+    }
+    uint64_t key = 0;
+    int pos = 0;
+    for (int l = 0; l < P.levels; ++l) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+            if (l < P.bits[a]) {
+                key |= (uint64_t)((c[a] >> l) & 1u) << pos;
+                ++pos;
+            }
+    }
+    keys[i] = key;
+    vals[i] = (uint32_t)i;
+}
+
+// perm_out[n]: query indices in Morton order.  lohi = bounding box of the query cloud (host).
+int morton_order(const void *xyz, int dtype, int64_t n, const double lohi[6], double cell, uint32_t *perm_out,
+                 cudaStream_t stream)
+{
+    if (n <= 0) return NBR_OK;
+    if (n >= (int64_t)1 << 32) return fail(NBR_ERR_UNSUPPORTED, "morton_order: more than 2^32 queries");
+    MortonParam P;
+    P.inv_cell = 1.0 / cell;
+    P.levels = 0;
+    int total = 0;
+    for (int a = 0; a < 3; ++a) {
+        P.lo[a] = lohi[a];
+        double cells = (lohi[3 + a] - lohi[a]) / cell + 1.0;
+        int b = 1;
+        while (b < 21 && (double)(1u << b) < cells) ++b;
+        P.bits[a] = b;
+        P.levels = std::max(P.levels, b);
+        total += b;
+    }
+    Scratch keys, keys_tmp, vals_tmp;
+    NBR_TRY(keys.alloc(sizeof(uint64_t) * n, stream));
+    NBR_TRY(keys_tmp.alloc(sizeof(uint64_t) * n, stream));
+    NBR_TRY(vals_tmp.alloc(sizeof(uint32_t) * n, stream));
+    morton_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(xyz, dtype, n, P, keys.as<uint64_t>(), perm_out);
+    NBR_LAUNCHED();
+    return sort_pairs(keys.as<uint64_t>(), keys_tmp.as<uint64_t>(), perm_out, vals_tmp.as<uint32_t>(), n, 0, total, stream);
+}
+
+}  // namespace nbr
