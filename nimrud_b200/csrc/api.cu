@@ -7,6 +7,7 @@
 
 #include "common.cuh"
 #include "lattice.cuh"
+#include "radius_rows.cuh"
 
 namespace nbr {
 
@@ -83,11 +84,8 @@ PhaseTimer::~PhaseTimer()
 int radius_features_exact(const Lattice *lat, const void *query, int dtype, int64_t nq, const double *radii, int nr,
                           void *out, int out_dtype, int64_t row_stride, int col_offset, int descriptor_mask,
                           cudaStream_t stream);
-int radius_features_rows(const Lattice *lat, const void *query, int dtype, const uint32_t *perm, int64_t nq,
-                         const double *radii, int nr, void *out, int out_dtype, int64_t row_stride, int col_offset,
-                         int descriptor_mask, cudaStream_t stream, bool *handled);
 int morton_order(const void *xyz, int dtype, int64_t n, const double lohi[6], double cell, uint32_t *perm_out,
-                 cudaStream_t stream);
+                 void *sorted_xyz_out, cudaStream_t stream);
 int radius_sets(const Lattice *lat, const void *query, int dtype, int64_t nq, double radius, int64_t *offsets,
                 int32_t *indices, cudaStream_t stream);
 
@@ -104,19 +102,30 @@ int radius_features(const Lattice *lat, const void *query, int dtype, const uint
     if (lat->grid.ndim != 3) return fail(NBR_ERR_INVALID, "radius_features: the feature path is 3-D only");
     for (int k = 0; k < nr; ++k)
         if (!(radii[k] >= 0)) return fail(NBR_ERR_INVALID, "radius_features: radii must be >= 0");
-    if (algorithm != 1) {
-        bool handled = false;
-        NBR_TRY(radius_features_rows(lat, query, dtype, perm, nq, radii, nr, out, out_dtype, row_stride, col_offset,
-                                     descriptor_mask, stream, &handled));
-        if (handled) return NBR_OK;
-        if (algorithm == 2) return fail(NBR_ERR_UNSUPPORTED, "radius_features: row-interval kernel does not cover this r/e");
+    const int ncol = (descriptor_mask & NBR_DESC_EXTENDED) ? NBR_COLS_EXTENDED : NBR_COLS_REFERENCE;
+    if (algorithm != 1 && rows_supported(lat->grid.edge, radii, nr)) {
+        for (int base = 0; base < nr; base += RW_MAX_RADII) {
+            RowsLaunch launch;
+            memset(&launch, 0, sizeof(launch));
+            const int n = std::min(RW_MAX_RADII, nr - base);
+            int cols[RW_MAX_RADII];
+            for (int k = 0; k < n; ++k) cols[k] = col_offset + (base + k) * ncol;
+            launch.n_lat = 1;
+            launch.lat[0] = lat->dev();
+            NBR_TRY(rows_param(lat, radii + base, cols, n, &launch.rows[0]));
+            NBR_TRY(radius_rows_launch(&launch, query, dtype, perm, nq, out, out_dtype, row_stride, descriptor_mask, stream));
+        }
+        return NBR_OK;
     }
+    if (algorithm == 2) return fail(NBR_ERR_UNSUPPORTED, "radius_features: row-interval kernel does not cover this r/e");
+    if (perm) return fail(NBR_ERR_INVALID, "radius_features: the exact kernel takes queries in natural order");
     return radius_features_exact(lat, query, dtype, nq, radii, nr, out, out_dtype, row_stride, col_offset,
                                  descriptor_mask, stream);
 }
 
-// groups scales by edge length, builds one lattice per distinct edge and runs the fused kernel once
-// per group (all radii of the group in one pass over each query's neighborhood).
+// groups scales by edge length, builds one lattice per distinct edge, orders the queries along a
+// Morton curve and runs ONE fused kernel over all lattices (all radii of a lattice share one pass over
+// each query's window).  scales the row kernel cannot take (r/e > 9.5) go through the exact kernel.
 int multiscale_features(const void *query, int q_dtype, int64_t nq, const void *search, int s_dtype, int64_t ns,
                         const double *edges, const double *radii, int n_scales, void *out, int out_dtype,
                         int descriptor_mask, const double *global_lohi, int64_t *n_voxels_host, cudaStream_t stream)
@@ -128,6 +137,10 @@ int multiscale_features(const void *query, int q_dtype, int64_t nq, const void *
     if (ns < 2) return fail(NBR_ERR_TOO_FEW_POINTS, "need at least 2 points to define a voxel grid");
     if (n_scales == 0 || nq == 0) return NBR_OK;
     if (!query || !search || !edges || !radii || !out) return fail(NBR_ERR_INVALID, "multiscale_features: null argument");
+    for (int s = 0; s < n_scales; ++s) {
+        if (!(edges[s] > 0)) return fail(NBR_ERR_INVALID, "multiscale_features: edge lengths must be > 0");
+        if (!(radii[s] >= 0)) return fail(NBR_ERR_INVALID, "multiscale_features: radii must be >= 0");
+    }
 
     double lohi[6];
     if (global_lohi) {
@@ -143,74 +156,97 @@ int multiscale_features(const void *query, int q_dtype, int64_t nq, const void *
         NBR_CUDA(cudaStreamSynchronize(stream));
     }
 
-    // processing order of the queries: Morton curve at 4 finest voxels per cell
-    Scratch perm;
-    NBR_TRY(perm.alloc(sizeof(uint32_t) * nq, stream));
+    const int ncol = (descriptor_mask & NBR_DESC_EXTENDED) ? NBR_COLS_EXTENDED : NBR_COLS_REFERENCE;
+    const int64_t row_stride = (int64_t)ncol * n_scales;
+
+    // ---- one lattice per distinct edge
+    struct Group { double edge; Lattice *lat; std::vector<int> scales; };
+    std::vector<Group> groups;
+    for (int s = 0; s < n_scales; ++s) {
+        size_t gi = 0;
+        while (gi < groups.size() && groups[gi].edge != edges[s]) ++gi;
+        if (gi == groups.size()) groups.push_back({edges[s], nullptr, {}});
+        groups[gi].scales.push_back(s);
+    }
+    int rc = NBR_OK;
+    auto cleanup = [&]() { for (auto &g : groups) delete g.lat; };
     {
+        PhaseTimer t(PHASE_INDEX, stream);
+        for (auto &g : groups) {
+            nbr_grid grid;
+            rc = grid_from_bbox(lohi, lohi + 3, g.edge, 3, &grid);
+            if (!rc) rc = lattice_create(&g.lat, search, s_dtype, ns, &grid, 0, stream);
+            if (rc) break;
+        }
+    }
+    if (rc) { cleanup(); return rc; }
+
+    // ---- processing order of the queries: Morton curve, cells of 4 finest voxels; sorted copy of the cloud
+    Scratch perm, sorted;
+    rc = perm.alloc(sizeof(uint32_t) * nq, stream);
+    if (!rc) rc = sorted.alloc((size_t)nq * 3 * (q_dtype == NBR_F32 ? 4 : 8), stream);
+    if (!rc) {
         PhaseTimer t(PHASE_ORDER, stream);
         double qbox[6];
         if (query == search && nq == ns && q_dtype == s_dtype && !global_lohi) {
             std::copy(lohi, lohi + 6, qbox);
         } else {
             Scratch box;
-            NBR_TRY(box.alloc(sizeof(double) * 6, stream));
-            NBR_TRY(bbox(query, q_dtype, nq, 3, box.as<double>(), stream));
-            NBR_CUDA(cudaMemcpyAsync(qbox, box.ptr, sizeof(qbox), cudaMemcpyDeviceToHost, stream));
-            NBR_CUDA(cudaStreamSynchronize(stream));
+            rc = box.alloc(sizeof(double) * 6, stream);
+            if (!rc) rc = bbox(query, q_dtype, nq, 3, box.as<double>(), stream);
+            if (!rc && (cudaMemcpyAsync(qbox, box.ptr, sizeof(qbox), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+                        cudaStreamSynchronize(stream) != cudaSuccess))
+                rc = fail(NBR_ERR_CUDA, "multiscale_features: query bounding box copy failed");
         }
         double finest = edges[0];
         for (int s = 1; s < n_scales; ++s) finest = std::min(finest, edges[s]);
-        if (!(finest > 0)) return fail(NBR_ERR_INVALID, "multiscale_features: edge lengths must be > 0");
-        NBR_TRY(morton_order(query, q_dtype, nq, qbox, 4.0 * finest, perm.as<uint32_t>(), stream));
+        if (!rc) rc = morton_order(query, q_dtype, nq, qbox, 4.0 * finest, perm.as<uint32_t>(), sorted.ptr, stream);
     }
+    if (rc) { cleanup(); return rc; }
 
-    const int ncol = (descriptor_mask & NBR_DESC_EXTENDED) ? NBR_COLS_EXTENDED : NBR_COLS_REFERENCE;
-    const int64_t row_stride = (int64_t)ncol * n_scales;
-    std::vector<char> done(n_scales, 0);
-    std::vector<Lattice *> lattices;
-    std::vector<std::pair<Lattice *, int>> voxel_of_scale;   // lattice, scale
-    int rc = NBR_OK;
-    for (int s = 0; s < n_scales && rc == NBR_OK; ++s) {
-        if (done[s]) continue;
-        nbr_grid grid;
-        rc = grid_from_bbox(lohi, lohi + 3, edges[s], 3, &grid);
-        if (rc) break;
-        Lattice *lat = nullptr;
-        {
-            PhaseTimer t(PHASE_INDEX, stream);
-            rc = lattice_create(&lat, search, s_dtype, ns, &grid, 0, stream);
-        }
-        if (rc) break;
-        lattices.push_back(lat);
-        // scales sharing this edge form runs of consecutive columns where possible
-        int t = s;
-        while (t < n_scales && rc == NBR_OK) {
-            if (done[t] || edges[t] != edges[s]) { ++t; continue; }
-            int u = t;
-            std::vector<double> group;
-            while (u < n_scales && !done[u] && edges[u] == edges[s]) {
-                group.push_back(radii[u]);
-                done[u] = 1;
-                voxel_of_scale.push_back({lat, u});
-                ++u;
+    // ---- fused launches
+    {
+        PhaseTimer tm(PHASE_FEATURES, stream);
+        RowsLaunch launch;
+        memset(&launch, 0, sizeof(launch));
+        auto flush = [&]() -> int {
+            if (launch.n_lat == 0) return NBR_OK;
+            int r = radius_rows_launch(&launch, sorted.ptr, q_dtype, perm.as<uint32_t>(), nq, out, out_dtype, row_stride,
+                                       descriptor_mask, stream);
+            memset(&launch, 0, sizeof(launch));
+            return r;
+        };
+        for (auto &g : groups) {
+            std::vector<double> rr;
+            std::vector<int> cc;
+            for (int s : g.scales) {
+                if (rows_supported(g.edge, &radii[s], 1)) { rr.push_back(radii[s]); cc.push_back(s * ncol); }
+                else {
+                    rc = radius_features_exact(g.lat, query, q_dtype, nq, &radii[s], 1, out, out_dtype, row_stride,
+                                               s * ncol, descriptor_mask, stream);
+                    if (rc) break;
+                }
             }
-            {
-                PhaseTimer tm(PHASE_FEATURES, stream);
-                rc = radius_features(lat, query, q_dtype, perm.as<uint32_t>(), nq, group.data(), (int)group.size(), out,
-                                     out_dtype, row_stride, t * ncol, descriptor_mask, 0, stream);
+            for (size_t base = 0; base < rr.size() && !rc; base += RW_MAX_RADII) {
+                const int n = (int)std::min<size_t>(RW_MAX_RADII, rr.size() - base);
+                launch.lat[launch.n_lat] = g.lat->dev();
+                rc = rows_param(g.lat, rr.data() + base, cc.data() + base, n, &launch.rows[launch.n_lat]);
+                ++launch.n_lat;
+                if (!rc && launch.n_lat == RW_MAX_LATTICES) rc = flush();
             }
-            t = u;
+            if (rc) break;
         }
+        if (!rc) rc = flush();
     }
     if (rc == NBR_OK && n_voxels_host) {
-        for (auto &p : voxel_of_scale) {
+        for (auto &g : groups) {
             int64_t nv = 0;
-            rc = lattice_counts(p.first, &nv, nullptr);
+            rc = lattice_counts(g.lat, &nv, nullptr);
             if (rc) break;
-            n_voxels_host[p.second] = nv;
+            for (int s : g.scales) n_voxels_host[s] = nv;
         }
     }
-    for (Lattice *l : lattices) delete l;
+    cleanup();
     return rc;
 }
 

@@ -27,9 +27,10 @@ struct Moments {
 // the trigonometric closed form alone loses half the digits on a (near-)double eigenvalue
 // (acos near +-1), which is the normal case here: lines give l2 = l3 = 0, flat patches l1 = l2.
 // so it is only used to pick the ISOLATED eigenvalue (largest if the half-determinant r >= 0,
-// smallest otherwise), which it gets to full precision; that eigenpair is deflated and the other two
-// come from the 2x2 block in the orthogonal complement through the cancellation-free
-// m +- hypot(.,.) form.  absolute error ~1e-16 on every eigenvalue, clusters included.
+// smallest otherwise) and its eigenvector, in float32; that eigenpair is then deflated in float64
+// (Rayleigh quotient + the 2x2 block in the orthogonal complement through the cancellation-free
+// m +- hypot(.,.) form).  the float32 error of the eigenvector enters at second order only, so every
+// eigenvalue comes out with absolute error ~1e-13, clusters included.
 __device__ __forceinline__ void sym_mul(const double a[6], const double x[3], double y[3])
 {
     y[0] = a[0] * x[0] + a[1] * x[1] + a[2] * x[2];
@@ -37,10 +38,12 @@ __device__ __forceinline__ void sym_mul(const double a[6], const double x[3], do
     y[2] = a[2] * x[0] + a[4] * x[1] + a[5] * x[2];
 }
 
-__device__ __forceinline__ void eig3_unit_trace(const double a[6], double l[3], double normal[3])
+// float64 closed form (trigonometric); only used when the matrix is (nearly) a multiple of the
+// identity, where the three eigenvalues are within ~1e-3 of each other and half-precision loss on a
+// double root is harmless.
+static __device__ __noinline__ void eig3_near_isotropic(const double a[6], double l[3])
 {
     const double q = 1.0 / 3.0;
-    normal[0] = 0.0; normal[1] = 0.0; normal[2] = 1.0;
     const double p1 = a[1] * a[1] + a[2] * a[2] + a[4] * a[4];
     const double d0 = a[0] - q, d1 = a[3] - q, d2 = a[5] - q;
     const double p2 = d0 * d0 + d1 * d1 + d2 * d2 + 2.0 * p1;
@@ -51,36 +54,51 @@ __device__ __forceinline__ void eig3_unit_trace(const double a[6], double l[3], 
     double r = 0.5 * (b0 * (b3 * b5 - b4 * b4) - b1 * (b1 * b5 - b4 * b2) + b2 * (b1 * b4 - b3 * b2));
     r = fmin(1.0, fmax(-1.0, r));
     const double phi = acos(r) * (1.0 / 3.0);
-    const bool top = r >= 0.0;          // true: the largest eigenvalue is the isolated one
-    double lam = top ? q + 2.0 * p * cos(phi) : q + 2.0 * p * cos(phi + 2.0943951023931954923);
+    const double e0 = q + 2.0 * p * cos(phi), e2 = q + 2.0 * p * cos(phi + 2.0943951023931954923);
+    l[0] = e0; l[2] = e2; l[1] = 1.0 - e0 - e2;
+}
 
-    // eigenvector of the isolated eigenvalue: best-conditioned cross product of rows of (A - lam I)
-    const double r0[3] = {a[0] - lam, a[1], a[2]};
-    const double r1[3] = {a[1], a[3] - lam, a[4]};
-    const double r2[3] = {a[2], a[4], a[5] - lam};
-    double c0[3] = {r0[1] * r1[2] - r0[2] * r1[1], r0[2] * r1[0] - r0[0] * r1[2], r0[0] * r1[1] - r0[1] * r1[0]};
-    double c1[3] = {r0[1] * r2[2] - r0[2] * r2[1], r0[2] * r2[0] - r0[0] * r2[2], r0[0] * r2[1] - r0[1] * r2[0]};
-    double c2[3] = {r1[1] * r2[2] - r1[2] * r2[1], r1[2] * r2[0] - r1[0] * r2[2], r1[0] * r2[1] - r1[1] * r2[0]};
-    const double n0 = c0[0] * c0[0] + c0[1] * c0[1] + c0[2] * c0[2];
-    const double n1 = c1[0] * c1[0] + c1[1] * c1[1] + c1[2] * c1[2];
-    const double n2 = c2[0] * c2[0] + c2[1] * c2[1] + c2[2] * c2[2];
-    double v[3], nn = n0;
-    v[0] = c0[0]; v[1] = c0[1]; v[2] = c0[2];
-    if (n1 > nn) { nn = n1; v[0] = c1[0]; v[1] = c1[1]; v[2] = c1[2]; }
-    if (n2 > nn) { nn = n2; v[0] = c2[0]; v[1] = c2[1]; v[2] = c2[2]; }
-    if (!(nn > 1e-60)) {
-        // (numerically) three equal eigenvalues: the closed form is as good as anything
-        const double e0 = q + 2.0 * p * cos(phi), e2 = q + 2.0 * p * cos(phi + 2.0943951023931954923);
-        l[0] = e0; l[2] = e2; l[1] = 1.0 - e0 - e2;
-        return;
-    }
-    const double inv = rsqrt(nn);
+__device__ __forceinline__ void eig3_unit_trace(const double a[6], double l[3], double normal[3])
+{
+    normal[0] = 0.0; normal[1] = 0.0; normal[2] = 1.0;
+    // ---- float32: which eigenvalue is isolated, and its eigenvector to ~1e-6
+    const float qf = 1.0f / 3.0f;
+    const float f0 = (float)a[0], f1 = (float)a[1], f2 = (float)a[2], f3 = (float)a[3], f4 = (float)a[4],
+                f5 = (float)a[5];
+    const float g0 = f0 - qf, g1 = f3 - qf, g2 = f5 - qf;
+    const float p2 = g0 * g0 + g1 * g1 + g2 * g2 + 2.0f * (f1 * f1 + f2 * f2 + f4 * f4);
+    if (!(p2 > 1e-7f)) { eig3_near_isotropic(a, l); return; }
+    const float p = sqrtf(p2 * (1.0f / 6.0f));
+    const float ip = 1.0f / p;
+    const float b0 = g0 * ip, b1 = f1 * ip, b2 = f2 * ip, b3 = g1 * ip, b4 = f4 * ip, b5 = g2 * ip;
+    float r = 0.5f * (b0 * (b3 * b5 - b4 * b4) - b1 * (b1 * b5 - b4 * b2) + b2 * (b1 * b4 - b3 * b2));
+    r = fminf(1.0f, fmaxf(-1.0f, r));
+    const float phi = acosf(r) * (1.0f / 3.0f);
+    const bool top = r >= 0.0f;          // true: the largest eigenvalue is the isolated one
+    const float lamf = top ? qf + 2.0f * p * __cosf(phi) : qf + 2.0f * p * __cosf(phi + 2.0943951f);
+    // best-conditioned cross product of rows of (A - lam I)
+    const float r00 = f0 - lamf, r11 = f3 - lamf, r22 = f5 - lamf;
+    const float c0x = f1 * f4 - f2 * r11, c0y = f2 * f1 - r00 * f4, c0z = r00 * r11 - f1 * f1;      // row0 x row1
+    const float c1x = f1 * r22 - f2 * f4, c1y = f2 * f2 - r00 * r22, c1z = r00 * f4 - f1 * f2;      // row0 x row2
+    const float c2x = r11 * r22 - f4 * f4, c2y = f4 * f2 - f1 * r22, c2z = f1 * f4 - r11 * f2;      // row1 x row2
+    const float n0 = c0x * c0x + c0y * c0y + c0z * c0z;
+    const float n1 = c1x * c1x + c1y * c1y + c1z * c1z;
+    const float n2 = c2x * c2x + c2y * c2y + c2z * c2z;
+    float vx = c0x, vy = c0y, vz = c0z, nn = n0;
+    if (n1 > nn) { nn = n1; vx = c1x; vy = c1y; vz = c1z; }
+    if (n2 > nn) { nn = n2; vx = c2x; vy = c2y; vz = c2z; }
+    if (!(nn > 1e-30f)) { eig3_near_isotropic(a, l); return; }
+    const float invf = rsqrtf(nn);
+
+    // ---- float64: exact deflation around that (approximate) eigenvector.  an error d in v only
+    // enters the results at second order (spread * d^2 ~ 1e-13).
+    double v[3] = {(double)(vx * invf), (double)(vy * invf), (double)(vz * invf)};
+    const double inv = rsqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
     v[0] *= inv; v[1] *= inv; v[2] *= inv;
     double av[3];
     sym_mul(a, v, av);
-    lam = v[0] * av[0] + v[1] * av[1] + v[2] * av[2];           // Rayleigh quotient
+    const double lam = v[0] * av[0] + v[1] * av[1] + v[2] * av[2];           // Rayleigh quotient
 
-    // orthonormal basis of the complement
     double u1[3], u2[3];
     const double ax = fabs(v[0]), ay = fabs(v[1]), az = fabs(v[2]);
     if (ax <= ay && ax <= az) { u1[0] = 0.0; u1[1] = -v[2]; u1[2] = v[1]; }

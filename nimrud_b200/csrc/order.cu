@@ -44,9 +44,29 @@ morton_kernel(const void *__restrict__ xyz, int dtype, int64_t n, MortonParam P,
     vals[i] = (uint32_t)i;
 }
 
-// perm_out[n]: query indices in Morton order.  lohi = bounding box of the query cloud (host).
+// sorted_out[i] = xyz[perm[i]] (same dtype as the input)
+__global__ void __launch_bounds__(256)
+gather_kernel(const void *__restrict__ xyz, int dtype, int64_t n, const uint32_t *__restrict__ perm,
+              void *__restrict__ sorted_out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t j = perm[i];
+    if (dtype == NBR_F32) {
+        const float *src = reinterpret_cast<const float *>(xyz) + j * 3;
+        float *dst = reinterpret_cast<float *>(sorted_out) + i * 3;
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+    } else {
+        const double *src = reinterpret_cast<const double *>(xyz) + j * 3;
+        double *dst = reinterpret_cast<double *>(sorted_out) + i * 3;
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+    }
+}
+
+// perm_out[n]: query indices in Morton order; sorted_xyz_out (optional): the cloud in that order.
+// lohi = bounding box of the query cloud (host).
 int morton_order(const void *xyz, int dtype, int64_t n, const double lohi[6], double cell, uint32_t *perm_out,
-                 cudaStream_t stream)
+                 void *sorted_xyz_out, cudaStream_t stream)
 {
     if (n <= 0) return NBR_OK;
     if (n >= (int64_t)1 << 32) return fail(NBR_ERR_UNSUPPORTED, "morton_order: more than 2^32 queries");
@@ -69,7 +89,12 @@ int morton_order(const void *xyz, int dtype, int64_t n, const double lohi[6], do
     NBR_TRY(vals_tmp.alloc(sizeof(uint32_t) * n, stream));
     morton_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(xyz, dtype, n, P, keys.as<uint64_t>(), perm_out);
     NBR_LAUNCHED();
-    return sort_pairs(keys.as<uint64_t>(), keys_tmp.as<uint64_t>(), perm_out, vals_tmp.as<uint32_t>(), n, 0, total, stream);
+    NBR_TRY(sort_pairs(keys.as<uint64_t>(), keys_tmp.as<uint64_t>(), perm_out, vals_tmp.as<uint32_t>(), n, 0, total, stream));
+    if (sorted_xyz_out) {
+        gather_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(xyz, dtype, n, perm_out, sorted_xyz_out);
+        NBR_LAUNCHED();
+    }
+    return NBR_OK;
 }
 
 }  // namespace nbr

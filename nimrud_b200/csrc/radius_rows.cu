@@ -1,11 +1,15 @@
 // radius_rows.cu -- the fused radius query + covariance + eigensolve + feature kernel (hot path).
 //
 // replaces nimrud/minimal/multiscale.py:94-122 (chunk kd-tree, query_ball_tree, take, population,
-// centroid, pca) for one lattice (one voxel edge) and all radii that share it.
+// centroid, pca) for EVERY scale of a call in one launch.
 //
-// the search set is a voxel LATTICE, so a ball is a stack of x-intervals, one per (y,z) row.
-//   * one warp owns 32 consecutive queries (callers pass a spatially coherent order).  it stages the
-//     occupancy bricks covering the warp's bounding box + halo into shared memory once, coalesced.
+// the search set of a scale is a voxel LATTICE, so a ball is a stack of x-intervals, one per (y,z) row.
+//   * one warp owns 32 consecutive queries of a spatially coherent (Morton) order and walks through
+//     the lattices (one per distinct voxel edge) in turn.  for each lattice it stages the occupancy
+//     bricks covering the warp's bounding box + halo into shared memory with 16-byte cp.async copies.
+//     if the box does not fit the staging buffer (sparse points, or the Morton curve jumped inside the
+//     warp) the lanes read their rows straight from global memory, skipping empty bricks through the
+//     directory.
 //   * each lane then walks the (2W+1)^2 rows of its own window.  per row the x-interval is found in
 //     float32 from sqrt(rho^2 - dy^2 - dz^2); an endpoint closer than a rounding bound to a cell
 //     boundary sends that row to the exact float64 test of the reference
@@ -13,29 +17,12 @@
 //   * occupancy & interval mask -> count / sum x / sum x^2 through a 256-entry byte table; y and z
 //     are row constants.  all moments are exact integers; finalize.cuh turns them into features in
 //     the same kernel.  no neighbor list ever exists in memory.
-// windows too large for the staging buffer (outlier queries far from the cloud) fall back to the
-// exact per-candidate kernel's traversal for that warp.
 #include "common.cuh"
 #include "finalize.cuh"
 #include "lattice.cuh"
+#include "radius_rows.cuh"
 
 namespace nbr {
-
-constexpr int RW_WARPS = 4;
-constexpr int RW_CAP_BRICKS = 48;                 // staged bricks per warp (6 KB)
-constexpr int RW_MAX_W = 15;                      // 2W+1 <= 31 bits per row
-constexpr int RW_MAX_RADII = 8;
-
-struct RowsParam {
-    double r[RW_MAX_RADII];      // exact radii (fallback test)
-    float rho2[RW_MAX_RADII];    // (r/e)^2
-    float eps_a[RW_MAX_RADII];   // rounding bound: delta = eps_a * min(rsqrt(T), 1e3) + eps_b
-    float t_min[RW_MAX_RADII];   // rows with T < t_min are certainly empty
-    int w[RW_MAX_RADII];         // window half-width of each radius
-    float eps_b;
-    int n;
-    int wmax;
-};
 
 // byte -> count | sum(pos) << 8 | sum(pos^2) << 16     (positions 0..7)
 __device__ __forceinline__ uint32_t byte_moments(uint32_t b)
@@ -68,261 +55,280 @@ __device__ __noinline__ uint32_t exact_row_mask(const GridDev &g, double qx, dou
     return m;
 }
 
+// everything a lane needs to know about one (query, lattice)
+struct LaneCtx {
+    double q[3];
+    int c[3];
+    float fxm, fym, fzm;      // query position in window cell units (cell j' has its centre at j')
+    int W;
+};
+
+// x-interval of one row in float32, exact float64 fallback near cell boundaries; then the byte table.
+// returns count | sum x | sum x^2 of (bits & ball) in cnt, sx, sxx; x in window units 0..2W
+__device__ __forceinline__ void row_moments(const GridDev &g, const RowsParam &P, int ri, const LaneCtx &X, int jy,
+                                            int jz, float T, uint32_t bits, const uint32_t *s_lut, int &cnt, int &sx,
+                                            int &sxx)
+{
+    const int W = X.W;
+    const float Tc = fmaxf(T, 0.0f);
+    const float rs = fminf(rsqrtf(Tc), 1.0e3f);
+    const float s = Tc * rs;
+    const float a = X.fxm - s, b = X.fxm + s;
+    const float ca = ceilf(a), fb = floorf(b);
+    const float delta = P.eps_a[ri] * rs + P.eps_b;
+    const bool unsure = (ca - a < delta) | (a - (ca - 1.0f) < delta) | (b - fb < delta) | (fb + 1.0f - b < delta) |
+                        (T < -P.t_min[ri]);
+    uint32_t m;
+    if (unsure) {
+        m = exact_row_mask(g, X.q[0], X.q[1], X.q[2], X.c[0], X.c[1] - W + jy, X.c[2] - W + jz, W, P.r[ri]);
+    } else {
+        const int il = max((int)ca, 0), ih = min((int)fb, 2 * W);
+        m = ih >= il ? (((2u << ih) - 1u) & ~((1u << il) - 1u)) : 0u;
+    }
+    m &= bits;
+    cnt = 0; sx = 0; sxx = 0;
+    if (m == 0) return;
+#pragma unroll
+    for (int byte = 0; byte < 3; ++byte) {
+        if (byte * 8 <= 2 * W) {
+            const uint32_t e = s_lut[(m >> (8 * byte)) & 255u];
+            const int bc = e & 255, b1 = (e >> 8) & 255, b2 = e >> 16;
+            cnt += bc;
+            sx += b1 + 8 * byte * bc;
+            sxx += b2 + 16 * byte * b1 + 64 * byte * byte * bc;
+        }
+    }
+}
+
+// one lane, one radius: walk the (2Wr+1)^2 rows of the window.
+// STAGED: rows come from the warp's shared-memory window (bricks [iz][iy][ix], origin lo[] in bricks).
+// !STAGED: rows come straight from the directory + pool in global memory (incoherent warps); empty
+//          bricks are skipped through the directory.
+template <bool STAGED>
+__device__ __forceinline__ void lane_rows(const LatticeDev &L, const RowsParam &P, int ri, const LaneCtx &X,
+                                          const uint32_t *win, const int lo[3], int nb0, int nb1,
+                                          const uint32_t *s_lut, Acc &A)
+{
+    const GridDev &g = L.g;
+    const int W = X.W, Wr = P.w[ri];
+    const float rho2 = P.rho2[ri], t_min = P.t_min[ri];
+    const uint32_t rowmask = (2u << (2 * W)) - 1u;
+    // x alignment: window bit 0 <-> absolute cell c0 - W
+    const int xa = X.c[0] - W;                                    // absolute cell of window bit 0
+    const int bx0 = xa >> BRICK_XS;                               // floor
+    const int sh = xa & 31;
+    const bool two = sh + 2 * W + 1 > 32;
+    const int ixs = STAGED ? bx0 - lo[0] : 0;
+    const int ya = X.c[1] - W, za = X.c[2] - W;                   // absolute cells of rows jy' = 0, jz' = 0
+    int cached_gy = 0x7fffffff, cached_gz = 0x7fffffff;
+    uint32_t slot_a = 0, slot_b = 0;
+
+    for (int jz = W - Wr; jz <= W + Wr; ++jz) {
+        const float dz = X.fzm - (float)jz;
+        const float Tz = rho2 - dz * dz;
+        if (Tz < t_min) continue;
+        const int az = za + jz;
+        const int gz = az >> BRICK_ZS;
+        const int wz = (az & (BRICK_Z - 1)) << BRICK_YS;
+        if (!STAGED && (gz < 0 || gz >= L.nbz)) continue;
+        const int zoff = STAGED ? ((gz - lo[2]) * nb1) * nb0 * BRICK_WORDS + wz : 0;
+        int C = 0, SX = 0, SXX = 0, SY = 0, SYY = 0, SXY = 0;
+        for (int jy = W - Wr; jy <= W + Wr; ++jy) {
+            const float dy = X.fym - (float)jy;
+            const float T = Tz - dy * dy;
+            if (T < t_min) continue;
+            const int ay = ya + jy;
+            const int gy = ay >> BRICK_YS;
+            uint32_t w0, w1;
+            if (STAGED) {
+                const int off = zoff + ((gy - lo[1]) * nb0 + ixs) * BRICK_WORDS + (ay & (BRICK_Y - 1));
+                w0 = win[off];
+                w1 = two ? win[off + BRICK_WORDS] : 0u;
+            } else {
+                if (gy < 0 || gy >= L.nby) continue;
+                if (gy != cached_gy || gz != cached_gz) {
+                    cached_gy = gy; cached_gz = gz;
+                    const int64_t rowb = ((int64_t)gz * L.nby + gy) * L.nbx;
+                    slot_a = (bx0 >= 0 && bx0 < L.nbx) ? L.dir[rowb + bx0] : 0u;
+                    slot_b = (two && bx0 + 1 >= 0 && bx0 + 1 < L.nbx) ? L.dir[rowb + bx0 + 1] : 0u;
+                }
+                if ((slot_a | slot_b) == 0) continue;
+                const int word = wz | (ay & (BRICK_Y - 1));
+                w0 = slot_a ? L.pool[(int64_t)slot_a * BRICK_WORDS + word] : 0u;
+                w1 = slot_b ? L.pool[(int64_t)slot_b * BRICK_WORDS + word] : 0u;
+            }
+            const uint32_t bits = __funnelshift_r(w0, w1, sh) & rowmask;
+            if (bits == 0) continue;
+            int cnt, sx, sxx;
+            row_moments(g, P, ri, X, jy, jz, T, bits, s_lut, cnt, sx, sxx);
+            C += cnt; SX += sx; SXX += sxx;
+            SY += jy * cnt; SYY += jy * jy * cnt; SXY += jy * sx;
+        }
+        A.n += C; A.sx += SX; A.sxx += SXX; A.sy += SY; A.syy += SYY; A.sxy += SXY;
+        A.sz += jz * C; A.szz += jz * jz * C; A.sxz += jz * SX; A.syz += jz * SY;
+    }
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *gptr, bool valid)
+{
+    const int src_bytes = valid ? 16 : 0;      // 0 -> the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gptr), "r"(src_bytes));
+}
+
 template <typename OutT>
 __global__ void __launch_bounds__(RW_WARPS * 32)
-radius_rows_kernel(LatticeDev L, const void *__restrict__ query, int dtype, const uint32_t *__restrict__ perm,
-                   int64_t nq, RowsParam P, OutT *__restrict__ out, int64_t row_stride, int col_offset,
+radius_rows_kernel(const RowsLaunch *__restrict__ launch, const void *__restrict__ query, int dtype,
+                   const uint32_t *__restrict__ perm, int64_t nq, OutT *__restrict__ out, int64_t row_stride,
                    int descriptor_mask)
 {
     __shared__ uint32_t s_lut[256];
-    __shared__ uint32_t s_win[RW_WARPS][RW_CAP_BRICKS * BRICK_WORDS];
+    __shared__ __align__(16) uint32_t s_win[RW_WARPS][RW_CAP_BRICKS * BRICK_WORDS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = byte_moments(i);
     __syncthreads();
 
-    const GridDev &g = L.g;
-    const int ncol = (descriptor_mask & NBR_DESC_EXTENDED) ? NBR_COLS_EXTENDED : NBR_COLS_REFERENCE;
     uint32_t *win = s_win[warp];
+    const uint32_t win_addr = (uint32_t)__cvta_generic_to_shared(win);
     const int64_t n_groups = (nq + 31) >> 5;
+    const int n_lat = launch->n_lat;
 
     for (int64_t grp = (int64_t)blockIdx.x * RW_WARPS + warp; grp < n_groups; grp += (int64_t)gridDim.x * RW_WARPS) {
         const int64_t slot_i = grp * 32 + lane;
         const bool active = slot_i < nq;
-        const int64_t qi = perm ? (int64_t)perm[active ? slot_i : grp * 32] : (active ? slot_i : grp * 32);
-        double q[3], f[3];
-        int c[3];
+        const int64_t src = active ? slot_i : grp * 32;             // inactive lanes shadow lane 0
+        const int64_t qi = perm ? (int64_t)perm[src] : src;         // row of the output
+        LaneCtx X;
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            q[a] = load_coord(query, dtype, qi, 3, a);
-            query_anchor(q[a], g.minc[a], g.edge, c[a], f[a]);
-        }
-        // warp bounding box of the anchor cells -> brick window
-        const int W = P.wmax;
-        int lo[3], nb[3];
-        bool fits = true;
+        for (int a = 0; a < 3; ++a) X.q[a] = load_coord(query, dtype, src, 3, a);
+        OutT *dst_row = out + qi * row_stride;
+
+        for (int li = 0; li < n_lat; ++li) {
+            const LatticeDev &L = launch->lat[li];
+            const RowsParam &P = launch->rows[li];
+            const GridDev &g = L.g;
+            double f[3];
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const int mn = __reduce_min_sync(0xffffffffu, c[a]) - W;
-            const int mx = __reduce_max_sync(0xffffffffu, c[a]) + W;
-            const int sh = a == 0 ? BRICK_XS : (a == 1 ? BRICK_YS : BRICK_ZS);
-            lo[a] = mn >> sh;                       // arithmetic shift = floor division
-            const long long cnt = (long long)(mx >> sh) - lo[a] + 1;
-            fits &= cnt <= RW_CAP_BRICKS;
-            nb[a] = (int)cnt;
-        }
-        fits = fits && (long long)nb[0] * nb[1] * nb[2] <= RW_CAP_BRICKS;
+            for (int a = 0; a < 3; ++a) query_anchor(X.q[a], g.minc[a], g.edge, X.c[a], f[a]);
+            const int W = P.wmax;
+            X.W = W;
+            X.fxm = (float)f[0] - 0.5f + (float)W;
+            X.fym = (float)f[1] - 0.5f + (float)W;
+            X.fzm = (float)f[2] - 0.5f + (float)W;
 
-        OutT *dst = out + qi * row_stride + col_offset;
+            // ---- brick window of the whole warp
+            int lo[3], nb[3];
+            long long vol = 1;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const int mn = __reduce_min_sync(0xffffffffu, X.c[a]) - W;
+                const int mx = __reduce_max_sync(0xffffffffu, X.c[a]) + W;
+                const int sh = a == 0 ? BRICK_XS : (a == 1 ? BRICK_YS : BRICK_ZS);
+                lo[a] = mn >> sh;                       // arithmetic shift = floor division
+                const long long cnt = (long long)(mx >> sh) - lo[a] + 1;
+                nb[a] = (int)(cnt < 1000 ? cnt : 1000);
+                vol *= nb[a];
+            }
+            const bool staged = vol <= RW_CAP_BRICKS;
 
-        if (!fits) {
-            // outlier warp: exact per-candidate traversal straight from global memory
+            if (staged) {
+                // brick (ix,iy,iz) -> win[((iz*nb1)+iy)*nb0+ix][32]; 16-byte async copies, 4 bricks per step
+                const int total = nb[0] * nb[1] * nb[2];
+                __syncwarp();
+                uint32_t slot0 = 0, slot1 = 0;
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const int b = lane + 32 * t;
+                    uint32_t s = 0;
+                    if (b < total) {
+                        const int ix = b % nb[0], iy = (b / nb[0]) % nb[1], iz = b / (nb[0] * nb[1]);
+                        const int gx = lo[0] + ix, gy = lo[1] + iy, gz = lo[2] + iz;
+                        if (gx >= 0 && gx < L.nbx && gy >= 0 && gy < L.nby && gz >= 0 && gz < L.nbz)
+                            s = L.dir[((int64_t)gz * L.nby + gy) * L.nbx + gx];
+                    }
+                    if (t == 0) slot0 = s; else slot1 = s;
+                }
+                const int sub = lane >> 3, chunk = lane & 7;
+                for (int b0 = 0; b0 < total; b0 += 4) {
+                    const int b = b0 + sub;
+                    const uint32_t s = __shfl_sync(0xffffffffu, b < 32 ? slot0 : slot1, b & 31);
+                    if (b < total)
+                        cp_async16(win_addr + (uint32_t)(b * BRICK_WORDS + chunk * 4) * 4u,
+                                   L.pool + (int64_t)s * BRICK_WORDS + chunk * 4, s != 0);
+                }
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                __syncwarp();
+            }
+
             for (int ri = 0; ri < P.n; ++ri) {
-                Moments m;
-                m.n = 0;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) m.s1[k] = 0;
-#pragma unroll
-                for (int k = 0; k < 6; ++k) m.s2[k] = 0;
-                const double radius = P.r[ri];
-                const double r2 = __dmul_rn(radius, radius);
-                const int Wr = P.w[ri];
-                int l3[3], h3[3];
-                bool none = false;
-#pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    l3[a] = c[a] - Wr < 0 ? 0 : c[a] - Wr;
-                    h3[a] = (long long)c[a] + Wr > g.ncell[a] - 1 ? g.ncell[a] - 1 : c[a] + Wr;
-                    none |= (c[a] < -Wr - 1) | (l3[a] > h3[a]);
+                Acc A = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+                if (staged) lane_rows<true>(L, P, ri, X, win, lo, nb[0], nb[1], s_lut, A);
+                else        lane_rows<false>(L, P, ri, X, win, lo, nb[0], nb[1], s_lut, A);
+                if (active) {
+                    // shift the unsigned window coordinates j' = j + W back to offsets from the anchor
+                    Moments m;
+                    const long long n = A.n, w = W;
+                    m.n = n;
+                    m.s1[0] = A.sx - w * n; m.s1[1] = A.sy - w * n; m.s1[2] = A.sz - w * n;
+                    m.s2[0] = A.sxx - 2 * w * A.sx + w * w * n;
+                    m.s2[3] = A.syy - 2 * w * A.sy + w * w * n;
+                    m.s2[5] = A.szz - 2 * w * A.sz + w * w * n;
+                    m.s2[1] = A.sxy - w * A.sx - w * A.sy + w * w * n;
+                    m.s2[2] = A.sxz - w * A.sx - w * A.sz + w * w * n;
+                    m.s2[4] = A.syz - w * A.sy - w * A.sz + w * w * n;
+                    emit_features<OutT>(m, f, g.edge, dst_row + P.col[ri], descriptor_mask);
                 }
-                if (!none)
-                    for (int kz = l3[2]; kz <= h3[2]; ++kz) {
-                        const double dz2 = sqdiff(q[2], cell_centre(kz, g.minc[2], g.edge));
-                        if (dz2 > r2) continue;
-                        for (int ky = l3[1]; ky <= h3[1]; ++ky) {
-                            const double dy2 = sqdiff(q[1], cell_centre(ky, g.minc[1], g.edge));
-                            if (dy2 > r2) continue;
-                            const int word = ((kz & (BRICK_Z - 1)) << BRICK_YS) | (ky & (BRICK_Y - 1));
-                            const int64_t rowb = ((int64_t)(kz >> BRICK_ZS) * L.nby + (ky >> BRICK_YS)) * L.nbx;
-                            for (int bx = l3[0] >> BRICK_XS; bx <= h3[0] >> BRICK_XS; ++bx) {
-                                const uint32_t slot = L.dir[rowb + bx];
-                                if (!slot) continue;
-                                uint32_t w = L.pool[(int64_t)slot * BRICK_WORDS + word];
-                                const int x0 = bx << BRICK_XS;
-                                if (l3[0] > x0) w &= ~0u << (l3[0] - x0);
-                                if (h3[0] < x0 + 31) w &= ~0u >> (x0 + 31 - h3[0]);
-                                while (w) {
-                                    const int b = __ffs(w) - 1;
-                                    w &= w - 1;
-                                    double s = sqdiff(q[0], cell_centre(x0 + b, g.minc[0], g.edge));
-                                    s = __dadd_rn(s, dy2);
-                                    s = __dadd_rn(s, dz2);
-                                    if (s <= r2) {
-                                        const long long jx = x0 + b - c[0], jy = ky - c[1], jz = kz - c[2];
-                                        m.n += 1;
-                                        m.s1[0] += jx; m.s1[1] += jy; m.s1[2] += jz;
-                                        m.s2[0] += jx * jx; m.s2[1] += jx * jy; m.s2[2] += jx * jz;
-                                        m.s2[3] += jy * jy; m.s2[4] += jy * jz; m.s2[5] += jz * jz;
-                                    }
-                                }
-                            }
-                        }
-                    }
-                if (active) emit_features<OutT>(m, f, g.edge, dst + ri * ncol, descriptor_mask);
             }
-            continue;
+            __syncwarp();
         }
-
-        // ---- stage the window: brick (ix,iy,iz) of the window -> win[((iz*nb1)+iy)*nb0+ix][32]
-        const int total = nb[0] * nb[1] * nb[2];
-        __syncwarp();
-        {
-            // each lane resolves the slot of bricks lane, lane+32; then the warp copies brick by brick
-            uint32_t slot0 = 0, slot1 = 0;
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                const int b = lane + 32 * t;
-                uint32_t s = 0;
-                if (b < total) {
-                    const int ix = b % nb[0], iy = (b / nb[0]) % nb[1], iz = b / (nb[0] * nb[1]);
-                    const int gx = lo[0] + ix, gy = lo[1] + iy, gz = lo[2] + iz;
-                    if (gx >= 0 && gx < L.nbx && gy >= 0 && gy < L.nby && gz >= 0 && gz < L.nbz)
-                        s = L.dir[((int64_t)gz * L.nby + gy) * L.nbx + gx];
-                }
-                if (t == 0) slot0 = s; else slot1 = s;
-            }
-            for (int b = 0; b < total; ++b) {
-                const uint32_t s = __shfl_sync(0xffffffffu, b < 32 ? slot0 : slot1, b & 31);
-                win[b * BRICK_WORDS + lane] = s ? L.pool[(int64_t)s * BRICK_WORDS + lane] : 0u;
-            }
-        }
-        __syncwarp();
-
-        // ---- per-lane row walk
-        const int x0 = c[0] - W - lo[0] * BRICK_X;                 // >= 0
-        const int ix = x0 >> 5, sh = x0 & 31;
-        const bool two = sh + 2 * W + 1 > 32;
-        const int y0 = c[1] - W - lo[1] * BRICK_Y;             // window-local cell of row jy' = 0
-        const int z0 = c[2] - W - lo[2] * BRICK_Z;
-        const float fxm = (float)f[0] - 0.5f + (float)W;         // cell j' has its centre at x = j'
-        const float fym = (float)f[1] - 0.5f + (float)W;
-        const float fzm = (float)f[2] - 0.5f + (float)W;
-        const uint32_t rowmask = (2u << (2 * W)) - 1u;
-
-        for (int ri = 0; ri < P.n; ++ri) {
-            const float rho2 = P.rho2[ri], eps_a = P.eps_a[ri], t_min = P.t_min[ri];
-            const int Wr = P.w[ri];
-            Acc A = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-            for (int jz = W - Wr; jz <= W + Wr; ++jz) {
-                const float dz = fzm - (float)jz;
-                const float Tz = rho2 - dz * dz;
-                if (Tz < t_min) continue;
-                const int lz = z0 + jz;
-                const int zoff = ((lz >> BRICK_ZS) * nb[1]) * nb[0] * BRICK_WORDS + ((lz & (BRICK_Z - 1)) << BRICK_YS);
-                int C = 0, SX = 0, SXX = 0, SY = 0, SYY = 0, SXY = 0;
-                for (int jy = W - Wr; jy <= W + Wr; ++jy) {
-                    const float dy = fym - (float)jy;
-                    const float T = Tz - dy * dy;
-                    if (T < t_min) continue;
-                    const int ly = y0 + jy;
-                    const int off = zoff + ((ly >> BRICK_YS) * nb[0] + ix) * BRICK_WORDS + (ly & (BRICK_Y - 1));
-                    const uint32_t w0 = win[off];
-                    const uint32_t w1 = two ? win[off + BRICK_WORDS] : 0u;
-                    const uint32_t bits = __funnelshift_r(w0, w1, sh) & rowmask;
-                    if (bits == 0) continue;
-                    // float32 interval [fxm - s, fxm + s]
-                    const float Tc = fmaxf(T, 0.0f);
-                    const float rs = fminf(rsqrtf(Tc), 1.0e3f);
-                    const float s = Tc * rs;
-                    const float a = fxm - s, b = fxm + s;
-                    const float ca = ceilf(a), fb = floorf(b);
-                    const float delta = eps_a * rs + P.eps_b;
-                    const bool unsure = (ca - a < delta) | (a - (ca - 1.0f) < delta) | (b - fb < delta) |
-                                        (fb + 1.0f - b < delta) | (T < -t_min);
-                    uint32_t m;
-                    if (unsure) {
-                        m = exact_row_mask(g, q[0], q[1], q[2], c[0], c[1] - W + jy, c[2] - W + jz, W, P.r[ri]);
-                    } else {
-                        const int il = max((int)ca, 0), ih = min((int)fb, 2 * W);
-                        m = ih >= il ? (((2u << ih) - 1u) & ~((1u << il) - 1u)) : 0u;
-                    }
-                    m &= bits;
-                    if (m == 0) continue;
-                    // moments of the row through the byte table
-                    int cnt = 0, sx = 0, sxx = 0;
-#pragma unroll
-                    for (int byte = 0; byte < 4; ++byte) {
-                        if (byte * 8 <= 2 * RW_MAX_W && byte * 8 <= 2 * W) {
-                            const uint32_t e = s_lut[(m >> (8 * byte)) & 255u];
-                            const int bc = e & 255, b1 = (e >> 8) & 255, b2 = e >> 16;
-                            cnt += bc;
-                            sx += b1 + 8 * byte * bc;
-                            sxx += b2 + 16 * byte * b1 + 64 * byte * byte * bc;
-                        }
-                    }
-                    C += cnt; SX += sx; SXX += sxx;
-                    SY += jy * cnt; SYY += jy * jy * cnt; SXY += jy * sx;
-                }
-                A.n += C; A.sx += SX; A.sxx += SXX; A.sy += SY; A.syy += SYY; A.sxy += SXY;
-                A.sz += jz * C; A.szz += jz * jz * C; A.sxz += jz * SX; A.syz += jz * SY;
-            }
-            if (active) {
-                // shift the unsigned window coordinates j' = j + W back to offsets from the anchor cell
-                Moments m;
-                const long long n = A.n, w = W;
-                m.n = n;
-                m.s1[0] = A.sx - w * n; m.s1[1] = A.sy - w * n; m.s1[2] = A.sz - w * n;
-                m.s2[0] = A.sxx - 2 * w * A.sx + w * w * n;
-                m.s2[3] = A.syy - 2 * w * A.sy + w * w * n;
-                m.s2[5] = A.szz - 2 * w * A.sz + w * w * n;
-                m.s2[1] = A.sxy - w * A.sx - w * A.sy + w * w * n;
-                m.s2[2] = A.sxz - w * A.sx - w * A.sz + w * w * n;
-                m.s2[4] = A.syz - w * A.sy - w * A.sz + w * w * n;
-                emit_features<OutT>(m, f, g.edge, dst + ri * ncol, descriptor_mask);
-            }
-        }
-        __syncwarp();
     }
 }
 
-int radius_features_rows(const Lattice *lat, const void *query, int dtype, const uint32_t *perm, int64_t nq,
-                         const double *radii, int nr, void *out, int out_dtype, int64_t row_stride, int col_offset,
-                         int descriptor_mask, cudaStream_t stream, bool *handled)
+int rows_param(const Lattice *lat, const double *radii, const int *cols, int nr, RowsParam *P)
 {
-    *handled = false;
-    if (nq <= 0 || nr <= 0) { *handled = true; return NBR_OK; }
     const double e = lat->grid.edge;
-    const int ncol = (descriptor_mask & NBR_DESC_EXTENDED) ? NBR_COLS_EXTENDED : NBR_COLS_REFERENCE;
-    for (int k = 0; k < nr; ++k)
-        if (!(radii[k] / e + 0.5 + 1e-6 < RW_MAX_W + 1)) return NBR_OK;       // window too wide: caller falls back
-    const int blocks = (int)std::min<int64_t>(ceil_div(ceil_div(nq, 32), RW_WARPS), (int64_t)device_sm_count() * 16);
-    for (int base = 0; base < nr; base += RW_MAX_RADII) {
-        RowsParam P;
-        P.n = std::min(RW_MAX_RADII, nr - base);
-        P.wmax = 0;
-        for (int k = 0; k < P.n; ++k) {
-            const double rho = radii[base + k] / e;
-            P.r[k] = radii[base + k];
-            P.rho2[k] = (float)(rho * rho);
-            P.w[k] = (int)floor(rho + 0.5 + 1e-6);
-            P.wmax = std::max(P.wmax, P.w[k]);
-        }
-        for (int k = 0; k < P.n; ++k) {
-            const double mag = (double)P.rho2[k] + (P.wmax + 1.0) * (P.wmax + 1.0);
-            P.eps_a[k] = (float)(8.0 * 5.96e-8 * mag);
-            P.t_min[k] = (float)(-16.0 * 5.96e-8 * mag);
-        }
-        P.eps_b = (float)(4.77e-7 * (P.wmax + 1.0));
-        if (out_dtype == NBR_F32)
-            radius_rows_kernel<float><<<blocks, RW_WARPS * 32, 0, stream>>>(lat->dev(), query, dtype, perm, nq, P,
-                                                                            (float *)out, row_stride,
-                                                                            col_offset + base * ncol, descriptor_mask);
-        else
-            radius_rows_kernel<double><<<blocks, RW_WARPS * 32, 0, stream>>>(lat->dev(), query, dtype, perm, nq, P,
-                                                                             (double *)out, row_stride,
-                                                                             col_offset + base * ncol, descriptor_mask);
-        NBR_LAUNCHED();
+    if (nr > RW_MAX_RADII) return fail(NBR_ERR_INVALID, "rows_param: too many radii in one group");
+    P->n = nr;
+    P->wmax = 0;
+    for (int k = 0; k < nr; ++k) {
+        const double rho = radii[k] / e;
+        P->r[k] = radii[k];
+        P->rho2[k] = (float)(rho * rho);
+        P->w[k] = (int)floor(rho + 0.5 + 1e-6);
+        P->col[k] = cols[k];
+        P->wmax = std::max(P->wmax, P->w[k]);
     }
-    *handled = true;
+    for (int k = 0; k < nr; ++k) {
+        const double mag = (double)P->rho2[k] + (P->wmax + 1.0) * (P->wmax + 1.0);
+        P->eps_a[k] = (float)(8.0 * 5.96e-8 * mag);
+        P->t_min[k] = (float)(-16.0 * 5.96e-8 * mag);
+    }
+    P->eps_b = (float)(4.77e-7 * (P->wmax + 1.0));
+    return NBR_OK;
+}
+
+bool rows_supported(double edge, const double *radii, int nr)
+{
+    for (int k = 0; k < nr; ++k)
+        if (!(radii[k] / edge + 0.5 + 1e-6 < RW_MAX_W + 1)) return false;
+    return true;
+}
+
+// launch->lat / rows / n_lat filled by the caller (host copy); one launch covers every lattice in it
+int radius_rows_launch(const RowsLaunch *launch_host, const void *query, int dtype, const uint32_t *perm, int64_t nq,
+                       void *out, int out_dtype, int64_t row_stride, int descriptor_mask, cudaStream_t stream)
+{
+    if (nq <= 0 || launch_host->n_lat <= 0) return NBR_OK;
+    Scratch dev;
+    NBR_TRY(dev.alloc(sizeof(RowsLaunch), stream));
+    NBR_CUDA(cudaMemcpyAsync(dev.ptr, launch_host, sizeof(RowsLaunch), cudaMemcpyHostToDevice, stream));
+    const int blocks = (int)std::min<int64_t>(ceil_div(ceil_div(nq, 32), RW_WARPS), (int64_t)device_sm_count() * 16);
+    if (out_dtype == NBR_F32)
+        radius_rows_kernel<float><<<blocks, RW_WARPS * 32, 0, stream>>>(dev.as<RowsLaunch>(), query, dtype, perm, nq,
+                                                                        (float *)out, row_stride, descriptor_mask);
+    else
+        radius_rows_kernel<double><<<blocks, RW_WARPS * 32, 0, stream>>>(dev.as<RowsLaunch>(), query, dtype, perm, nq,
+                                                                         (double *)out, row_stride, descriptor_mask);
+    NBR_LAUNCHED();
     return NBR_OK;
 }
 

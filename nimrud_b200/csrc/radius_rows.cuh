@@ -1,0 +1,39 @@
+// radius_rows.cuh -- launch description of the fused row-interval feature kernel.
+#pragma once
+#include "common.cuh"
+#include "lattice.cuh"
+
+namespace nbr {
+
+constexpr int RW_WARPS = 4;
+constexpr int RW_CAP_BRICKS = 48;                 // staged bricks per warp (6 KB)
+constexpr int RW_MAX_W = 9;                       // a single query's window (2*4*6 bricks) must fit the buffer
+constexpr int RW_MAX_RADII = 8;                   // radii per lattice in one launch
+constexpr int RW_MAX_LATTICES = 8;                // lattices per launch
+
+struct RowsParam {
+    double r[RW_MAX_RADII];      // exact radii (float64 test)
+    float rho2[RW_MAX_RADII];    // (r/e)^2
+    float eps_a[RW_MAX_RADII];   // rounding bound: delta = eps_a * min(rsqrt(T), 1e3) + eps_b
+    float t_min[RW_MAX_RADII];   // rows with T < t_min are certainly empty
+    int w[RW_MAX_RADII];         // window half-width of each radius
+    int col[RW_MAX_RADII];       // first output column of each radius
+    float eps_b;
+    int n;
+    int wmax;
+    int pad;
+};
+
+struct RowsLaunch {
+    LatticeDev lat[RW_MAX_LATTICES];
+    RowsParam rows[RW_MAX_LATTICES];
+    int n_lat;
+    int pad[3];
+};
+
+int rows_param(const Lattice *lat, const double *radii, const int *cols, int nr, RowsParam *P);
+bool rows_supported(double edge, const double *radii, int nr);
+int radius_rows_launch(const RowsLaunch *launch_host, const void *query, int dtype, const uint32_t *perm, int64_t nq,
+                       void *out, int out_dtype, int64_t row_stride, int descriptor_mask, cudaStream_t stream);
+
+}  // namespace nbr
