@@ -200,7 +200,7 @@ int multiscale_features(const void *query, int q_dtype, int64_t nq, const void *
         }
         double finest = edges[0];
         for (int s = 1; s < n_scales; ++s) finest = std::min(finest, edges[s]);
-        if (!rc) rc = morton_order(query, q_dtype, nq, qbox, 4.0 * finest, perm.as<uint32_t>(), sorted.ptr, stream);
+        if (!rc) rc = morton_order(query, q_dtype, nq, qbox, 2.0 * finest, perm.as<uint32_t>(), sorted.ptr, stream);
     }
     if (rc) { cleanup(); return rc; }
 

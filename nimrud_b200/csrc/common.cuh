@@ -75,6 +75,7 @@ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 struct GridDev {
     double minc[3];
     double edge;
+    double inv_edge;
     int32_t widths[3];
     int32_t shifts[3];
     int32_t ncell[3];   // number of addressable cells actually spanned by the bounding box

@@ -140,73 +140,118 @@ __device__ __forceinline__ void eig3_unit_trace(const double a[6], double l[3], 
     }
 }
 
-// writes 4 (reference) or 16 (extended) columns at out[0..]
+// the columns from: n, the centroid distance, and the UNNORMALISED matrix a = n*S2 - S1*S1^T
+// (exact integers converted to double).  writes 4 (reference) or 16 (extended) columns at out[0..]
 template <typename OutT>
-__device__ __forceinline__ void emit_features(const Moments &m, const double f[3], double edge, OutT *out,
-                                              int descriptor_mask)
+__device__ __forceinline__ void emit_core(long long n_int, double centroid, double a[6], double edge, OutT *out,
+                                          int descriptor_mask)
 {
     const int ncol = (descriptor_mask & NBR_DESC_EXTENDED) ? NBR_COLS_EXTENDED : NBR_COLS_REFERENCE;
-    double col[NBR_COLS_EXTENDED];
+    const double n = (double)n_int;
+    double l0 = 0.0, l1 = 0.0;
+    double ext[12];
 #pragma unroll
-    for (int i = 0; i < NBR_COLS_EXTENDED; ++i) col[i] = 0.0;
-    const double n = (double)m.n;
-    col[0] = n;
-    if (m.n > 0) {
-        const double inv = 1.0 / n;
-        const double dx = (f[0] - 0.5 - (double)m.s1[0] * inv) * edge;
-        const double dy = (f[1] - 0.5 - (double)m.s1[1] * inv) * edge;
-        const double dz = (f[2] - 0.5 - (double)m.s1[2] * inv) * edge;
-        col[1] = sqrt(dx * dx + dy * dy + dz * dz);
-    }
-    if (m.n >= 2) {
-        // exact integers: n*S2 - S1*S1^T  (= n^2 * biased covariance in cell units)
-        double a[6];
-        a[0] = (double)(m.n * m.s2[0] - m.s1[0] * m.s1[0]);
-        a[1] = (double)(m.n * m.s2[1] - m.s1[0] * m.s1[1]);
-        a[2] = (double)(m.n * m.s2[2] - m.s1[0] * m.s1[2]);
-        a[3] = (double)(m.n * m.s2[3] - m.s1[1] * m.s1[1]);
-        a[4] = (double)(m.n * m.s2[4] - m.s1[1] * m.s1[2]);
-        a[5] = (double)(m.n * m.s2[5] - m.s1[2] * m.s1[2]);
+    for (int i = 0; i < 12; ++i) ext[i] = 0.0;
+    if (n_int >= 2) {
         const double tr = a[0] + a[3] + a[5];
         if (tr > 0.0) {
-            const double it = 1.0 / tr;
+            // 1/tr: float32 seed + one Newton step (relative error ~1e-14)
+            const double r0 = (double)__frcp_rn((float)tr);
+            const double it = r0 * (2.0 - tr * r0);
 #pragma unroll
             for (int i = 0; i < 6; ++i) a[i] *= it;
             double l[3], v[3];
             eig3_unit_trace(a, l, v);
-            col[2] = l[0];
-            col[3] = l[1];
-            if ((descriptor_mask & NBR_DESC_EXTENDED) && m.n >= 3) {
+            l0 = l[0];
+            l1 = l[1];
+            if ((descriptor_mask & NBR_DESC_EXTENDED) && n_int >= 3) {
                 const double e1 = fmax(l[0], 0.0), e2 = fmax(l[1], 0.0), e3 = fmax(l[2], 0.0);
                 const double i1 = 1.0 / e1;
-                col[4] = (e1 - e2) * i1;               // linearity
-                col[5] = (e2 - e3) * i1;               // planarity
-                col[6] = e3 * i1;                      // sphericity
-                col[7] = cbrt(e1 * e2 * e3);           // omnivariance
-                col[8] = (e1 - e3) * i1;               // anisotropy
+                ext[0] = (e1 - e2) * i1;               // linearity
+                ext[1] = (e2 - e3) * i1;               // planarity
+                ext[2] = e3 * i1;                      // sphericity
+                ext[3] = cbrt(e1 * e2 * e3);           // omnivariance
+                ext[4] = (e1 - e3) * i1;               // anisotropy
                 double ent = 0.0;
                 if (e1 > 0) ent -= e1 * log(e1);
                 if (e2 > 0) ent -= e2 * log(e2);
                 if (e3 > 0) ent -= e3 * log(e3);
-                col[9] = ent;                          // eigenentropy
-                col[10] = e3;                          // change of curvature
+                ext[5] = ent;                          // eigenentropy
+                ext[6] = e3;                           // change of curvature
                 if (v[2] < 0 || (v[2] == 0 && (v[1] < 0 || (v[1] == 0 && v[0] < 0)))) {
                     v[0] = -v[0]; v[1] = -v[1]; v[2] = -v[2];
                 }
-                col[11] = 1.0 - fabs(v[2]);            // verticality
-                col[12] = v[0]; col[13] = v[1]; col[14] = v[2];
-                col[15] = tr * edge * edge / (n * (n - 1.0));   // trace of the ddof=1 covariance
+                ext[7] = 1.0 - fabs(v[2]);             // verticality
+                ext[8] = v[0]; ext[9] = v[1]; ext[10] = v[2];
+                ext[11] = tr * edge * edge / (n * (n - 1.0));   // trace of the ddof=1 covariance
             }
         }
     }
-    for (int i = 0; i < ncol; ++i) out[i] = (OutT)col[i];
+    out[0] = (OutT)n;
+    out[1] = (OutT)centroid;
+    out[2] = (OutT)l0;
+    out[3] = (OutT)l1;
+    if (ncol > 4) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) out[4 + i] = (OutT)ext[i];
+    }
+}
+
+// int64 moments relative to the anchor cell (exact kernel, kNN)
+template <typename OutT>
+__device__ __forceinline__ void emit_features(const Moments &m, const double f[3], double edge, OutT *out,
+                                              int descriptor_mask)
+{
+    double centroid = 0.0;
+    if (m.n > 0) {
+        const double inv = 1.0 / (double)m.n;
+        const double dx = (f[0] - 0.5 - (double)m.s1[0] * inv) * edge;
+        const double dy = (f[1] - 0.5 - (double)m.s1[1] * inv) * edge;
+        const double dz = (f[2] - 0.5 - (double)m.s1[2] * inv) * edge;
+        centroid = sqrt(dx * dx + dy * dy + dz * dz);
+    }
+    double a[6];
+    a[0] = (double)(m.n * m.s2[0] - m.s1[0] * m.s1[0]);
+    a[1] = (double)(m.n * m.s2[1] - m.s1[0] * m.s1[1]);
+    a[2] = (double)(m.n * m.s2[2] - m.s1[0] * m.s1[2]);
+    a[3] = (double)(m.n * m.s2[3] - m.s1[1] * m.s1[1]);
+    a[4] = (double)(m.n * m.s2[4] - m.s1[1] * m.s1[2]);
+    a[5] = (double)(m.n * m.s2[5] - m.s1[2] * m.s1[2]);
+    emit_core<OutT>(m.n, centroid, a, edge, out, descriptor_mask);
+}
+
+// int32 moments in WINDOW coordinates j' = j + W (row kernel).  the matrix n*S2 - S1*S1^T does not
+// depend on the origin, only the centroid needs the shift.  fm[a] = f[a] - 0.5 + W (float32): the query
+// in window units.  SMALL: every product fits int32 (W <= 6).
+template <typename OutT, bool SMALL>
+__device__ __forceinline__ void emit_features_window(int n, int sx, int sy, int sz, int sxx, int sxy, int sxz, int syy,
+                                                     int syz, int szz, float fxm, float fym, float fzm, double edge,
+                                                     OutT *out, int descriptor_mask)
+{
+    double centroid = 0.0;
+    if (n > 0) {
+        const float inv = 1.0f / (float)n;
+        const float dx = fxm - (float)sx * inv, dy = fym - (float)sy * inv, dz = fzm - (float)sz * inv;
+        centroid = (double)sqrtf(dx * dx + dy * dy + dz * dz) * edge;
+    }
+    double a[6];
+    if (SMALL) {
+        a[0] = (double)(n * sxx - sx * sx); a[1] = (double)(n * sxy - sx * sy); a[2] = (double)(n * sxz - sx * sz);
+        a[3] = (double)(n * syy - sy * sy); a[4] = (double)(n * syz - sy * sz); a[5] = (double)(n * szz - sz * sz);
+    } else {
+        const long long N = n, X = sx, Y = sy, Z = sz;
+        a[0] = (double)(N * sxx - X * X); a[1] = (double)(N * sxy - X * Y); a[2] = (double)(N * sxz - X * Z);
+        a[3] = (double)(N * syy - Y * Y); a[4] = (double)(N * syz - Y * Z); a[5] = (double)(N * szz - Z * Z);
+    }
+    emit_core<OutT>(n, centroid, a, edge, out, descriptor_mask);
 }
 
 // anchor cell and fractional position of a query on one axis.  c is clamped so that far-away
 // queries cannot overflow; f in [0,1) when unclamped.
-__device__ __forceinline__ void query_anchor(double q, double minc, double edge, int &c, double &f)
+__device__ __forceinline__ void query_anchor(double q, double minc, double inv_edge, int &c, double &f)
 {
-    const double u = __ddiv_rn(__dsub_rn(q, minc), edge);
+    // the anchor only positions the window, so a reciprocal multiply is as good as the division
+    const double u = (q - minc) * inv_edge;
     double cf = floor(u);
     cf = fmin(fmax(cf, -1.0e9), 1.0e9);
     c = (int)cf;

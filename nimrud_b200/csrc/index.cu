@@ -124,6 +124,7 @@ int grid_to_dev(const nbr_grid *g, GridDev *d)
         d->ncell[a] = (int32_t)cells;
     }
     d->edge = g->edge;
+    d->inv_edge = 1.0 / g->edge;
     d->ndim = g->ndim;
     return NBR_OK;
 }

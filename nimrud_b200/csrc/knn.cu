@@ -77,7 +77,7 @@ knn_kernel(LatticeDev L, const void *__restrict__ query, int dtype, int64_t nq, 
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             q[a] = load_coord(query, dtype, qi, 3, a);
-            query_anchor(q[a], g.minc[a], g.edge, c[a], f[a]);
+            query_anchor(q[a], g.minc[a], g.inv_edge, c[a], f[a]);
         }
         int have = 0;
         long long rho = 2;

@@ -75,7 +75,7 @@ radius_features_exact_kernel(LatticeDev L, const void *__restrict__ query, int d
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         q[a] = load_coord(query, dtype, i, 3, a);
-        query_anchor(q[a], L.g.minc[a], L.g.edge, c[a], f[a]);
+        query_anchor(q[a], L.g.minc[a], L.g.inv_edge, c[a], f[a]);
     }
     Moments m;
     m.n = 0;
@@ -131,7 +131,7 @@ radius_count_kernel(LatticeDev L, const void *__restrict__ query, int dtype, int
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         q[a] = load_coord(query, dtype, i, 3, a);
-        query_anchor(q[a], L.g.minc[a], L.g.edge, c[a], f);
+        query_anchor(q[a], L.g.minc[a], L.g.inv_edge, c[a], f);
     }
     long long n = 0;
     for_each_member(L, q, c, radius, [&](int, int, int, uint32_t, int, int) { ++n; });
@@ -149,7 +149,7 @@ radius_fill_kernel(LatticeDev L, const void *__restrict__ query, int dtype, int6
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         q[a] = load_coord(query, dtype, i, 3, a);
-        query_anchor(q[a], L.g.minc[a], L.g.edge, c[a], f);
+        query_anchor(q[a], L.g.minc[a], L.g.inv_edge, c[a], f);
     }
     int32_t *dst = indices + offsets[i];
     for_each_member(L, q, c, radius, [&](int, int, int, uint32_t slot, int word, int b) {

@@ -22,6 +22,8 @@
 #include "lattice.cuh"
 #include "radius_rows.cuh"
 
+#include <stdlib.h>
+
 namespace nbr {
 
 // byte -> count | sum(pos) << 8 | sum(pos^2) << 16     (positions 0..7)
@@ -32,6 +34,17 @@ __device__ __forceinline__ uint32_t byte_moments(uint32_t b)
     for (int i = 0; i < 8; ++i)
         if (b & (1u << i)) { cnt += 1; s1 += i; s2 += i * i; }
     return cnt | (s1 << 8) | (s2 << 16);
+}
+
+// 7-bit row -> count | sum(pos) << 10 | sum(pos^2) << 20: fields wide enough to add up a whole z-slab
+// of a W <= 3 window (49 cells) and its jy-weighted sums without unpacking
+__device__ __forceinline__ uint32_t row7_moments(uint32_t b)
+{
+    uint32_t cnt = 0, s1 = 0, s2 = 0;
+#pragma unroll
+    for (int i = 0; i < 7; ++i)
+        if (b & (1u << i)) { cnt += 1; s1 += i; s2 += i * i; }
+    return cnt | (s1 << 10) | (s2 << 20);
 }
 
 struct Acc {
@@ -105,7 +118,7 @@ __device__ __forceinline__ void row_moments(const GridDev &g, const RowsParam &P
 // !STAGED: rows come straight from the directory + pool in global memory (incoherent warps); empty
 //          bricks are skipped through the directory.
 template <bool STAGED>
-__device__ __forceinline__ void lane_rows(const LatticeDev &L, const RowsParam &P, int ri, const LaneCtx &X,
+__device__ __noinline__ void lane_rows(const LatticeDev &L, const RowsParam &P, int ri, const LaneCtx &X,
                                           const uint32_t *win, const int lo[3], int nb0, int nb1,
                                           const uint32_t *s_lut, Acc &A)
 {
@@ -169,6 +182,178 @@ __device__ __forceinline__ void lane_rows(const LatticeDev &L, const RowsParam &
     }
 }
 
+// ---- W <= 3 (r/e < 3.5) specialisation ---------------------------------------------------------
+// the 2W+1 rows of a z-slab are processed as one straight-line block (no per-row branches, so the
+// rows overlap in the pipeline); a slab is summed in packed form; rows whose float32 interval is too
+// close to a cell boundary are redone exactly in a (rare) tail.
+template <int W>
+struct SmallCtx {
+    static constexpr int N = 2 * W + 1;
+    float dy2[N];
+    float rho2, t_min, eps_a, eps_b;
+    double radius;
+};
+
+// one slab: bits[jy] = occupancy of row jy (bit t <-> cell cx - W + t)
+template <int W>
+__device__ __forceinline__ void slab_small(const GridDev &g, const SmallCtx<W> &S, const LaneCtx &X, int jz, float Tz,
+                                           const uint32_t (&bits)[2 * W + 1], const uint32_t *s_lut10, Acc &A)
+{
+    constexpr int N = 2 * W + 1;
+    uint32_t Pk = 0, Qk = 0, unsure_rows = 0;
+    int R = 0;
+#pragma unroll
+    for (int jy = 0; jy < N; ++jy) {
+        const float T = Tz - S.dy2[jy];
+        const float Tc = fmaxf(T, 0.0f);
+        const float rs = fminf(rsqrtf(Tc), 1.0e3f);
+        const float s = Tc * rs;
+        const float a = X.fxm - s, b = X.fxm + s;
+        const float ca = ceilf(a), fb = floorf(b);
+        const float delta = S.eps_a * rs + S.eps_b;
+        const float da = ca - a, db = b - fb;                      // both in [0, 1)
+        const bool unsure = (fminf(da, db) < delta) | (fmaxf(da, db) > 1.0f - delta) | (T < -S.t_min);
+        const int il = max((int)ca, 0), ih = (int)fb;              // ih in [0, 2W+1] by construction
+        uint32_t m = ((2u << ih) - 1u) & ~((1u << il) - 1u) & bits[jy];
+        if (T < S.t_min) m = 0;
+        if (unsure & (bits[jy] != 0) & (T >= S.t_min)) { unsure_rows |= 1u << jy; m = 0; }
+        const uint32_t e = s_lut10[m];
+        Pk += e;
+        Qk += jy * e;
+        R += jy * jy * (int)(e & 1023u);
+    }
+    if (unsure_rows) {                                             // rare: exact float64 redo of those rows
+#pragma unroll
+        for (int jy = 0; jy < N; ++jy)
+            if (unsure_rows & (1u << jy)) {
+                const uint32_t m = exact_row_mask(g, X.q[0], X.q[1], X.q[2], X.c[0], X.c[1] - W + jy, X.c[2] - W + jz, W,
+                                                  S.radius) & bits[jy];
+                const uint32_t e = s_lut10[m];
+                Pk += e;
+                Qk += jy * e;
+                R += jy * jy * (int)(e & 1023u);
+            }
+    }
+    const int C = Pk & 1023, SX = (Pk >> 10) & 1023, SXX = Pk >> 20;
+    const int SY = Qk & 1023, SXY = (Qk >> 10) & 1023;
+    A.n += C; A.sx += SX; A.sxx += SXX; A.sy += SY; A.syy += R; A.sxy += SXY;
+    A.sz += jz * C; A.szz += jz * jz * C; A.sxz += jz * SX; A.syz += jz * SY;
+}
+
+template <int W>
+__device__ __forceinline__ void small_ctx_init(SmallCtx<W> &S, const RowsParam &P, int ri, const LaneCtx &X)
+{
+#pragma unroll
+    for (int j = 0; j < 2 * W + 1; ++j) {
+        const float dy = X.fym - (float)j;
+        S.dy2[j] = dy * dy;
+    }
+    S.rho2 = P.rho2[ri]; S.t_min = P.t_min[ri]; S.eps_a = P.eps_a[ri]; S.eps_b = P.eps_b;
+    S.radius = P.r[ri];
+}
+
+// rows from the warp's staged window
+template <int W>
+__device__ __forceinline__ void lane_rows_small(const LatticeDev &L, const RowsParam &P, int ri, const LaneCtx &X,
+                                                const uint32_t *win, const int lo[3], int nb0, int nb1,
+                                                const uint32_t *s_lut10, Acc &A)
+{
+    constexpr int N = 2 * W + 1;
+    SmallCtx<W> S;
+    small_ctx_init<W>(S, P, ri, X);
+    const uint32_t rowmask = (1u << N) - 1u;
+    const int xa = X.c[0] - W;
+    const int sh = xa & 31;
+    const bool two = sh + N > 32;
+    const int ixs = (xa >> BRICK_XS) - lo[0];
+    const int ya = X.c[1] - W, za = X.c[2] - W;
+    int yoff[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const int ay = ya + j;
+        yoff[j] = (((ay >> BRICK_YS) - lo[1]) * nb0 + ixs) * BRICK_WORDS + (ay & (BRICK_Y - 1));
+    }
+    const int zstride = nb1 * nb0 * BRICK_WORDS;
+    for (int jz = 0; jz < N; ++jz) {
+        const float dz = X.fzm - (float)jz;
+        const float Tz = S.rho2 - dz * dz;
+        if (Tz < S.t_min) continue;
+        const int az = za + jz;
+        const int zoff = ((az >> BRICK_ZS) - lo[2]) * zstride + ((az & (BRICK_Z - 1)) << BRICK_YS);
+        uint32_t bits[N];
+        uint32_t any = 0;
+#pragma unroll
+        for (int jy = 0; jy < N; ++jy) {
+            const int off = zoff + yoff[jy];
+            const uint32_t w0 = win[off];
+            const uint32_t w1 = two ? win[off + BRICK_WORDS] : 0u;
+            bits[jy] = __funnelshift_r(w0, w1, sh) & rowmask;
+            any |= bits[jy];
+        }
+        if (any == 0) continue;
+        slab_small<W>(L.g, S, X, jz, Tz, bits, s_lut10, A);
+    }
+}
+
+// rows straight from global memory (warps whose joint window does not fit the staging buffer): the
+// <= 2 x 2 x 3 bricks of the lane's own window are resolved through the directory first, all loads in
+// flight together; slabs whose bricks are all empty are skipped without touching the pool.
+template <int W>
+__device__ __forceinline__ void lane_rows_small_direct(const LatticeDev &L, const RowsParam &P, int ri,
+                                                       const LaneCtx &X, const uint32_t *s_lut10, Acc &A)
+{
+    constexpr int N = 2 * W + 1;
+    SmallCtx<W> S;
+    small_ctx_init<W>(S, P, ri, X);
+    const uint32_t rowmask = (1u << N) - 1u;
+    const int xa = X.c[0] - W;
+    const int sh = xa & 31;
+    const bool two = sh + N > 32;
+    const int bx0 = xa >> BRICK_XS;
+    const int ya = X.c[1] - W, za = X.c[2] - W;
+    const int by0 = ya >> BRICK_YS, bz0 = za >> BRICK_ZS;
+    // slots[iz][iy][ix]
+    uint32_t slot[3][2][2];
+#pragma unroll
+    for (int iz = 0; iz < 3; ++iz)
+#pragma unroll
+        for (int iy = 0; iy < 2; ++iy)
+#pragma unroll
+            for (int ix = 0; ix < 2; ++ix) {
+                const int gx = bx0 + ix, gy = by0 + iy, gz = bz0 + iz;
+                const bool ok = (ix == 0 || two) && gx >= 0 && gx < L.nbx && gy >= 0 && gy < L.nby && gz >= 0 && gz < L.nbz;
+                slot[iz][iy][ix] = ok ? L.dir[((int64_t)gz * L.nby + gy) * L.nbx + gx] : 0u;
+            }
+    for (int jz = 0; jz < N; ++jz) {
+        const float dz = X.fzm - (float)jz;
+        const float Tz = S.rho2 - dz * dz;
+        if (Tz < S.t_min) continue;
+        const int az = za + jz;
+        const int iz = (az >> BRICK_ZS) - bz0;                     // 0..2
+        const uint32_t s00 = iz == 0 ? slot[0][0][0] : (iz == 1 ? slot[1][0][0] : slot[2][0][0]);
+        const uint32_t s01 = iz == 0 ? slot[0][0][1] : (iz == 1 ? slot[1][0][1] : slot[2][0][1]);
+        const uint32_t s10 = iz == 0 ? slot[0][1][0] : (iz == 1 ? slot[1][1][0] : slot[2][1][0]);
+        const uint32_t s11 = iz == 0 ? slot[0][1][1] : (iz == 1 ? slot[1][1][1] : slot[2][1][1]);
+        if ((s00 | s01 | s10 | s11) == 0) continue;
+        const int wz = (az & (BRICK_Z - 1)) << BRICK_YS;
+        uint32_t bits[N];
+        uint32_t any = 0;
+#pragma unroll
+        for (int jy = 0; jy < N; ++jy) {
+            const int ay = ya + jy;
+            const bool up = (ay >> BRICK_YS) != by0;
+            const uint32_t sa = up ? s10 : s00, sb = up ? s11 : s01;
+            const int word = wz | (ay & (BRICK_Y - 1));
+            const uint32_t w0 = sa ? L.pool[(int64_t)sa * BRICK_WORDS + word] : 0u;
+            const uint32_t w1 = sb ? L.pool[(int64_t)sb * BRICK_WORDS + word] : 0u;
+            bits[jy] = __funnelshift_r(w0, w1, sh) & rowmask;
+            any |= bits[jy];
+        }
+        if (any == 0) continue;
+        slab_small<W>(L.g, S, X, jz, Tz, bits, s_lut10, A);
+    }
+}
+
 __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *gptr, bool valid)
 {
     const int src_bytes = valid ? 16 : 0;      // 0 -> the 16 bytes are zero-filled
@@ -176,15 +361,17 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *gptr,
 }
 
 template <typename OutT>
-__global__ void __launch_bounds__(RW_WARPS * 32)
+__global__ void __launch_bounds__(RW_WARPS * 32, 4)
 radius_rows_kernel(const RowsLaunch *__restrict__ launch, const void *__restrict__ query, int dtype,
                    const uint32_t *__restrict__ perm, int64_t nq, OutT *__restrict__ out, int64_t row_stride,
                    int descriptor_mask)
 {
     __shared__ uint32_t s_lut[256];
+    __shared__ uint32_t s_lut10[128];
     __shared__ __align__(16) uint32_t s_win[RW_WARPS][RW_CAP_BRICKS * BRICK_WORDS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = byte_moments(i);
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) s_lut10[i] = row7_moments(i);
     __syncthreads();
 
     uint32_t *win = s_win[warp];
@@ -208,7 +395,7 @@ radius_rows_kernel(const RowsLaunch *__restrict__ launch, const void *__restrict
             const GridDev &g = L.g;
             double f[3];
 #pragma unroll
-            for (int a = 0; a < 3; ++a) query_anchor(X.q[a], g.minc[a], g.edge, X.c[a], f[a]);
+            for (int a = 0; a < 3; ++a) query_anchor(X.q[a], g.minc[a], g.inv_edge, X.c[a], f[a]);
             const int W = P.wmax;
             X.W = W;
             X.fxm = (float)f[0] - 0.5f + (float)W;
@@ -229,6 +416,11 @@ radius_rows_kernel(const RowsLaunch *__restrict__ launch, const void *__restrict
                 vol *= nb[a];
             }
             const bool staged = vol <= RW_CAP_BRICKS;
+            if (launch->stats && lane == 0) {
+                unsigned long long *st = launch->stats + li * 8;
+                atomicAdd(st + (staged ? 0 : 1), 1ull);
+                if (staged) atomicAdd(st + 2, (unsigned long long)vol);
+            }
 
             if (staged) {
                 // brick (ix,iy,iz) -> win[((iz*nb1)+iy)*nb0+ix][32]; 16-byte async copies, 4 bricks per step
@@ -261,21 +453,23 @@ radius_rows_kernel(const RowsLaunch *__restrict__ launch, const void *__restrict
 
             for (int ri = 0; ri < P.n; ++ri) {
                 Acc A = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-                if (staged) lane_rows<true>(L, P, ri, X, win, lo, nb[0], nb[1], s_lut, A);
-                else        lane_rows<false>(L, P, ri, X, win, lo, nb[0], nb[1], s_lut, A);
+                if (staged) {
+                    if (W == 3)      lane_rows_small<3>(L, P, ri, X, win, lo, nb[0], nb[1], s_lut10, A);
+                    else if (W == 2) lane_rows_small<2>(L, P, ri, X, win, lo, nb[0], nb[1], s_lut10, A);
+                    else             lane_rows<true>(L, P, ri, X, win, lo, nb[0], nb[1], s_lut, A);
+                } else {
+                    if (W == 3)      lane_rows_small_direct<3>(L, P, ri, X, s_lut10, A);
+                    else if (W == 2) lane_rows_small_direct<2>(L, P, ri, X, s_lut10, A);
+                    else             lane_rows<false>(L, P, ri, X, win, lo, nb[0], nb[1], s_lut, A);
+                }
                 if (active) {
-                    // shift the unsigned window coordinates j' = j + W back to offsets from the anchor
-                    Moments m;
-                    const long long n = A.n, w = W;
-                    m.n = n;
-                    m.s1[0] = A.sx - w * n; m.s1[1] = A.sy - w * n; m.s1[2] = A.sz - w * n;
-                    m.s2[0] = A.sxx - 2 * w * A.sx + w * w * n;
-                    m.s2[3] = A.syy - 2 * w * A.sy + w * w * n;
-                    m.s2[5] = A.szz - 2 * w * A.sz + w * w * n;
-                    m.s2[1] = A.sxy - w * A.sx - w * A.sy + w * w * n;
-                    m.s2[2] = A.sxz - w * A.sx - w * A.sz + w * w * n;
-                    m.s2[4] = A.syz - w * A.sy - w * A.sz + w * w * n;
-                    emit_features<OutT>(m, f, g.edge, dst_row + P.col[ri], descriptor_mask);
+                    OutT *dst = dst_row + P.col[ri];
+                    if (W <= 6)
+                        emit_features_window<OutT, true>(A.n, A.sx, A.sy, A.sz, A.sxx, A.sxy, A.sxz, A.syy, A.syz, A.szz,
+                                                         X.fxm, X.fym, X.fzm, g.edge, dst, descriptor_mask);
+                    else
+                        emit_features_window<OutT, false>(A.n, A.sx, A.sy, A.sz, A.sxx, A.sxy, A.sxz, A.syy, A.syz, A.szz,
+                                                          X.fxm, X.fym, X.fzm, g.edge, dst, descriptor_mask);
                 }
             }
             __syncwarp();
@@ -318,9 +512,18 @@ int radius_rows_launch(const RowsLaunch *launch_host, const void *query, int dty
                        void *out, int out_dtype, int64_t row_stride, int descriptor_mask, cudaStream_t stream)
 {
     if (nq <= 0 || launch_host->n_lat <= 0) return NBR_OK;
-    Scratch dev;
+    Scratch dev, stats;
     NBR_TRY(dev.alloc(sizeof(RowsLaunch), stream));
-    NBR_CUDA(cudaMemcpyAsync(dev.ptr, launch_host, sizeof(RowsLaunch), cudaMemcpyHostToDevice, stream));
+    RowsLaunch copy = *launch_host;
+    const bool want_stats = getenv("NBR_ROW_STATS") != nullptr;
+    if (want_stats) {
+        NBR_TRY(stats.alloc(sizeof(unsigned long long) * 8 * RW_MAX_LATTICES, stream));
+        NBR_CUDA(cudaMemsetAsync(stats.ptr, 0, sizeof(unsigned long long) * 8 * RW_MAX_LATTICES, stream));
+        copy.stats = stats.as<unsigned long long>();
+    } else {
+        copy.stats = nullptr;
+    }
+    NBR_CUDA(cudaMemcpyAsync(dev.ptr, &copy, sizeof(RowsLaunch), cudaMemcpyHostToDevice, stream));
     const int blocks = (int)std::min<int64_t>(ceil_div(ceil_div(nq, 32), RW_WARPS), (int64_t)device_sm_count() * 16);
     if (out_dtype == NBR_F32)
         radius_rows_kernel<float><<<blocks, RW_WARPS * 32, 0, stream>>>(dev.as<RowsLaunch>(), query, dtype, perm, nq,
@@ -329,6 +532,15 @@ int radius_rows_launch(const RowsLaunch *launch_host, const void *query, int dty
         radius_rows_kernel<double><<<blocks, RW_WARPS * 32, 0, stream>>>(dev.as<RowsLaunch>(), query, dtype, perm, nq,
                                                                          (double *)out, row_stride, descriptor_mask);
     NBR_LAUNCHED();
+    if (want_stats) {
+        unsigned long long h[8 * RW_MAX_LATTICES];
+        NBR_CUDA(cudaMemcpyAsync(h, stats.ptr, sizeof(h), cudaMemcpyDeviceToHost, stream));
+        NBR_CUDA(cudaStreamSynchronize(stream));
+        for (int l = 0; l < launch_host->n_lat; ++l)
+            fprintf(stderr, "[nbr row stats] lattice %d edge %.3g W %d: staged warps %llu (avg %.1f bricks), direct warps %llu\n",
+                    l, launch_host->lat[l].g.edge, launch_host->rows[l].wmax, h[l * 8], h[l * 8] ? (double)h[l * 8 + 2] / h[l * 8] : 0.0,
+                    h[l * 8 + 1]);
+    }
     return NBR_OK;
 }
 

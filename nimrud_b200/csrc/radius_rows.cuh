@@ -27,8 +27,9 @@ struct RowsParam {
 struct RowsLaunch {
     LatticeDev lat[RW_MAX_LATTICES];
     RowsParam rows[RW_MAX_LATTICES];
+    unsigned long long *stats;   // optional diagnostics (NBR_ROW_STATS=1): per lattice 8 counters
     int n_lat;
-    int pad[3];
+    int pad;
 };
 
 int rows_param(const Lattice *lat, const double *radii, const int *cols, int nr, RowsParam *P);
