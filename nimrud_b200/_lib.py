@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libnimrud_b200.so")
+LIB_PATH = os.environ.get("NIMRUD_B200_LIB") or os.path.join(HERE, "lib", "libnimrud_b200.so")   # env: A/B builds
 
 OK = 0
 ERR_INVALID, ERR_TOO_FEW_POINTS, ERR_ADDRESS_BITS, ERR_CUDA, ERR_UNSUPPORTED, ERR_OUT_OF_BOUNDS = 1, 2, 3, 4, 5, 6

@@ -140,6 +140,30 @@ __device__ __forceinline__ void eig3_unit_trace(const double a[6], double l[3], 
     }
 }
 
+// the 12 extension columns (not on the reference path; kept out of line so the hot kernels stay small)
+static __device__ __noinline__ void extended_descriptors(const double l[3], double v[3], double trace, double ext[12])
+{
+    const double e1 = fmax(l[0], 0.0), e2 = fmax(l[1], 0.0), e3 = fmax(l[2], 0.0);
+    const double i1 = 1.0 / e1;
+    ext[0] = (e1 - e2) * i1;               // linearity
+    ext[1] = (e2 - e3) * i1;               // planarity
+    ext[2] = e3 * i1;                      // sphericity
+    ext[3] = cbrt(e1 * e2 * e3);           // omnivariance
+    ext[4] = (e1 - e3) * i1;               // anisotropy
+    double ent = 0.0;
+    if (e1 > 0) ent -= e1 * log(e1);
+    if (e2 > 0) ent -= e2 * log(e2);
+    if (e3 > 0) ent -= e3 * log(e3);
+    ext[5] = ent;                          // eigenentropy
+    ext[6] = e3;                           // change of curvature
+    if (v[2] < 0 || (v[2] == 0 && (v[1] < 0 || (v[1] == 0 && v[0] < 0)))) {
+        v[0] = -v[0]; v[1] = -v[1]; v[2] = -v[2];
+    }
+    ext[7] = 1.0 - fabs(v[2]);             // verticality
+    ext[8] = v[0]; ext[9] = v[1]; ext[10] = v[2];
+    ext[11] = trace;                       // trace of the ddof=1 covariance
+}
+
 // the columns from: n, the centroid distance, and the UNNORMALISED matrix a = n*S2 - S1*S1^T
 // (exact integers converted to double).  writes 4 (reference) or 16 (extended) columns at out[0..]
 template <typename OutT>
@@ -164,27 +188,8 @@ __device__ __forceinline__ void emit_core(long long n_int, double centroid, doub
             eig3_unit_trace(a, l, v);
             l0 = l[0];
             l1 = l[1];
-            if ((descriptor_mask & NBR_DESC_EXTENDED) && n_int >= 3) {
-                const double e1 = fmax(l[0], 0.0), e2 = fmax(l[1], 0.0), e3 = fmax(l[2], 0.0);
-                const double i1 = 1.0 / e1;
-                ext[0] = (e1 - e2) * i1;               // linearity
-                ext[1] = (e2 - e3) * i1;               // planarity
-                ext[2] = e3 * i1;                      // sphericity
-                ext[3] = cbrt(e1 * e2 * e3);           // omnivariance
-                ext[4] = (e1 - e3) * i1;               // anisotropy
-                double ent = 0.0;
-                if (e1 > 0) ent -= e1 * log(e1);
-                if (e2 > 0) ent -= e2 * log(e2);
-                if (e3 > 0) ent -= e3 * log(e3);
-                ext[5] = ent;                          // eigenentropy
-                ext[6] = e3;                           // change of curvature
-                if (v[2] < 0 || (v[2] == 0 && (v[1] < 0 || (v[1] == 0 && v[0] < 0)))) {
-                    v[0] = -v[0]; v[1] = -v[1]; v[2] = -v[2];
-                }
-                ext[7] = 1.0 - fabs(v[2]);             // verticality
-                ext[8] = v[0]; ext[9] = v[1]; ext[10] = v[2];
-                ext[11] = tr * edge * edge / (n * (n - 1.0));   // trace of the ddof=1 covariance
-            }
+            if ((descriptor_mask & NBR_DESC_EXTENDED) && n_int >= 3)
+                extended_descriptors(l, v, tr * edge * edge / (n * (n - 1.0)), ext);
         }
     }
     out[0] = (OutT)n;
@@ -223,10 +228,10 @@ __device__ __forceinline__ void emit_features(const Moments &m, const double f[3
 // int32 moments in WINDOW coordinates j' = j + W (row kernel).  the matrix n*S2 - S1*S1^T does not
 // depend on the origin, only the centroid needs the shift.  fm[a] = f[a] - 0.5 + W (float32): the query
 // in window units.  SMALL: every product fits int32 (W <= 6).
-template <typename OutT, bool SMALL>
+template <typename OutT>
 __device__ __forceinline__ void emit_features_window(int n, int sx, int sy, int sz, int sxx, int sxy, int sxz, int syy,
-                                                     int syz, int szz, float fxm, float fym, float fzm, double edge,
-                                                     OutT *out, int descriptor_mask)
+                                                     int syz, int szz, float fxm, float fym, float fzm, bool SMALL,
+                                                     double edge, OutT *out, int descriptor_mask)
 {
     double centroid = 0.0;
     if (n > 0) {

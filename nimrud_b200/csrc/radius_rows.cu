@@ -182,129 +182,22 @@ __device__ __noinline__ void lane_rows(const LatticeDev &L, const RowsParam &P, 
     }
 }
 
-// ---- W <= 3 (r/e < 3.5) specialisation ---------------------------------------------------------
-// the 2W+1 rows of a z-slab are processed as one straight-line block (no per-row branches, so the
-// rows overlap in the pipeline); a slab is summed in packed form; rows whose float32 interval is too
-// close to a cell boundary are redone exactly in a (rare) tail.
-template <int W>
-struct SmallCtx {
-    static constexpr int N = 2 * W + 1;
-    float dy2[N];
-    float rho2, t_min, eps_a, eps_b;
-    double radius;
-};
-
-// one slab: bits[jy] = occupancy of row jy (bit t <-> cell cx - W + t)
-template <int W>
-__device__ __forceinline__ void slab_small(const GridDev &g, const SmallCtx<W> &S, const LaneCtx &X, int jz, float Tz,
-                                           const uint32_t (&bits)[2 * W + 1], const uint32_t *s_lut10, Acc &A)
+// ---- W = 3 window (every r/e < 3.5) --------------------------------------------------------------
+// per z-slab the 7 rows x 7 bits of the lane's window are gathered into one 49-bit word by a short
+// unrolled block (all loads in flight together: shared memory when the warp's window is staged,
+// directory + pool in global memory otherwise), then a ROLLED loop walks the non-empty rows.  the hot
+// loop is ~60 instructions, so it lives in the L0 instruction cache; unrolling it made the kernel
+// instruction-fetch bound (ncu: 31% of stall samples were no_instruction, profiles/).
+//   staged: bricks [iz][iy][ix] at win, origin lo[] (bricks), nb0 x nb1 bricks per slab.
+//   direct: the 2 x 2 x 3 bricks of the lane's own window are resolved through the directory first;
+//           slabs whose bricks are all empty never touch the pool.
+__device__ __forceinline__ void lane_rows_w3(const LatticeDev &L, const RowsParam &P, int ri, const LaneCtx &X,
+                                             bool staged, const uint32_t *win, const int lo[3], int nb0, int nb1,
+                                             const uint32_t *s_lut10, Acc &A)
 {
-    constexpr int N = 2 * W + 1;
-    uint32_t Pk = 0, Qk = 0, unsure_rows = 0;
-    int R = 0;
-#pragma unroll
-    for (int jy = 0; jy < N; ++jy) {
-        const float T = Tz - S.dy2[jy];
-        const float Tc = fmaxf(T, 0.0f);
-        const float rs = fminf(rsqrtf(Tc), 1.0e3f);
-        const float s = Tc * rs;
-        const float a = X.fxm - s, b = X.fxm + s;
-        const float ca = ceilf(a), fb = floorf(b);
-        const float delta = S.eps_a * rs + S.eps_b;
-        const float da = ca - a, db = b - fb;                      // both in [0, 1)
-        const bool unsure = (fminf(da, db) < delta) | (fmaxf(da, db) > 1.0f - delta) | (T < -S.t_min);
-        const int il = max((int)ca, 0), ih = (int)fb;              // ih in [0, 2W+1] by construction
-        uint32_t m = ((2u << ih) - 1u) & ~((1u << il) - 1u) & bits[jy];
-        if (T < S.t_min) m = 0;
-        if (unsure & (bits[jy] != 0) & (T >= S.t_min)) { unsure_rows |= 1u << jy; m = 0; }
-        const uint32_t e = s_lut10[m];
-        Pk += e;
-        Qk += jy * e;
-        R += jy * jy * (int)(e & 1023u);
-    }
-    if (unsure_rows) {                                             // rare: exact float64 redo of those rows
-#pragma unroll
-        for (int jy = 0; jy < N; ++jy)
-            if (unsure_rows & (1u << jy)) {
-                const uint32_t m = exact_row_mask(g, X.q[0], X.q[1], X.q[2], X.c[0], X.c[1] - W + jy, X.c[2] - W + jz, W,
-                                                  S.radius) & bits[jy];
-                const uint32_t e = s_lut10[m];
-                Pk += e;
-                Qk += jy * e;
-                R += jy * jy * (int)(e & 1023u);
-            }
-    }
-    const int C = Pk & 1023, SX = (Pk >> 10) & 1023, SXX = Pk >> 20;
-    const int SY = Qk & 1023, SXY = (Qk >> 10) & 1023;
-    A.n += C; A.sx += SX; A.sxx += SXX; A.sy += SY; A.syy += R; A.sxy += SXY;
-    A.sz += jz * C; A.szz += jz * jz * C; A.sxz += jz * SX; A.syz += jz * SY;
-}
-
-template <int W>
-__device__ __forceinline__ void small_ctx_init(SmallCtx<W> &S, const RowsParam &P, int ri, const LaneCtx &X)
-{
-#pragma unroll
-    for (int j = 0; j < 2 * W + 1; ++j) {
-        const float dy = X.fym - (float)j;
-        S.dy2[j] = dy * dy;
-    }
-    S.rho2 = P.rho2[ri]; S.t_min = P.t_min[ri]; S.eps_a = P.eps_a[ri]; S.eps_b = P.eps_b;
-    S.radius = P.r[ri];
-}
-
-// rows from the warp's staged window
-template <int W>
-__device__ __forceinline__ void lane_rows_small(const LatticeDev &L, const RowsParam &P, int ri, const LaneCtx &X,
-                                                const uint32_t *win, const int lo[3], int nb0, int nb1,
-                                                const uint32_t *s_lut10, Acc &A)
-{
-    constexpr int N = 2 * W + 1;
-    SmallCtx<W> S;
-    small_ctx_init<W>(S, P, ri, X);
-    const uint32_t rowmask = (1u << N) - 1u;
-    const int xa = X.c[0] - W;
-    const int sh = xa & 31;
-    const bool two = sh + N > 32;
-    const int ixs = (xa >> BRICK_XS) - lo[0];
-    const int ya = X.c[1] - W, za = X.c[2] - W;
-    int yoff[N];
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-        const int ay = ya + j;
-        yoff[j] = (((ay >> BRICK_YS) - lo[1]) * nb0 + ixs) * BRICK_WORDS + (ay & (BRICK_Y - 1));
-    }
-    const int zstride = nb1 * nb0 * BRICK_WORDS;
-    for (int jz = 0; jz < N; ++jz) {
-        const float dz = X.fzm - (float)jz;
-        const float Tz = S.rho2 - dz * dz;
-        if (Tz < S.t_min) continue;
-        const int az = za + jz;
-        const int zoff = ((az >> BRICK_ZS) - lo[2]) * zstride + ((az & (BRICK_Z - 1)) << BRICK_YS);
-        uint32_t bits[N];
-        uint32_t any = 0;
-#pragma unroll
-        for (int jy = 0; jy < N; ++jy) {
-            const int off = zoff + yoff[jy];
-            const uint32_t w0 = win[off];
-            const uint32_t w1 = two ? win[off + BRICK_WORDS] : 0u;
-            bits[jy] = __funnelshift_r(w0, w1, sh) & rowmask;
-            any |= bits[jy];
-        }
-        if (any == 0) continue;
-        slab_small<W>(L.g, S, X, jz, Tz, bits, s_lut10, A);
-    }
-}
-
-// rows straight from global memory (warps whose joint window does not fit the staging buffer): the
-// <= 2 x 2 x 3 bricks of the lane's own window are resolved through the directory first, all loads in
-// flight together; slabs whose bricks are all empty are skipped without touching the pool.
-template <int W>
-__device__ __forceinline__ void lane_rows_small_direct(const LatticeDev &L, const RowsParam &P, int ri,
-                                                       const LaneCtx &X, const uint32_t *s_lut10, Acc &A)
-{
-    constexpr int N = 2 * W + 1;
-    SmallCtx<W> S;
-    small_ctx_init<W>(S, P, ri, X);
+    constexpr int W = 3, N = 7;
+    const GridDev &g = L.g;
+    const float rho2 = P.rho2[ri], t_min = P.t_min[ri], eps_a = P.eps_a[ri], eps_b = P.eps_b;
     const uint32_t rowmask = (1u << N) - 1u;
     const int xa = X.c[0] - W;
     const int sh = xa & 31;
@@ -312,45 +205,94 @@ __device__ __forceinline__ void lane_rows_small_direct(const LatticeDev &L, cons
     const int bx0 = xa >> BRICK_XS;
     const int ya = X.c[1] - W, za = X.c[2] - W;
     const int by0 = ya >> BRICK_YS, bz0 = za >> BRICK_ZS;
-    // slots[iz][iy][ix]
+    const int ycross = BRICK_Y - (ya & (BRICK_Y - 1));          // rows jy >= ycross live in the next y-brick
+    int ybase = 0, ystep = 0, zstride = 0;
     uint32_t slot[3][2][2];
+    if (staged) {
+        ybase = ((by0 - lo[1]) * nb0 + (bx0 - lo[0])) * BRICK_WORDS + (ya & (BRICK_Y - 1));
+        ystep = nb0 * BRICK_WORDS - BRICK_Y;                      // extra offset once the row crosses into the next brick
+        zstride = nb1 * nb0 * BRICK_WORDS;
+    } else {
 #pragma unroll
-    for (int iz = 0; iz < 3; ++iz)
+        for (int iz = 0; iz < 3; ++iz)
 #pragma unroll
-        for (int iy = 0; iy < 2; ++iy)
+            for (int iy = 0; iy < 2; ++iy)
 #pragma unroll
-            for (int ix = 0; ix < 2; ++ix) {
-                const int gx = bx0 + ix, gy = by0 + iy, gz = bz0 + iz;
-                const bool ok = (ix == 0 || two) && gx >= 0 && gx < L.nbx && gy >= 0 && gy < L.nby && gz >= 0 && gz < L.nbz;
-                slot[iz][iy][ix] = ok ? L.dir[((int64_t)gz * L.nby + gy) * L.nbx + gx] : 0u;
-            }
+                for (int ix = 0; ix < 2; ++ix) {
+                    const int gx = bx0 + ix, gy = by0 + iy, gz = bz0 + iz;
+                    const bool ok = (ix == 0 || two) && gx >= 0 && gx < L.nbx && gy >= 0 && gy < L.nby && gz >= 0 &&
+                                    gz < L.nbz;
+                    slot[iz][iy][ix] = ok ? L.dir[((int64_t)gz * L.nby + gy) * L.nbx + gx] : 0u;
+                }
+    }
     for (int jz = 0; jz < N; ++jz) {
         const float dz = X.fzm - (float)jz;
-        const float Tz = S.rho2 - dz * dz;
-        if (Tz < S.t_min) continue;
+        const float Tz = rho2 - dz * dz;
+        if (Tz < t_min) continue;
         const int az = za + jz;
-        const int iz = (az >> BRICK_ZS) - bz0;                     // 0..2
-        const uint32_t s00 = iz == 0 ? slot[0][0][0] : (iz == 1 ? slot[1][0][0] : slot[2][0][0]);
-        const uint32_t s01 = iz == 0 ? slot[0][0][1] : (iz == 1 ? slot[1][0][1] : slot[2][0][1]);
-        const uint32_t s10 = iz == 0 ? slot[0][1][0] : (iz == 1 ? slot[1][1][0] : slot[2][1][0]);
-        const uint32_t s11 = iz == 0 ? slot[0][1][1] : (iz == 1 ? slot[1][1][1] : slot[2][1][1]);
-        if ((s00 | s01 | s10 | s11) == 0) continue;
         const int wz = (az & (BRICK_Z - 1)) << BRICK_YS;
-        uint32_t bits[N];
-        uint32_t any = 0;
+        // ---- gather the slab: bits of row jy at [7*jy, 7*jy+7)
+        unsigned long long slab = 0;
+        if (staged) {
+            const int zoff = ((az >> BRICK_ZS) - lo[2]) * zstride + wz + ybase;
 #pragma unroll
-        for (int jy = 0; jy < N; ++jy) {
-            const int ay = ya + jy;
-            const bool up = (ay >> BRICK_YS) != by0;
-            const uint32_t sa = up ? s10 : s00, sb = up ? s11 : s01;
-            const int word = wz | (ay & (BRICK_Y - 1));
-            const uint32_t w0 = sa ? L.pool[(int64_t)sa * BRICK_WORDS + word] : 0u;
-            const uint32_t w1 = sb ? L.pool[(int64_t)sb * BRICK_WORDS + word] : 0u;
-            bits[jy] = __funnelshift_r(w0, w1, sh) & rowmask;
-            any |= bits[jy];
+            for (int jy = 0; jy < N; ++jy) {
+                const int off = zoff + jy + (jy >= ycross ? ystep : 0);
+                const uint32_t w0 = win[off];
+                const uint32_t w1 = two ? win[off + BRICK_WORDS] : 0u;
+                slab |= (unsigned long long)(__funnelshift_r(w0, w1, sh) & rowmask) << (N * jy);
+            }
+        } else {
+            const int iz = (az >> BRICK_ZS) - bz0;                     // 0..2
+            const uint32_t s00 = iz == 0 ? slot[0][0][0] : (iz == 1 ? slot[1][0][0] : slot[2][0][0]);
+            const uint32_t s01 = iz == 0 ? slot[0][0][1] : (iz == 1 ? slot[1][0][1] : slot[2][0][1]);
+            const uint32_t s10 = iz == 0 ? slot[0][1][0] : (iz == 1 ? slot[1][1][0] : slot[2][1][0]);
+            const uint32_t s11 = iz == 0 ? slot[0][1][1] : (iz == 1 ? slot[1][1][1] : slot[2][1][1]);
+            if ((s00 | s01 | s10 | s11) == 0) continue;
+#pragma unroll
+            for (int jy = 0; jy < N; ++jy) {
+                const bool up = jy >= ycross;
+                const uint32_t sa = up ? s10 : s00, sb = up ? s11 : s01;
+                const int word = wz | ((ya + jy) & (BRICK_Y - 1));
+                const uint32_t w0 = sa ? L.pool[(int64_t)sa * BRICK_WORDS + word] : 0u;
+                const uint32_t w1 = sb ? L.pool[(int64_t)sb * BRICK_WORDS + word] : 0u;
+                slab |= (unsigned long long)(__funnelshift_r(w0, w1, sh) & rowmask) << (N * jy);
+            }
         }
-        if (any == 0) continue;
-        slab_small<W>(L.g, S, X, jz, Tz, bits, s_lut10, A);
+        if (slab == 0) continue;
+        // ---- rolled walk over the rows
+        uint32_t Pk = 0, Qk = 0;
+        int R = 0;
+#pragma unroll 1
+        for (int jy = 0; jy < N; ++jy) {
+            const uint32_t bits = (uint32_t)(slab >> (N * jy)) & rowmask;
+            const float dy = X.fym - (float)jy;
+            const float T = Tz - dy * dy;
+            if (bits == 0 || T < t_min) continue;
+            const float Tc = fmaxf(T, 0.0f);
+            const float rs = fminf(rsqrtf(Tc), 1.0e3f);
+            const float s = Tc * rs;
+            const float a = X.fxm - s, b = X.fxm + s;
+            const float ca = ceilf(a), fb = floorf(b);
+            const float delta = eps_a * rs + eps_b;
+            const float da = ca - a, db = b - fb;                      // both in [0, 1)
+            const bool unsure = (fminf(da, db) < delta) | (fmaxf(da, db) > 1.0f - delta) | (T < -t_min);
+            uint32_t m;
+            if (unsure) {
+                m = exact_row_mask(g, X.q[0], X.q[1], X.q[2], X.c[0], ya + jy, az, W, P.r[ri]);
+            } else {
+                const int il = max((int)ca, 0), ih = (int)fb;          // ih in [0, 2W+1] by construction
+                m = ((2u << ih) - 1u) & ~((1u << il) - 1u);
+            }
+            const uint32_t e = s_lut10[m & bits];
+            Pk += e;
+            Qk += jy * e;
+            R += jy * jy * (int)(e & 1023u);
+        }
+        const int C = Pk & 1023, SX = (Pk >> 10) & 1023, SXX = Pk >> 20;
+        const int SY = Qk & 1023, SXY = (Qk >> 10) & 1023;
+        A.n += C; A.sx += SX; A.sxx += SXX; A.sy += SY; A.syy += R; A.sxy += SXY;
+        A.sz += jz * C; A.szz += jz * jz * C; A.sxz += jz * SX; A.syz += jz * SY;
     }
 }
 
@@ -396,7 +338,9 @@ radius_rows_kernel(const RowsLaunch *__restrict__ launch, const void *__restrict
             double f[3];
 #pragma unroll
             for (int a = 0; a < 3; ++a) query_anchor(X.q[a], g.minc[a], g.inv_edge, X.c[a], f[a]);
-            const int W = P.wmax;
+            // every window of half-width <= 3 runs through the one W = 3 code path (rows beyond the ball just
+            // fail the disc test)
+            const int W = P.wmax <= 3 ? 3 : P.wmax;
             X.W = W;
             X.fxm = (float)f[0] - 0.5f + (float)W;
             X.fym = (float)f[1] - 0.5f + (float)W;
@@ -453,24 +397,12 @@ radius_rows_kernel(const RowsLaunch *__restrict__ launch, const void *__restrict
 
             for (int ri = 0; ri < P.n; ++ri) {
                 Acc A = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-                if (staged) {
-                    if (W == 3)      lane_rows_small<3>(L, P, ri, X, win, lo, nb[0], nb[1], s_lut10, A);
-                    else if (W == 2) lane_rows_small<2>(L, P, ri, X, win, lo, nb[0], nb[1], s_lut10, A);
-                    else             lane_rows<true>(L, P, ri, X, win, lo, nb[0], nb[1], s_lut, A);
-                } else {
-                    if (W == 3)      lane_rows_small_direct<3>(L, P, ri, X, s_lut10, A);
-                    else if (W == 2) lane_rows_small_direct<2>(L, P, ri, X, s_lut10, A);
-                    else             lane_rows<false>(L, P, ri, X, win, lo, nb[0], nb[1], s_lut, A);
-                }
-                if (active) {
-                    OutT *dst = dst_row + P.col[ri];
-                    if (W <= 6)
-                        emit_features_window<OutT, true>(A.n, A.sx, A.sy, A.sz, A.sxx, A.sxy, A.sxz, A.syy, A.syz, A.szz,
-                                                         X.fxm, X.fym, X.fzm, g.edge, dst, descriptor_mask);
-                    else
-                        emit_features_window<OutT, false>(A.n, A.sx, A.sy, A.sz, A.sxx, A.sxy, A.sxz, A.syy, A.syz, A.szz,
-                                                          X.fxm, X.fym, X.fzm, g.edge, dst, descriptor_mask);
-                }
+                if (W == 3)      lane_rows_w3(L, P, ri, X, staged, win, lo, nb[0], nb[1], s_lut10, A);
+                else if (staged) lane_rows<true>(L, P, ri, X, win, lo, nb[0], nb[1], s_lut, A);
+                else             lane_rows<false>(L, P, ri, X, win, lo, nb[0], nb[1], s_lut, A);
+                if (active)
+                    emit_features_window<OutT>(A.n, A.sx, A.sy, A.sz, A.sxx, A.sxy, A.sxz, A.syy, A.syz, A.szz, X.fxm,
+                                               X.fym, X.fzm, W <= 6, g.edge, dst_row + P.col[ri], descriptor_mask);
             }
             __syncwarp();
         }
@@ -491,12 +423,13 @@ int rows_param(const Lattice *lat, const double *radii, const int *cols, int nr,
         P->col[k] = cols[k];
         P->wmax = std::max(P->wmax, P->w[k]);
     }
+    const int weff = std::max(P->wmax, 3);      // the kernel runs every window <= 3 as a W = 3 window
     for (int k = 0; k < nr; ++k) {
-        const double mag = (double)P->rho2[k] + (P->wmax + 1.0) * (P->wmax + 1.0);
+        const double mag = (double)P->rho2[k] + (weff + 1.0) * (weff + 1.0);
         P->eps_a[k] = (float)(8.0 * 5.96e-8 * mag);
         P->t_min[k] = (float)(-16.0 * 5.96e-8 * mag);
     }
-    P->eps_b = (float)(4.77e-7 * (P->wmax + 1.0));
+    P->eps_b = (float)(4.77e-7 * (weff + 1.0));
     return NBR_OK;
 }
 
