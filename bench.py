@@ -251,10 +251,22 @@ def gpu_arm(args, rank, world, local_rank):
         results = {}
         for label, tdt, code in (("f64", torch.float64, _lib.F64), ("f32", torch.float32, _lib.F32)):
             host_out = torch.empty((n, 4 * ns), dtype=tdt).pin_memory()
-            def host_step():
-                _lib.check(lib.nbr_multiscale_features_host(
-                    ctypes.c_void_p(host_in.data_ptr()), _lib.F32, n, ctypes.c_void_p(host_in.data_ptr()), _lib.F32, n,
-                    edges_p, radii_p, ns, ctypes.c_void_p(host_out.data_ptr()), code, 0, None))
+            if world > 1:
+                dev_in = torch.empty_like(cloud)
+                dev_out = torch.empty((n, 4 * ns), dtype=tdt, device=dev)
+                np_dt = np.float64 if tdt == torch.float64 else np.float32
+
+                def host_step():
+                    # host tile -> device, halo exchange + compute, features -> host
+                    dev_in.copy_(host_in, non_blocking=True)
+                    nd.process_tile(dev_in, EDGES, RADII, out=dev_out, out_dtype=np_dt, gather=False)
+                    host_out.copy_(dev_out, non_blocking=True)
+                    torch.cuda.synchronize()
+            else:
+                def host_step():
+                    _lib.check(lib.nbr_multiscale_features_host(
+                        ctypes.c_void_p(host_in.data_ptr()), _lib.F32, n, ctypes.c_void_p(host_in.data_ptr()), _lib.F32,
+                        n, edges_p, radii_p, ns, ctypes.c_void_p(host_out.data_ptr()), code, 0, None))
             host_step()
             barrier()
             t0 = time.perf_counter()

@@ -123,130 +123,159 @@ int radius_features(const Lattice *lat, const void *query, int dtype, const uint
                                  descriptor_mask, stream);
 }
 
-// groups scales by edge length, builds one lattice per distinct edge, orders the queries along a
-// Morton curve and runs ONE fused kernel over all lattices (all radii of a lattice share one pass over
-// each query's window).  scales the row kernel cannot take (r/e > 9.5) go through the exact kernel.
-int multiscale_features(const void *query, int q_dtype, int64_t nq, const void *search, int s_dtype, int64_t ns,
-                        const double *edges, const double *radii, int n_scales, void *out, int out_dtype,
-                        int descriptor_mask, const double *global_lohi, int64_t *n_voxels_host, cudaStream_t stream)
+// ------------------------------------------------------------------------------------------------
+// whole-path driver.  a Plan holds what depends on the SEARCH cloud only (one lattice per distinct
+// edge); plan_run handles one batch of queries: Morton order, one fused launch over all lattices
+// (all radii of a lattice share one pass over each query's window).  scales the row kernel cannot take
+// (r/e > 9.5) go through the exact kernel.
+// ------------------------------------------------------------------------------------------------
+struct Plan {
+    struct Group { double edge; Lattice *lat; std::vector<int> scales; };
+    std::vector<Group> groups;
+    std::vector<double> edges, radii;
+    int n_scales = 0, ncol = 4, descriptor_mask = 0;
+    double finest = 0.0;
+    double local_box[6];
+    ~Plan() { for (auto &g : groups) delete g.lat; }
+};
+
+int plan_create(Plan **out, const void *search, int s_dtype, int64_t ns, const double *edges, const double *radii,
+                int n_scales, int descriptor_mask, const double *global_lohi, cudaStream_t stream)
 {
-    NBR_TRY(check_cloud_dtype(q_dtype, "multiscale_features"));
     NBR_TRY(check_cloud_dtype(s_dtype, "multiscale_features"));
-    if (out_dtype != NBR_F32 && out_dtype != NBR_F64) return fail(NBR_ERR_INVALID, "multiscale_features: bad out_dtype");
-    if (n_scales < 0 || nq < 0) return fail(NBR_ERR_INVALID, "multiscale_features: negative size");
+    if (n_scales < 0) return fail(NBR_ERR_INVALID, "multiscale_features: negative number of scales");
     if (ns < 2) return fail(NBR_ERR_TOO_FEW_POINTS, "need at least 2 points to define a voxel grid");
-    if (n_scales == 0 || nq == 0) return NBR_OK;
-    if (!query || !search || !edges || !radii || !out) return fail(NBR_ERR_INVALID, "multiscale_features: null argument");
+    if (!search || (n_scales > 0 && (!edges || !radii))) return fail(NBR_ERR_INVALID, "multiscale_features: null argument");
     for (int s = 0; s < n_scales; ++s) {
         if (!(edges[s] > 0)) return fail(NBR_ERR_INVALID, "multiscale_features: edge lengths must be > 0");
         if (!(radii[s] >= 0)) return fail(NBR_ERR_INVALID, "multiscale_features: radii must be >= 0");
     }
-
-    double lohi[6];
-    if (global_lohi) {
-        std::copy(global_lohi, global_lohi + 6, lohi);
-    } else {
+    Plan *P = new Plan();
+    P->n_scales = n_scales;
+    P->descriptor_mask = descriptor_mask;
+    P->ncol = (descriptor_mask & NBR_DESC_EXTENDED) ? NBR_COLS_EXTENDED : NBR_COLS_REFERENCE;
+    P->edges.assign(edges, edges + n_scales);
+    P->radii.assign(radii, radii + n_scales);
+    // bounding box of the search cloud given to this call.  with global_lohi (multi-GPU: the all-reduced
+    // box) the lattices are ANCHORED on the global box but their directories only cover this local box.
+    int rc = NBR_OK;
+    {
         Scratch box;
-        NBR_TRY(box.alloc(sizeof(double) * 6, stream));
-        {
+        rc = box.alloc(sizeof(double) * 6, stream);
+        if (!rc) {
             PhaseTimer t(PHASE_BBOX, stream);
-            NBR_TRY(bbox(search, s_dtype, ns, 3, box.as<double>(), stream));
+            rc = bbox(search, s_dtype, ns, 3, box.as<double>(), stream);
         }
-        NBR_CUDA(cudaMemcpyAsync(lohi, box.ptr, sizeof(lohi), cudaMemcpyDeviceToHost, stream));
-        NBR_CUDA(cudaStreamSynchronize(stream));
+        if (!rc && (cudaMemcpyAsync(P->local_box, box.ptr, sizeof(P->local_box), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+                    cudaStreamSynchronize(stream) != cudaSuccess))
+            rc = fail(NBR_ERR_CUDA, "multiscale_features: bounding box copy failed");
     }
-
-    const int ncol = (descriptor_mask & NBR_DESC_EXTENDED) ? NBR_COLS_EXTENDED : NBR_COLS_REFERENCE;
-    const int64_t row_stride = (int64_t)ncol * n_scales;
-
-    // ---- one lattice per distinct edge
-    struct Group { double edge; Lattice *lat; std::vector<int> scales; };
-    std::vector<Group> groups;
+    if (rc) { delete P; return rc; }
+    const double *lohi = global_lohi ? global_lohi : P->local_box;
     for (int s = 0; s < n_scales; ++s) {
         size_t gi = 0;
-        while (gi < groups.size() && groups[gi].edge != edges[s]) ++gi;
-        if (gi == groups.size()) groups.push_back({edges[s], nullptr, {}});
-        groups[gi].scales.push_back(s);
+        while (gi < P->groups.size() && P->groups[gi].edge != edges[s]) ++gi;
+        if (gi == P->groups.size()) P->groups.push_back({edges[s], nullptr, {}});
+        P->groups[gi].scales.push_back(s);
+        P->finest = s == 0 ? edges[s] : std::min(P->finest, edges[s]);
     }
-    int rc = NBR_OK;
-    auto cleanup = [&]() { for (auto &g : groups) delete g.lat; };
     {
         PhaseTimer t(PHASE_INDEX, stream);
-        for (auto &g : groups) {
+        for (auto &g : P->groups) {
             nbr_grid grid;
             rc = grid_from_bbox(lohi, lohi + 3, g.edge, 3, &grid);
-            if (!rc) rc = lattice_create(&g.lat, search, s_dtype, ns, &grid, 0, stream);
+            if (!rc) rc = lattice_create(&g.lat, search, s_dtype, ns, &grid, 0, stream, global_lohi ? P->local_box : nullptr);
             if (rc) break;
         }
     }
-    if (rc) { cleanup(); return rc; }
+    if (rc) { delete P; return rc; }
+    *out = P;
+    return NBR_OK;
+}
 
-    // ---- processing order of the queries: Morton curve, cells of 4 finest voxels; sorted copy of the cloud
+// features of one batch of queries -> rows [0, nq) of `out` (row stride = ncol * n_scales)
+// qbox: bounding box of the batch if the caller knows it (else computed)
+int plan_run(const Plan *P, const void *query, int q_dtype, int64_t nq, const double *qbox_known, void *out,
+             int out_dtype, cudaStream_t stream)
+{
+    NBR_TRY(check_cloud_dtype(q_dtype, "multiscale_features"));
+    if (out_dtype != NBR_F32 && out_dtype != NBR_F64) return fail(NBR_ERR_INVALID, "multiscale_features: bad out_dtype");
+    if (nq <= 0 || P->n_scales == 0) return NBR_OK;
+    if (!query || !out) return fail(NBR_ERR_INVALID, "multiscale_features: null argument");
+    const int ncol = P->ncol;
+    const int64_t row_stride = (int64_t)ncol * P->n_scales;
+
+    // ---- processing order of the queries: Morton curve, cells of 2 finest voxels; sorted copy of the cloud
     Scratch perm, sorted;
-    rc = perm.alloc(sizeof(uint32_t) * nq, stream);
-    if (!rc) rc = sorted.alloc((size_t)nq * 3 * (q_dtype == NBR_F32 ? 4 : 8), stream);
-    if (!rc) {
+    NBR_TRY(perm.alloc(sizeof(uint32_t) * nq, stream));
+    NBR_TRY(sorted.alloc((size_t)nq * 3 * (q_dtype == NBR_F32 ? 4 : 8), stream));
+    {
         PhaseTimer t(PHASE_ORDER, stream);
         double qbox[6];
-        if (query == search && nq == ns && q_dtype == s_dtype && !global_lohi) {
-            std::copy(lohi, lohi + 6, qbox);
+        if (qbox_known) {
+            std::copy(qbox_known, qbox_known + 6, qbox);
         } else {
             Scratch box;
-            rc = box.alloc(sizeof(double) * 6, stream);
-            if (!rc) rc = bbox(query, q_dtype, nq, 3, box.as<double>(), stream);
-            if (!rc && (cudaMemcpyAsync(qbox, box.ptr, sizeof(qbox), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
-                        cudaStreamSynchronize(stream) != cudaSuccess))
-                rc = fail(NBR_ERR_CUDA, "multiscale_features: query bounding box copy failed");
+            NBR_TRY(box.alloc(sizeof(double) * 6, stream));
+            NBR_TRY(bbox(query, q_dtype, nq, 3, box.as<double>(), stream));
+            NBR_CUDA(cudaMemcpyAsync(qbox, box.ptr, sizeof(qbox), cudaMemcpyDeviceToHost, stream));
+            NBR_CUDA(cudaStreamSynchronize(stream));
         }
-        double finest = edges[0];
-        for (int s = 1; s < n_scales; ++s) finest = std::min(finest, edges[s]);
-        if (!rc) rc = morton_order(query, q_dtype, nq, qbox, 2.0 * finest, perm.as<uint32_t>(), sorted.ptr, stream);
+        NBR_TRY(morton_order(query, q_dtype, nq, qbox, 2.0 * P->finest, perm.as<uint32_t>(), sorted.ptr, stream));
     }
-    if (rc) { cleanup(); return rc; }
 
     // ---- fused launches
-    {
-        PhaseTimer tm(PHASE_FEATURES, stream);
-        RowsLaunch launch;
+    PhaseTimer tm(PHASE_FEATURES, stream);
+    RowsLaunch launch;
+    memset(&launch, 0, sizeof(launch));
+    auto flush = [&]() -> int {
+        if (launch.n_lat == 0) return NBR_OK;
+        int r = radius_rows_launch(&launch, sorted.ptr, q_dtype, perm.as<uint32_t>(), nq, out, out_dtype, row_stride,
+                                   P->descriptor_mask, stream);
         memset(&launch, 0, sizeof(launch));
-        auto flush = [&]() -> int {
-            if (launch.n_lat == 0) return NBR_OK;
-            int r = radius_rows_launch(&launch, sorted.ptr, q_dtype, perm.as<uint32_t>(), nq, out, out_dtype, row_stride,
-                                       descriptor_mask, stream);
-            memset(&launch, 0, sizeof(launch));
-            return r;
-        };
-        for (auto &g : groups) {
-            std::vector<double> rr;
-            std::vector<int> cc;
-            for (int s : g.scales) {
-                if (rows_supported(g.edge, &radii[s], 1)) { rr.push_back(radii[s]); cc.push_back(s * ncol); }
-                else {
-                    rc = radius_features_exact(g.lat, query, q_dtype, nq, &radii[s], 1, out, out_dtype, row_stride,
-                                               s * ncol, descriptor_mask, stream);
-                    if (rc) break;
-                }
-            }
-            for (size_t base = 0; base < rr.size() && !rc; base += RW_MAX_RADII) {
-                const int n = (int)std::min<size_t>(RW_MAX_RADII, rr.size() - base);
-                launch.lat[launch.n_lat] = g.lat->dev();
-                rc = rows_param(g.lat, rr.data() + base, cc.data() + base, n, &launch.rows[launch.n_lat]);
-                ++launch.n_lat;
-                if (!rc && launch.n_lat == RW_MAX_LATTICES) rc = flush();
-            }
-            if (rc) break;
+        return r;
+    };
+    for (auto &g : P->groups) {
+        std::vector<double> rr;
+        std::vector<int> cc;
+        for (int s : g.scales) {
+            if (rows_supported(g.edge, &P->radii[s], 1)) { rr.push_back(P->radii[s]); cc.push_back(s * ncol); }
+            else
+                NBR_TRY(radius_features_exact(g.lat, query, q_dtype, nq, &P->radii[s], 1, out, out_dtype, row_stride,
+                                              s * ncol, P->descriptor_mask, stream));
         }
-        if (!rc) rc = flush();
-    }
-    if (rc == NBR_OK && n_voxels_host) {
-        for (auto &g : groups) {
-            int64_t nv = 0;
-            rc = lattice_counts(g.lat, &nv, nullptr);
-            if (rc) break;
-            for (int s : g.scales) n_voxels_host[s] = nv;
+        for (size_t base = 0; base < rr.size(); base += RW_MAX_RADII) {
+            const int n = (int)std::min<size_t>(RW_MAX_RADII, rr.size() - base);
+            launch.lat[launch.n_lat] = g.lat->dev();
+            NBR_TRY(rows_param(g.lat, rr.data() + base, cc.data() + base, n, &launch.rows[launch.n_lat]));
+            ++launch.n_lat;
+            if (launch.n_lat == RW_MAX_LATTICES) NBR_TRY(flush());
         }
     }
-    cleanup();
+    return flush();
+}
+
+int plan_voxel_counts(const Plan *P, int64_t *n_voxels_host)
+{
+    for (auto &g : P->groups) {
+        int64_t nv = 0;
+        NBR_TRY(lattice_counts(g.lat, &nv, nullptr));
+        for (int s : g.scales) n_voxels_host[s] = nv;
+    }
+    return NBR_OK;
+}
+
+int multiscale_features(const void *query, int q_dtype, int64_t nq, const void *search, int s_dtype, int64_t ns,
+                        const double *edges, const double *radii, int n_scales, void *out, int out_dtype,
+                        int descriptor_mask, const double *global_lohi, int64_t *n_voxels_host, cudaStream_t stream)
+{
+    if (nq < 0) return fail(NBR_ERR_INVALID, "multiscale_features: negative size");
+    Plan *P = nullptr;
+    NBR_TRY(plan_create(&P, search, s_dtype, ns, edges, radii, n_scales, descriptor_mask, global_lohi, stream));
+    const bool same = query == search && nq == ns && q_dtype == s_dtype;
+    int rc = plan_run(P, query, q_dtype, nq, same ? P->local_box : nullptr, out, out_dtype, stream);
+    if (rc == NBR_OK && n_voxels_host) rc = plan_voxel_counts(P, n_voxels_host);
+    delete P;
     return rc;
 }
 
@@ -311,6 +340,9 @@ extern "C" int nbr_multiscale_features(const void *query_xyz, int q_dtype, int64
 
 static size_t elem_size(int dtype) { return dtype == NBR_F32 ? 4 : 8; }
 
+// HOST buffers.  the search cloud goes up once, the lattices are built once, then the queries are
+// processed in batches: the device->host copy of batch k (on a second stream) overlaps the kernels of
+// batch k+1.  pinned host buffers make the copies asynchronous; pageable ones still work.
 extern "C" int nbr_multiscale_features_host(const void *query_host, int q_dtype, int64_t n_query,
                                             const void *search_host, int s_dtype, int64_t n_search,
                                             const double *edges_host, const double *radii_host, int32_t n_scales,
@@ -323,31 +355,59 @@ extern "C" int nbr_multiscale_features_host(const void *query_host, int q_dtype,
     if (n_search < 2) return fail(NBR_ERR_TOO_FEW_POINTS, "need at least 2 points to define a voxel grid");
     if (n_query <= 0 || n_scales <= 0) return NBR_OK;
     if (!query_host || !search_host || !out_host) return fail(NBR_ERR_INVALID, "nbr_multiscale_features_host: null argument");
-    cudaStream_t stream;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
     NBR_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamDestroy(stream);
+        return fail(NBR_ERR_CUDA, "nbr_multiscale_features_host: cannot create the copy stream");
+    }
     const int ncol = (descriptor_mask & NBR_DESC_EXTENDED) ? NBR_COLS_EXTENDED : NBR_COLS_REFERENCE;
-    const size_t qbytes = (size_t)n_query * 3 * elem_size(q_dtype);
+    const size_t qrow = 3 * elem_size(q_dtype), orow = (size_t)ncol * n_scales * elem_size(out_dtype);
     const size_t sbytes = (size_t)n_search * 3 * elem_size(s_dtype);
-    const size_t obytes = (size_t)n_query * ncol * n_scales * elem_size(out_dtype);
     const bool same = query_host == search_host && q_dtype == s_dtype && n_query == n_search;
+    const int64_t batch = std::max<int64_t>(262144, (n_query + 7) / 8);
+    std::vector<cudaEvent_t> events;
     int rc = NBR_OK;
+    Plan *P = nullptr;
     {
         Scratch q, s, o;
         rc = s.alloc(sbytes, stream);
-        if (!rc && !same) rc = q.alloc(qbytes, stream);
-        if (!rc) rc = o.alloc(obytes, stream);
+        if (!rc && !same) rc = q.alloc((size_t)n_query * qrow, stream);
+        if (!rc) rc = o.alloc((size_t)n_query * orow, stream);
         cudaError_t e = cudaSuccess;
         if (!rc) e = cudaMemcpyAsync(s.ptr, search_host, sbytes, cudaMemcpyHostToDevice, stream);
-        if (!rc && e == cudaSuccess && !same) e = cudaMemcpyAsync(q.ptr, query_host, qbytes, cudaMemcpyHostToDevice, stream);
         if (!rc && e == cudaSuccess)
-            rc = multiscale_features(same ? s.ptr : q.ptr, q_dtype, n_query, s.ptr, s_dtype, n_search, edges_host,
-                                     radii_host, n_scales, o.ptr, out_dtype, descriptor_mask, nullptr, n_voxels_host,
-                                     stream);
-        if (!rc && e == cudaSuccess) e = cudaMemcpyAsync(out_host, o.ptr, obytes, cudaMemcpyDeviceToHost, stream);
+            rc = plan_create(&P, s.ptr, s_dtype, n_search, edges_host, radii_host, n_scales, descriptor_mask, nullptr, stream);
+        for (int64_t first = 0; !rc && e == cudaSuccess && first < n_query; first += batch) {
+            const int64_t n = std::min(batch, n_query - first);
+            char *qdev = (same ? (char *)s.ptr : (char *)q.ptr) + (size_t)first * qrow;
+            if (!same) e = cudaMemcpyAsync(qdev, (const char *)query_host + (size_t)first * qrow, (size_t)n * qrow,
+                                           cudaMemcpyHostToDevice, stream);
+            if (e != cudaSuccess) break;
+            char *odev = (char *)o.ptr + (size_t)first * orow;
+            rc = plan_run(P, qdev, q_dtype, n, same ? P->local_box : nullptr, odev, out_dtype, stream);
+            if (rc) break;
+            cudaEvent_t done;
+            e = cudaEventCreateWithFlags(&done, cudaEventDisableTiming);
+            if (e != cudaSuccess) break;
+            events.push_back(done);
+            e = cudaEventRecord(done, stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(copy_stream, done, 0);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync((char *)out_host + (size_t)first * orow, odev, (size_t)n * orow, cudaMemcpyDeviceToHost,
+                                    copy_stream);
+        }
         if (!rc && e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (!rc && e == cudaSuccess) e = cudaStreamSynchronize(copy_stream);
+        if (!rc && e == cudaSuccess && n_voxels_host) rc = plan_voxel_counts(P, n_voxels_host);
         if (!rc && e != cudaSuccess) rc = fail(NBR_ERR_CUDA, std::string("host path: ") + cudaGetErrorString(e));
+        cudaStreamSynchronize(copy_stream);
+        cudaStreamSynchronize(stream);
+        delete P;
     }
+    for (cudaEvent_t ev : events) cudaEventDestroy(ev);
     cudaStreamSynchronize(stream);
+    cudaStreamDestroy(copy_stream);
     cudaStreamDestroy(stream);
     return rc;
 }

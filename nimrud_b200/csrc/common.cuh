@@ -78,7 +78,9 @@ struct GridDev {
     double inv_edge;
     int32_t widths[3];
     int32_t shifts[3];
-    int32_t ncell[3];   // number of addressable cells actually spanned by the bounding box
+    int32_t ncell[3];   // cells covered by this lattice's directory (local cell coordinates 0..ncell-1)
+    int32_t cell_lo[3]; // global cell index of local cell 0: local = floor((p - minc)/e) - cell_lo.  non-zero
+                        // when the lattice is anchored on a global box (multi-GPU) but only covers a tile
     int32_t ndim;
 };
 
@@ -117,11 +119,20 @@ __device__ __forceinline__ double cell_centre(int64_t k, double minc, double edg
     return __dadd_rn(__dadd_rn(__dmul_rn((double)k, edge), minc), __dmul_rn(edge, 0.5));
 }
 
+// centre of LOCAL cell k on axis a
+struct GridDev;
+__device__ __forceinline__ double grid_centre(const GridDev &g, long long k, int a);
+
 // one squared coordinate difference; the membership sum is ((dx2 + dy2) + dz2) <= r2
 __device__ __forceinline__ double sqdiff(double q, double c)
 {
     double d = __dsub_rn(q, c);
     return __dmul_rn(d, d);
+}
+
+__device__ __forceinline__ double grid_centre(const GridDev &g, long long k, int a)
+{
+    return cell_centre(k + (long long)g.cell_lo[a], g.minc[a], g.edge);
 }
 
 __device__ __forceinline__ uint32_t lanemask_lt()

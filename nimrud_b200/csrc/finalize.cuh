@@ -253,14 +253,14 @@ __device__ __forceinline__ void emit_features_window(int n, int sx, int sy, int 
 
 // anchor cell and fractional position of a query on one axis.  c is clamped so that far-away
 // queries cannot overflow; f in [0,1) when unclamped.
-__device__ __forceinline__ void query_anchor(double q, double minc, double inv_edge, int &c, double &f)
+__device__ __forceinline__ void query_anchor(double q, const GridDev &g, int a, int &c, double &f)
 {
     // the anchor only positions the window, so a reciprocal multiply is as good as the division
-    const double u = (q - minc) * inv_edge;
+    const double u = (q - g.minc[a]) * g.inv_edge;
     double cf = floor(u);
-    cf = fmin(fmax(cf, -1.0e9), 1.0e9);
-    c = (int)cf;
     f = u - cf;
+    cf = fmin(fmax(cf - (double)g.cell_lo[a], -1.0e9), 1.0e9);     // local cell coordinate
+    c = (int)cf;
 }
 #endif
 

@@ -113,15 +113,26 @@ int grid_from_bbox(const double lo[3], const double hi[3], double edge, int ndim
     return NBR_OK;
 }
 
-int grid_to_dev(const nbr_grid *g, GridDev *d)
+// local_lohi (optional): bounding box of the points this lattice will hold; the directory then only
+// covers that part of the (possibly much larger, global) grid.
+int grid_to_dev(const nbr_grid *g, GridDev *d, const double *local_lohi)
 {
     for (int a = 0; a < 3; ++a) {
         d->minc[a] = g->min_corner[a];
         d->widths[a] = g->widths[a];
         d->shifts[a] = g->shifts[a];
-        double cells = a < g->ndim ? floor((g->max_corner[a] - g->min_corner[a]) / g->edge) + 1.0 : 1.0;
-        if (cells > 2147483000.0) return fail(NBR_ERR_UNSUPPORTED, "more than 2^31 cells along one axis");
-        d->ncell[a] = (int32_t)cells;
+        double first = 0.0;
+        double last = a < g->ndim ? floor((g->max_corner[a] - g->min_corner[a]) / g->edge) : 0.0;
+        if (local_lohi && a < g->ndim) {
+            // one cell of slack on both sides: host and device floor() agree to the last bit only in theory
+            first = fmax(first, floor((local_lohi[a] - g->min_corner[a]) / g->edge) - 1.0);
+            last = fmin(last, floor((local_lohi[3 + a] - g->min_corner[a]) / g->edge) + 1.0);
+            if (last < first) last = first;
+        }
+        if (last - first + 1.0 > 2147483000.0 || first > 2147483000.0)
+            return fail(NBR_ERR_UNSUPPORTED, "more than 2^31 cells along one axis");
+        d->cell_lo[a] = (int32_t)first;
+        d->ncell[a] = (int32_t)(last - first + 1.0);
     }
     d->edge = g->edge;
     d->inv_edge = 1.0 / g->edge;
@@ -222,9 +233,9 @@ __device__ __forceinline__ void point_cell(const void *xyz, int dtype, int64_t i
         int v = 0;
         if (a < g.ndim) {
             double p = load_coord(xyz, dtype, i, g.ndim, a);
-            double k = cell_coord_f(p, g.minc[a], g.edge);
-            // search points lie inside the box by construction; clamp defends against a caller-supplied
-            // (global) box that does not contain them.
+            double k = cell_coord_f(p, g.minc[a], g.edge) - (double)g.cell_lo[a];
+            // search points lie inside the covered range by construction; the clamp defends against a
+            // caller-supplied box that does not contain them.
             k = fmin(fmax(k, 0.0), (double)(g.ncell[a] - 1));
             v = (int)k;
         }
@@ -295,8 +306,8 @@ rowbase_kernel(const uint64_t *__restrict__ ukeys, const int64_t *__restrict__ n
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         uint64_t mask = g.widths[a] >= 64 ? ~0ull : ((1ull << g.widths[a]) - 1);
-        c[a] = (int)((k >> g.shifts[a]) & mask);
-        p[a] = (int)((kp >> g.shifts[a]) & mask);
+        c[a] = (int)((k >> g.shifts[a]) & mask) - g.cell_lo[a];
+        p[a] = (int)((kp >> g.shifts[a]) & mask) - g.cell_lo[a];
     }
     const bool head = i == 0 || c[2] != p[2] || c[1] != p[1] || (c[0] >> BRICK_XS) != (p[0] >> BRICK_XS);
     if (!head) return;
@@ -325,7 +336,7 @@ LatticeDev Lattice::dev() const
 }
 
 int lattice_create(Lattice **out, const void *xyz, int dtype, int64_t n, const nbr_grid *grid, int flags,
-                   cudaStream_t stream)
+                   cudaStream_t stream, const double *local_lohi)
 {
     if (!out || !xyz || !grid) return fail(NBR_ERR_INVALID, "lattice_create: null argument");
     if (dtype != NBR_F32 && dtype != NBR_F64) return fail(NBR_ERR_INVALID, "lattice_create: bad dtype");
@@ -335,7 +346,7 @@ int lattice_create(Lattice **out, const void *xyz, int dtype, int64_t n, const n
     L->stream = stream;
     L->grid = *grid;
     L->n_search = n;
-    int rc = grid_to_dev(grid, &L->gdev);
+    int rc = grid_to_dev(grid, &L->gdev, local_lohi);
     if (rc) { delete L; return rc; }
     L->nbx = (L->gdev.ncell[0] + BRICK_X - 1) / BRICK_X;
     L->nby = (L->gdev.ncell[1] + BRICK_Y - 1) / BRICK_Y;
@@ -434,7 +445,7 @@ extern "C" int nbr_voxel_addresses(const void *xyz, int dtype, int64_t n, const 
     if (!xyz || !grid || !addresses) return fail(NBR_ERR_INVALID, "nbr_voxel_addresses: null argument");
     if (n <= 0) return NBR_OK;
     GridDev g;
-    NBR_TRY(grid_to_dev(grid, &g));
+    NBR_TRY(grid_to_dev(grid, &g, nullptr));
     if (oob_dev) NBR_CUDA(cudaMemsetAsync(oob_dev, 0, sizeof(int32_t), (cudaStream_t)stream));
     address_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(
         xyz, dtype, n, g, grid->max_corner[0], grid->max_corner[1], grid->max_corner[2], addresses, oob_dev);
@@ -453,7 +464,7 @@ extern "C" int nbr_voxel_centres(const int64_t *addresses, int64_t n, const nbr_
     if (!addresses || !grid || !xyz_out) return fail(NBR_ERR_INVALID, "nbr_voxel_centres: null argument");
     if (n <= 0) return NBR_OK;
     GridDev g;
-    NBR_TRY(grid_to_dev(grid, &g));
+    NBR_TRY(grid_to_dev(grid, &g, nullptr));
     centre_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(addresses, n, g, xyz_out);
     NBR_LAUNCHED();
     return NBR_OK;

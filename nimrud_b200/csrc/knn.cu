@@ -77,7 +77,7 @@ knn_kernel(LatticeDev L, const void *__restrict__ query, int dtype, int64_t nq, 
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             q[a] = load_coord(query, dtype, qi, 3, a);
-            query_anchor(q[a], g.minc[a], g.inv_edge, c[a], f[a]);
+            query_anchor(q[a], g, a, c[a], f[a]);
         }
         int have = 0;
         long long rho = 2;
@@ -97,9 +97,9 @@ knn_kernel(LatticeDev L, const void *__restrict__ query, int dtype, int64_t nq, 
             int worst_idx = 0x7fffffff;
             if (!empty) {
                 for (int kz = lo[2]; kz <= hi[2]; ++kz) {
-                    const double dz2 = sqdiff(q[2], cell_centre(kz, g.minc[2], g.edge));
+                    const double dz2 = sqdiff(q[2], grid_centre(g, kz, 2));
                     for (int ky = lo[1]; ky <= hi[1]; ++ky) {
-                        const double dy2 = sqdiff(q[1], cell_centre(ky, g.minc[1], g.edge));
+                        const double dy2 = sqdiff(q[1], grid_centre(g, ky, 1));
                         const int word = ((kz & (BRICK_Z - 1)) << BRICK_YS) | (ky & (BRICK_Y - 1));
                         const int64_t rowb = ((int64_t)(kz >> BRICK_ZS) * L.nby + (ky >> BRICK_YS)) * L.nbx;
                         for (int bx = lo[0] >> BRICK_XS; bx <= hi[0] >> BRICK_XS; ++bx) {
@@ -118,7 +118,7 @@ knn_kernel(LatticeDev L, const void *__restrict__ query, int dtype, int64_t nq, 
                             e.kx = x0 + lane; e.ky = ky; e.kz = kz;
                             e.d2 = INFINITY; e.idx = 0;
                             if (cand) {
-                                double s = sqdiff(q[0], cell_centre(e.kx, g.minc[0], g.edge));
+                                double s = sqdiff(q[0], grid_centre(g, e.kx, 0));
                                 s = __dadd_rn(s, dy2);
                                 s = __dadd_rn(s, dz2);
                                 e.d2 = s;

@@ -26,10 +26,10 @@ struct Lattice {
 };
 
 int lattice_create(Lattice **out, const void *xyz, int dtype, int64_t n, const nbr_grid *grid, int flags,
-                   cudaStream_t stream);
+                   cudaStream_t stream, const double *local_lohi = nullptr);
 int lattice_counts(const Lattice *L, int64_t *n_voxels, int64_t *n_bricks);
 int bbox(const void *xyz, int dtype, int64_t n, int ndim, double *lohi_dev, cudaStream_t stream);
 int grid_from_bbox(const double lo[3], const double hi[3], double edge, int ndim, nbr_grid *out);
-int grid_to_dev(const nbr_grid *g, GridDev *d);
+int grid_to_dev(const nbr_grid *g, GridDev *d, const double *local_lohi);
 
 }  // namespace nbr

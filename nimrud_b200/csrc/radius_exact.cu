@@ -28,10 +28,10 @@ __device__ __forceinline__ void for_each_member(const LatticeDev &L, const doubl
         if (c[a] < -W - 1 || lo[a] > hi[a]) return;
     }
     for (int kz = lo[2]; kz <= hi[2]; ++kz) {
-        const double dz2 = sqdiff(q[2], cell_centre(kz, g.minc[2], g.edge));
+        const double dz2 = sqdiff(q[2], grid_centre(g, kz, 2));
         if (dz2 > r2) continue;
         for (int ky = lo[1]; ky <= hi[1]; ++ky) {
-            const double dy2 = sqdiff(q[1], cell_centre(ky, g.minc[1], g.edge));
+            const double dy2 = sqdiff(q[1], grid_centre(g, ky, 1));
             if (dy2 > r2) continue;
             const int word = ((kz & (BRICK_Z - 1)) << BRICK_YS) | (ky & (BRICK_Y - 1));
             const int64_t rowb = ((int64_t)(kz >> BRICK_ZS) * L.nby + (ky >> BRICK_YS)) * L.nbx;
@@ -47,7 +47,7 @@ __device__ __forceinline__ void for_each_member(const LatticeDev &L, const doubl
                     w &= w - 1;
                     const int kx = x0 + b;
                     // ((dx*dx + dy*dy) + dz*dz) <= r*r, float64, inclusive
-                    double s = sqdiff(q[0], cell_centre(kx, g.minc[0], g.edge));
+                    double s = sqdiff(q[0], grid_centre(g, kx, 0));
                     s = __dadd_rn(s, dy2);
                     s = __dadd_rn(s, dz2);
                     if (s <= r2) fn(kx - c[0], ky - c[1], kz - c[2], slot, word, b);
@@ -75,7 +75,7 @@ radius_features_exact_kernel(LatticeDev L, const void *__restrict__ query, int d
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         q[a] = load_coord(query, dtype, i, 3, a);
-        query_anchor(q[a], L.g.minc[a], L.g.inv_edge, c[a], f[a]);
+        query_anchor(q[a], L.g, a, c[a], f[a]);
     }
     Moments m;
     m.n = 0;
@@ -131,7 +131,7 @@ radius_count_kernel(LatticeDev L, const void *__restrict__ query, int dtype, int
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         q[a] = load_coord(query, dtype, i, 3, a);
-        query_anchor(q[a], L.g.minc[a], L.g.inv_edge, c[a], f);
+        query_anchor(q[a], L.g, a, c[a], f);
     }
     long long n = 0;
     for_each_member(L, q, c, radius, [&](int, int, int, uint32_t, int, int) { ++n; });
@@ -149,7 +149,7 @@ radius_fill_kernel(LatticeDev L, const void *__restrict__ query, int dtype, int6
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         q[a] = load_coord(query, dtype, i, 3, a);
-        query_anchor(q[a], L.g.minc[a], L.g.inv_edge, c[a], f);
+        query_anchor(q[a], L.g, a, c[a], f);
     }
     int32_t *dst = indices + offsets[i];
     for_each_member(L, q, c, radius, [&](int, int, int, uint32_t slot, int word, int b) {

@@ -56,11 +56,11 @@ __device__ __noinline__ uint32_t exact_row_mask(const GridDev &g, double qx, dou
                                                 int kz, int W, double radius)
 {
     const double r2 = __dmul_rn(radius, radius);
-    const double dy2 = sqdiff(qy, cell_centre(ky, g.minc[1], g.edge));
-    const double dz2 = sqdiff(qz, cell_centre(kz, g.minc[2], g.edge));
+    const double dy2 = sqdiff(qy, grid_centre(g, ky, 1));
+    const double dz2 = sqdiff(qz, grid_centre(g, kz, 2));
     uint32_t m = 0;
     for (int t = 0; t <= 2 * W; ++t) {
-        double s = sqdiff(qx, cell_centre((long long)cx - W + t, g.minc[0], g.edge));
+        double s = sqdiff(qx, grid_centre(g, (long long)cx - W + t, 0));
         s = __dadd_rn(s, dy2);
         s = __dadd_rn(s, dz2);
         if (s <= r2) m |= 1u << t;
@@ -337,7 +337,7 @@ radius_rows_kernel(const RowsLaunch *__restrict__ launch, const void *__restrict
             const GridDev &g = L.g;
             double f[3];
 #pragma unroll
-            for (int a = 0; a < 3; ++a) query_anchor(X.q[a], g.minc[a], g.inv_edge, X.c[a], f[a]);
+            for (int a = 0; a < 3; ++a) query_anchor(X.q[a], g, a, X.c[a], f[a]);
             // every window of half-width <= 3 runs through the one W = 3 code path (rows beyond the ball just
             // fail the disc test)
             const int W = P.wmax <= 3 ? 3 : P.wmax;

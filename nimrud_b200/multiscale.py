@@ -64,7 +64,8 @@ def _check_inputs(query_cloud, search_cloud):
 
 
 def process_single_core(query_cloud, search_cloud, edge_lengths, radii, verbose=False,
-                        out_dtype=np.float64, descriptors="reference", return_voxel_counts=False):
+                        out_dtype=np.float64, descriptors="reference", return_voxel_counts=False,
+                        global_bbox=None, out=None):
     """
     compute features at multiple scales. returns an array of feature vectors aligned with the query
     cloud.  (reference: multiscale.py:27-67)
@@ -73,6 +74,10 @@ def process_single_core(query_cloud, search_cloud, edge_lengths, radii, verbose=
       out_dtype            float64 (drop-in) or float32
       descriptors          "reference" (4 columns per scale) or "extended" (16 columns per scale)
       return_voxel_counts  also return the number of unique search voxels per scale
+      global_bbox          (lo, hi) of the WHOLE search cloud when `search_cloud` is only a tile of it
+                           (+ halo): the voxel lattices are anchored on that box, so every tile sees the
+                           same voxels (multi-GPU path, CUDA tensors only)
+      out                  preallocated CUDA output tensor (CUDA tensors only)
     """
     assert(len(edge_lengths) == len(radii)), \
         "edge_lengths and radii should be equal-length sequences."
@@ -95,12 +100,22 @@ def process_single_core(query_cloud, search_cloud, edge_lengths, radii, verbose=
             s, sc = q, qc
         else:
             s, sc = device_cloud(search_cloud, q.device)
-        out = torch.zeros((nq, ncol * n_scales), dtype=_TORCH_OUT[np_out], device=q.device)
+        if out is None:
+            out = torch.zeros((nq, ncol * n_scales), dtype=_TORCH_OUT[np_out], device=q.device)
+        elif (tuple(out.shape) != (nq, ncol * n_scales) or out.dtype != _TORCH_OUT[np_out] or not out.is_cuda
+              or not out.is_contiguous()):
+            raise ValueError("out has the wrong shape, dtype or device")
+        box_p = None
+        if global_bbox is not None:
+            box_arr, box_p = _lib.f64_array(np.concatenate([np.asarray(global_bbox[0], dtype=np.float64),
+                                                             np.asarray(global_bbox[1], dtype=np.float64)]))
         with torch.cuda.device(q.device):
             _lib.check(_lib.lib().nbr_multiscale_features(
-                ptr(q), qc, nq, ptr(s), sc, ns, edges_p, radii_p, n_scales, ptr(out), out_code, mask, None,
+                ptr(q), qc, nq, ptr(s), sc, ns, edges_p, radii_p, n_scales, ptr(out), out_code, mask, box_p,
                 counts_p, stream_ptr(q.device)))
     else:
+        if global_bbox is not None or out is not None:
+            raise ValueError("global_bbox / out are only supported for CUDA tensor inputs")
         q, qc = host_cloud(query_cloud.cpu().numpy() if is_torch(query_cloud) else query_cloud)
         if search_cloud is query_cloud:
             s, sc = q, qc

@@ -1,0 +1,81 @@
+"""
+world_size-2 gloo test of the multi-GPU host logic (box reduction, halo selection, all-to-all-v, gather):
+tile + halo with globally anchored lattices must reproduce the unpartitioned result bit for bit.
+the compute function injected here is the oracle (the CUDA path cannot run in this container).
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+EDGES = (0.2, 0.5)
+RADII = (0.6, 1.5)
+
+
+def anchored_oracle(query, search, edges, radii, bbox, out_dtype, out):
+    """oracle features with the voxel lattice anchored on `bbox` instead of on search's own box."""
+    from oracle import nimrud_oracle as O
+    q = query.numpy().astype(np.float64)
+    s = search.numpy().astype(np.float64)
+    blocks = []
+    for e, r in zip(edges, radii):
+        params = O.GridParams(bbox[0] - e / 2, bbox[1] + e / 2, e)
+        _, centres = O.unique_voxels(params, s)
+        off, idx = O.radius_sets(q, centres, r)
+        blocks.append(O.rows_from_sets(q, centres, off, idx))
+    return torch.from_numpy(np.concatenate(blocks, axis=1))
+
+
+def make_cloud():
+    rs = np.random.RandomState(7)
+    pts = rs.rand(1600, 3) * [8.0, 4.0, 1.5]
+    return pts.astype(np.float32)
+
+
+def worker(rank, world, port, tmp):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nimrud_b200 import distributed as nd
+    cloud = make_cloud()
+    left = cloud[:, 0] < 4.0
+    mine = torch.from_numpy(cloud[left] if rank == 0 else cloud[~left])
+    halo, (g_lo, g_hi), _ = nd.exchange_halo(mine, EDGES, RADII)
+    # the halo is exactly the foreign points within h of my box
+    other = torch.from_numpy(cloud[~left] if rank == 0 else cloud[left])
+    lo, hi = nd.tile_box(mine)
+    expect = other[nd.select_halo(other, lo, hi, nd.halo_width(EDGES, RADII))]
+    assert halo.shape == expect.shape and torch.equal(halo, expect)
+    assert torch.equal(g_lo, torch.from_numpy(cloud.astype(np.float64).min(0)))
+    assert torch.equal(g_hi, torch.from_numpy(cloud.astype(np.float64).max(0)))
+    feats = nd.process_tile(mine, EDGES, RADII, gather=True, compute=anchored_oracle)
+    if rank == 0:
+        np.save(os.path.join(tmp, "gathered.npy"), feats.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_tile_plus_halo_equals_unpartitioned(tmp_path):
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = np.load(os.path.join(str(tmp_path), "gathered.npy"))
+    from oracle import nimrud_oracle as O
+    cloud = make_cloud().astype(np.float64)
+    left = cloud[:, 0] < 4.0
+    order = np.concatenate([np.nonzero(left)[0], np.nonzero(~left)[0]])
+    ref = O.process(cloud, cloud, EDGES, RADII)[order]
+    assert got.shape == ref.shape
+    assert np.array_equal(got, ref)          # bit for bit: same voxels, same neighbor sets
+
+
+def test_halo_width_rule():
+    from nimrud_b200 import distributed as nd
+    assert nd.halo_width((0.1, 1.6), (0.3, 4.8)) >= 4.8 + 0.8
