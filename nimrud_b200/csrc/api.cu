@@ -81,9 +81,9 @@ PhaseTimer::~PhaseTimer()
     g_spans.push_back({phase, start, stop});
 }
 
-int radius_features_exact(const Lattice *lat, const void *query, int dtype, int64_t nq, const double *radii, int nr,
-                          void *out, int out_dtype, int64_t row_stride, int col_offset, int descriptor_mask,
-                          cudaStream_t stream);
+int radius_features_exact(const Lattice *lat, const void *query, int dtype, const uint32_t *perm, int64_t nq,
+                          const double *radii, int nr, void *out, int out_dtype, int64_t row_stride, int col_offset,
+                          int descriptor_mask, cudaStream_t stream);
 int morton_order(const void *xyz, int dtype, int64_t n, const double lohi[6], double cell, uint32_t *perm_out,
                  void *sorted_xyz_out, cudaStream_t stream);
 int radius_sets(const Lattice *lat, const void *query, int dtype, int64_t nq, double radius, int64_t *offsets,
@@ -118,8 +118,7 @@ int radius_features(const Lattice *lat, const void *query, int dtype, const uint
         return NBR_OK;
     }
     if (algorithm == 2) return fail(NBR_ERR_UNSUPPORTED, "radius_features: row-interval kernel does not cover this r/e");
-    if (perm) return fail(NBR_ERR_INVALID, "radius_features: the exact kernel takes queries in natural order");
-    return radius_features_exact(lat, query, dtype, nq, radii, nr, out, out_dtype, row_stride, col_offset,
+    return radius_features_exact(lat, query, dtype, perm, nq, radii, nr, out, out_dtype, row_stride, col_offset,
                                  descriptor_mask, stream);
 }
 
@@ -129,6 +128,20 @@ int radius_features(const Lattice *lat, const void *query, int dtype, const uint
 // (all radii of a lattice share one pass over each query's window).  scales the row kernel cannot take
 // (r/e > 9.5) go through the exact kernel.
 // ------------------------------------------------------------------------------------------------
+// bounding box of a device cloud, copied to the host (synchronises the stream)
+static int host_bbox(const void *xyz, int dtype, int64_t n, double *lohi_host, cudaStream_t stream)
+{
+    Scratch box;
+    NBR_TRY(box.alloc(sizeof(double) * 6, stream));
+    {
+        PhaseTimer t(PHASE_BBOX, stream);
+        NBR_TRY(bbox(xyz, dtype, n, 3, box.as<double>(), stream));
+    }
+    NBR_CUDA(cudaMemcpyAsync(lohi_host, box.ptr, sizeof(double) * 6, cudaMemcpyDeviceToHost, stream));
+    NBR_CUDA(cudaStreamSynchronize(stream));
+    return NBR_OK;
+}
+
 struct Plan {
     struct Group { double edge; Lattice *lat; std::vector<int> scales; };
     std::vector<Group> groups;
@@ -140,7 +153,8 @@ struct Plan {
 };
 
 int plan_create(Plan **out, const void *search, int s_dtype, int64_t ns, const double *edges, const double *radii,
-                int n_scales, int descriptor_mask, const double *global_lohi, cudaStream_t stream)
+                int n_scales, int descriptor_mask, const double *global_lohi, const double *known_local_box,
+                cudaStream_t stream)
 {
     NBR_TRY(check_cloud_dtype(s_dtype, "multiscale_features"));
     if (n_scales < 0) return fail(NBR_ERR_INVALID, "multiscale_features: negative number of scales");
@@ -159,16 +173,10 @@ int plan_create(Plan **out, const void *search, int s_dtype, int64_t ns, const d
     // bounding box of the search cloud given to this call.  with global_lohi (multi-GPU: the all-reduced
     // box) the lattices are ANCHORED on the global box but their directories only cover this local box.
     int rc = NBR_OK;
-    {
-        Scratch box;
-        rc = box.alloc(sizeof(double) * 6, stream);
-        if (!rc) {
-            PhaseTimer t(PHASE_BBOX, stream);
-            rc = bbox(search, s_dtype, ns, 3, box.as<double>(), stream);
-        }
-        if (!rc && (cudaMemcpyAsync(P->local_box, box.ptr, sizeof(P->local_box), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
-                    cudaStreamSynchronize(stream) != cudaSuccess))
-            rc = fail(NBR_ERR_CUDA, "multiscale_features: bounding box copy failed");
+    if (known_local_box) {
+        std::copy(known_local_box, known_local_box + 6, P->local_box);
+    } else {
+        rc = host_bbox(search, s_dtype, ns, P->local_box, stream);
     }
     if (rc) { delete P; return rc; }
     const double *lohi = global_lohi ? global_lohi : P->local_box;
@@ -193,45 +201,21 @@ int plan_create(Plan **out, const void *search, int s_dtype, int64_t ns, const d
     return NBR_OK;
 }
 
-// features of one batch of queries -> rows [0, nq) of `out` (row stride = ncol * n_scales)
-// qbox: bounding box of the batch if the caller knows it (else computed)
-int plan_run(const Plan *P, const void *query, int q_dtype, int64_t nq, const double *qbox_known, void *out,
-             int out_dtype, cudaStream_t stream)
+// features of one batch of queries that is already in a coherent order: row i of `sorted` is query
+// perm[i] (perm == NULL: identity) and its features go to row perm[i] of `out`
+int plan_run_sorted(const Plan *P, const void *sorted, int q_dtype, const uint32_t *perm, int64_t nq, void *out,
+                    int out_dtype, cudaStream_t stream)
 {
-    NBR_TRY(check_cloud_dtype(q_dtype, "multiscale_features"));
     if (out_dtype != NBR_F32 && out_dtype != NBR_F64) return fail(NBR_ERR_INVALID, "multiscale_features: bad out_dtype");
     if (nq <= 0 || P->n_scales == 0) return NBR_OK;
-    if (!query || !out) return fail(NBR_ERR_INVALID, "multiscale_features: null argument");
     const int ncol = P->ncol;
     const int64_t row_stride = (int64_t)ncol * P->n_scales;
-
-    // ---- processing order of the queries: Morton curve, cells of 2 finest voxels; sorted copy of the cloud
-    Scratch perm, sorted;
-    NBR_TRY(perm.alloc(sizeof(uint32_t) * nq, stream));
-    NBR_TRY(sorted.alloc((size_t)nq * 3 * (q_dtype == NBR_F32 ? 4 : 8), stream));
-    {
-        PhaseTimer t(PHASE_ORDER, stream);
-        double qbox[6];
-        if (qbox_known) {
-            std::copy(qbox_known, qbox_known + 6, qbox);
-        } else {
-            Scratch box;
-            NBR_TRY(box.alloc(sizeof(double) * 6, stream));
-            NBR_TRY(bbox(query, q_dtype, nq, 3, box.as<double>(), stream));
-            NBR_CUDA(cudaMemcpyAsync(qbox, box.ptr, sizeof(qbox), cudaMemcpyDeviceToHost, stream));
-            NBR_CUDA(cudaStreamSynchronize(stream));
-        }
-        NBR_TRY(morton_order(query, q_dtype, nq, qbox, 2.0 * P->finest, perm.as<uint32_t>(), sorted.ptr, stream));
-    }
-
-    // ---- fused launches
     PhaseTimer tm(PHASE_FEATURES, stream);
     RowsLaunch launch;
     memset(&launch, 0, sizeof(launch));
     auto flush = [&]() -> int {
         if (launch.n_lat == 0) return NBR_OK;
-        int r = radius_rows_launch(&launch, sorted.ptr, q_dtype, perm.as<uint32_t>(), nq, out, out_dtype, row_stride,
-                                   P->descriptor_mask, stream);
+        int r = radius_rows_launch(&launch, sorted, q_dtype, perm, nq, out, out_dtype, row_stride, P->descriptor_mask, stream);
         memset(&launch, 0, sizeof(launch));
         return r;
     };
@@ -241,7 +225,7 @@ int plan_run(const Plan *P, const void *query, int q_dtype, int64_t nq, const do
         for (int s : g.scales) {
             if (rows_supported(g.edge, &P->radii[s], 1)) { rr.push_back(P->radii[s]); cc.push_back(s * ncol); }
             else
-                NBR_TRY(radius_features_exact(g.lat, query, q_dtype, nq, &P->radii[s], 1, out, out_dtype, row_stride,
+                NBR_TRY(radius_features_exact(g.lat, sorted, q_dtype, perm, nq, &P->radii[s], 1, out, out_dtype, row_stride,
                                               s * ncol, P->descriptor_mask, stream));
         }
         for (size_t base = 0; base < rr.size(); base += RW_MAX_RADII) {
@@ -253,6 +237,31 @@ int plan_run(const Plan *P, const void *query, int q_dtype, int64_t nq, const do
         }
     }
     return flush();
+}
+
+// Morton order of a cloud (cells of 4 finest voxels) + the cloud in that order
+int order_queries(const void *query, int q_dtype, int64_t nq, const double *qbox_known, double finest, Scratch &perm,
+                  Scratch &sorted, cudaStream_t stream)
+{
+    NBR_TRY(perm.alloc(sizeof(uint32_t) * nq, stream));
+    NBR_TRY(sorted.alloc((size_t)nq * 3 * (q_dtype == NBR_F32 ? 4 : 8), stream));
+    double qbox[6];
+    if (qbox_known) std::copy(qbox_known, qbox_known + 6, qbox);
+    else NBR_TRY(host_bbox(query, q_dtype, nq, qbox, stream));
+    PhaseTimer t(PHASE_ORDER, stream);
+    return morton_order(query, q_dtype, nq, qbox, 4.0 * finest, perm.as<uint32_t>(), sorted.ptr, stream);
+}
+
+// features of one batch of queries in arbitrary order -> rows [0, nq) of `out`
+int plan_run(const Plan *P, const void *query, int q_dtype, int64_t nq, const double *qbox_known, void *out,
+             int out_dtype, cudaStream_t stream)
+{
+    NBR_TRY(check_cloud_dtype(q_dtype, "multiscale_features"));
+    if (nq <= 0 || P->n_scales == 0) return NBR_OK;
+    if (!query || !out) return fail(NBR_ERR_INVALID, "multiscale_features: null argument");
+    Scratch perm, sorted;
+    NBR_TRY(order_queries(query, q_dtype, nq, qbox_known, P->finest, perm, sorted, stream));
+    return plan_run_sorted(P, sorted.ptr, q_dtype, perm.as<uint32_t>(), nq, out, out_dtype, stream);
 }
 
 int plan_voxel_counts(const Plan *P, int64_t *n_voxels_host)
@@ -270,10 +279,32 @@ int multiscale_features(const void *query, int q_dtype, int64_t nq, const void *
                         int descriptor_mask, const double *global_lohi, int64_t *n_voxels_host, cudaStream_t stream)
 {
     if (nq < 0) return fail(NBR_ERR_INVALID, "multiscale_features: negative size");
+    NBR_TRY(check_cloud_dtype(q_dtype, "multiscale_features"));
+    NBR_TRY(check_cloud_dtype(s_dtype, "multiscale_features"));
+    if (ns < 2) return fail(NBR_ERR_TOO_FEW_POINTS, "need at least 2 points to define a voxel grid");
+    if (!search) return fail(NBR_ERR_INVALID, "multiscale_features: null argument");
+    const bool same = query == search && nq == ns && q_dtype == s_dtype && n_scales > 0 && out;
     Plan *P = nullptr;
-    NBR_TRY(plan_create(&P, search, s_dtype, ns, edges, radii, n_scales, descriptor_mask, global_lohi, stream));
-    const bool same = query == search && nq == ns && q_dtype == s_dtype;
-    int rc = plan_run(P, query, q_dtype, nq, same ? P->local_box : nullptr, out, out_dtype, stream);
+    int rc;
+    if (same) {
+        // query cloud == search cloud: order it once and build the lattices from the ordered copy too
+        // (coalesced directory / pool updates); the lattices do not depend on the order of the points
+        double box[6], finest = 0.0;
+        for (int s = 0; s < n_scales; ++s) {
+            if (!edges || !(edges[s] > 0)) return fail(NBR_ERR_INVALID, "multiscale_features: edge lengths must be > 0");
+            finest = s == 0 ? edges[s] : std::min(finest, edges[s]);
+        }
+        NBR_TRY(host_bbox(search, s_dtype, ns, box, stream));
+        Scratch perm, sorted;
+        NBR_TRY(order_queries(query, q_dtype, nq, box, finest, perm, sorted, stream));
+        NBR_TRY(plan_create(&P, sorted.ptr, s_dtype, ns, edges, radii, n_scales, descriptor_mask, global_lohi, box, stream));
+        rc = plan_run_sorted(P, sorted.ptr, q_dtype, perm.as<uint32_t>(), nq, out, out_dtype, stream);
+        if (rc == NBR_OK && n_voxels_host) rc = plan_voxel_counts(P, n_voxels_host);
+        delete P;
+        return rc;
+    }
+    NBR_TRY(plan_create(&P, search, s_dtype, ns, edges, radii, n_scales, descriptor_mask, global_lohi, nullptr, stream));
+    rc = plan_run(P, query, q_dtype, nq, nullptr, out, out_dtype, stream);
     if (rc == NBR_OK && n_voxels_host) rc = plan_voxel_counts(P, n_voxels_host);
     delete P;
     return rc;
@@ -377,7 +408,7 @@ extern "C" int nbr_multiscale_features_host(const void *query_host, int q_dtype,
         cudaError_t e = cudaSuccess;
         if (!rc) e = cudaMemcpyAsync(s.ptr, search_host, sbytes, cudaMemcpyHostToDevice, stream);
         if (!rc && e == cudaSuccess)
-            rc = plan_create(&P, s.ptr, s_dtype, n_search, edges_host, radii_host, n_scales, descriptor_mask, nullptr, stream);
+            rc = plan_create(&P, s.ptr, s_dtype, n_search, edges_host, radii_host, n_scales, descriptor_mask, nullptr, nullptr, stream);
         for (int64_t first = 0; !rc && e == cudaSuccess && first < n_query; first += batch) {
             const int64_t n = std::min(batch, n_query - first);
             char *qdev = (same ? (char *)s.ptr : (char *)q.ptr) + (size_t)first * qrow;

@@ -113,6 +113,18 @@ __device__ __forceinline__ double cell_coord_f(double p, double minc, double edg
     return floor(__ddiv_rn(__dsub_rn(p, minc), edge));
 }
 
+// the same value without the division in the common case: u = (p - min_corner) * (1/e) is within a few
+// ulp of the quotient, so floor(u) can only differ from floor(quotient) when u sits next to an integer;
+// only then is the division done.  bit-identical to cell_coord_f.
+__device__ __forceinline__ double cell_coord_fast(double p, double minc, double edge, double inv_edge)
+{
+    const double d = __dsub_rn(p, minc);
+    const double u = d * inv_edge;
+    const double r = rint(u);
+    if (fabs(u - r) <= 4.0e-15 * fabs(u) + 1e-300) return floor(__ddiv_rn(d, edge));
+    return floor(u);
+}
+
 // (k*e + min_corner) + e*0.5 -- utils/geometry.py:137
 __device__ __forceinline__ double cell_centre(int64_t k, double minc, double edge)
 {

@@ -31,26 +31,27 @@ __device__ __forceinline__ double warp_max(double v)
     return v;
 }
 
-// partial[block][6]
+// partial[block][6].  one point per thread and trip; float32 clouds are reduced in float32 (exact).
+template <typename T, int NDIM>
 __global__ void __launch_bounds__(BBOX_THREADS)
-bbox_partial_kernel(const void *__restrict__ xyz, int dtype, int64_t n, int ndim, double *__restrict__ partial)
+bbox_partial_kernel(const T *__restrict__ xyz, int64_t n, double *__restrict__ partial)
 {
-    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    // flat coalesced sweep over the n*ndim scalars; axis = flat index mod ndim
-    const int64_t total = n * ndim;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        double v = dtype == NBR_F32 ? (double)reinterpret_cast<const float *>(xyz)[i]
-                                    : reinterpret_cast<const double *>(xyz)[i];
-        int a = (int)(i % ndim);
+    T lo[3], hi[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k)
-            if (a == k) { lo[k] = fmin(lo[k], v); hi[k] = fmax(hi[k], v); }
+    for (int k = 0; k < 3; ++k) { lo[k] = (T)INFINITY; hi[k] = (T)-INFINITY; }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < NDIM; ++k) {
+            const T v = xyz[i * NDIM + k];
+            lo[k] = v < lo[k] ? v : lo[k];
+            hi[k] = v > hi[k] ? v : hi[k];
+        }
     }
     __shared__ double s[BBOX_THREADS / 32][6];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        double a = warp_min(lo[k]), b = warp_max(hi[k]);
+        double a = warp_min((double)lo[k]), b = warp_max((double)hi[k]);
         if (lane == 0) { s[warp][k] = a; s[warp][3 + k] = b; }
     }
     __syncthreads();
@@ -62,26 +63,35 @@ bbox_partial_kernel(const void *__restrict__ xyz, int dtype, int64_t n, int ndim
     }
 }
 
+// 6 warps, one per output value
 __global__ void bbox_final_kernel(const double *__restrict__ partial, int blocks, int ndim, double *__restrict__ out)
 {
-    const int k = threadIdx.x;
-    if (k >= 6) return;
-    double r = partial[k];
-    for (int b = 1; b < blocks; ++b) r = k < 3 ? fmin(r, partial[b * 6 + k]) : fmax(r, partial[b * 6 + k]);
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double r = k < 3 ? INFINITY : -INFINITY;
+    for (int b = lane; b < blocks; b += 32) r = k < 3 ? fmin(r, partial[b * 6 + k]) : fmax(r, partial[b * 6 + k]);
+    r = k < 3 ? warp_min(r) : warp_max(r);
     if ((k % 3) >= ndim) r = 0.0;
-    out[k] = r;
+    if (lane == 0) out[k] = r;
 }
 
 int bbox(const void *xyz, int dtype, int64_t n, int ndim, double *lohi_dev, cudaStream_t stream)
 {
     if (n < 1) return fail(NBR_ERR_TOO_FEW_POINTS, "need at least 1 point for a bounding box");
-    int blocks = (int)std::min<int64_t>(ceil_div(n * ndim, BBOX_THREADS * 8), device_sm_count() * 4);
+    int blocks = (int)std::min<int64_t>(ceil_div(n, BBOX_THREADS * 4), device_sm_count() * 8);
     if (blocks < 1) blocks = 1;
     Scratch partial;
     NBR_TRY(partial.alloc(sizeof(double) * 6 * blocks, stream));
-    bbox_partial_kernel<<<blocks, BBOX_THREADS, 0, stream>>>(xyz, dtype, n, ndim, partial.as<double>());
+    double *pp = partial.as<double>();
+    if (dtype == NBR_F32 && ndim == 3)
+        bbox_partial_kernel<float, 3><<<blocks, BBOX_THREADS, 0, stream>>>((const float *)xyz, n, pp);
+    else if (dtype == NBR_F32)
+        bbox_partial_kernel<float, 2><<<blocks, BBOX_THREADS, 0, stream>>>((const float *)xyz, n, pp);
+    else if (ndim == 3)
+        bbox_partial_kernel<double, 3><<<blocks, BBOX_THREADS, 0, stream>>>((const double *)xyz, n, pp);
+    else
+        bbox_partial_kernel<double, 2><<<blocks, BBOX_THREADS, 0, stream>>>((const double *)xyz, n, pp);
     NBR_LAUNCHED();
-    bbox_final_kernel<<<1, 32, 0, stream>>>(partial.as<double>(), blocks, ndim, lohi_dev);
+    bbox_final_kernel<<<1, 192, 0, stream>>>(partial.as<double>(), blocks, ndim, lohi_dev);
     NBR_LAUNCHED();
     return NBR_OK;
 }
@@ -157,7 +167,7 @@ address_kernel(const void *__restrict__ xyz, int dtype, int64_t n, GridDev g, do
         if (a < g.ndim) {
             double p = load_coord(xyz, dtype, i, g.ndim, a);
             bad |= (p < g.minc[a]) | (p > maxc[a]);
-            int64_t k = (int64_t)cell_coord_f(p, g.minc[a], g.edge);
+            int64_t k = (int64_t)cell_coord_fast(p, g.minc[a], g.edge, g.inv_edge);
             a64 += k << g.shifts[a];
         }
     }
@@ -233,7 +243,7 @@ __device__ __forceinline__ void point_cell(const void *xyz, int dtype, int64_t i
         int v = 0;
         if (a < g.ndim) {
             double p = load_coord(xyz, dtype, i, g.ndim, a);
-            double k = cell_coord_f(p, g.minc[a], g.edge) - (double)g.cell_lo[a];
+            double k = cell_coord_fast(p, g.minc[a], g.edge, g.inv_edge) - (double)g.cell_lo[a];
             // search points lie inside the covered range by construction; the clamp defends against a
             // caller-supplied box that does not contain them.
             k = fmin(fmax(k, 0.0), (double)(g.ncell[a] - 1));

@@ -14,7 +14,22 @@ struct MortonParam {
     double inv_cell;
     int bits[3];
     int levels;
+    int common;   // levels present on all three axes
+    // position of bit l of axis a in the key (axes with fewer bits drop out of the upper levels)
+    unsigned char pos[3][21];
 };
+
+// spread the low 21 bits of x so that bit i lands at 3*i
+__device__ __forceinline__ uint64_t spread3(uint32_t v)
+{
+    uint64_t x = v & 0x1fffffu;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
 
 __global__ void __launch_bounds__(256)
 morton_kernel(const void *__restrict__ xyz, int dtype, int64_t n, MortonParam P, uint64_t *__restrict__ keys,
@@ -22,24 +37,21 @@ morton_kernel(const void *__restrict__ xyz, int dtype, int64_t n, MortonParam P,
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    // the order only has to be spatially coherent, so float32 quantisation is fine here
     uint32_t c[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        double v = (load_coord(xyz, dtype, i, 3, a) - P.lo[a]) * P.inv_cell;
-        const double top = (double)((1u << P.bits[a]) - 1u);
-        v = fmin(fmax(v, 0.0), top);
+        float v = (float)(load_coord(xyz, dtype, i, 3, a) - P.lo[a]) * (float)P.inv_cell;
+        const float top = (float)((1u << P.bits[a]) - 1u);
+        v = fminf(fmaxf(v, 0.0f), top);
         c[a] = (uint32_t)v;
     }
-    uint64_t key = 0;
-    int pos = 0;
-    for (int l = 0; l < P.levels; ++l) {
+    // levels shared by all three axes: classic 3-way bit interleave; the rest (axes with more bits) generically
+    const uint32_t low = (1u << P.common) - 1u;
+    uint64_t key = spread3(c[0] & low) | (spread3(c[1] & low) << 1) | (spread3(c[2] & low) << 2);
 #pragma unroll
-        for (int a = 0; a < 3; ++a)
-            if (l < P.bits[a]) {
-                key |= (uint64_t)((c[a] >> l) & 1u) << pos;
-                ++pos;
-            }
-    }
+    for (int a = 0; a < 3; ++a)
+        for (int l = P.common; l < P.bits[a]; ++l) key |= (uint64_t)((c[a] >> l) & 1u) << P.pos[a][l];
     keys[i] = key;
     vals[i] = (uint32_t)i;
 }
@@ -82,6 +94,13 @@ int morton_order(const void *xyz, int dtype, int64_t n, const double lohi[6], do
         P.bits[a] = b;
         P.levels = std::max(P.levels, b);
         total += b;
+    }
+    P.common = std::min(P.bits[0], std::min(P.bits[1], P.bits[2]));
+    {
+        int pos = 0;
+        for (int l = 0; l < P.levels; ++l)
+            for (int a = 0; a < 3; ++a)
+                if (l < P.bits[a]) P.pos[a][l] = (unsigned char)pos++;
     }
     Scratch keys, keys_tmp, vals_tmp;
     NBR_TRY(keys.alloc(sizeof(uint64_t) * n, stream));

@@ -64,8 +64,9 @@ struct RadiiParam {
 
 template <typename OutT>
 __global__ void __launch_bounds__(128)
-radius_features_exact_kernel(LatticeDev L, const void *__restrict__ query, int dtype, int64_t nq, RadiiParam rp,
-                             OutT *__restrict__ out, int64_t row_stride, int col_offset, int descriptor_mask)
+radius_features_exact_kernel(LatticeDev L, const void *__restrict__ query, int dtype,
+                             const uint32_t *__restrict__ perm, int64_t nq, RadiiParam rp, OutT *__restrict__ out,
+                             int64_t row_stride, int col_offset, int descriptor_mask)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nq) return;
@@ -90,12 +91,13 @@ radius_features_exact_kernel(LatticeDev L, const void *__restrict__ query, int d
         m.s2[3] += (long long)jy * jy; m.s2[4] += (long long)jy * jz; m.s2[5] += (long long)jz * jz;
     });
     const int ncol = (descriptor_mask & NBR_DESC_EXTENDED) ? NBR_COLS_EXTENDED : NBR_COLS_REFERENCE;
-    emit_features<OutT>(m, f, L.g.edge, out + i * row_stride + col_offset + ri * ncol, descriptor_mask);
+    const int64_t row = perm ? (int64_t)perm[i] : i;       // queries may come in a sorted order
+    emit_features<OutT>(m, f, L.g.edge, out + row * row_stride + col_offset + ri * ncol, descriptor_mask);
 }
 
-int radius_features_exact(const Lattice *lat, const void *query, int dtype, int64_t nq, const double *radii, int nr,
-                          void *out, int out_dtype, int64_t row_stride, int col_offset, int descriptor_mask,
-                          cudaStream_t stream)
+int radius_features_exact(const Lattice *lat, const void *query, int dtype, const uint32_t *perm, int64_t nq,
+                          const double *radii, int nr, void *out, int out_dtype, int64_t row_stride, int col_offset,
+                          int descriptor_mask, cudaStream_t stream)
 {
     if (nq <= 0 || nr <= 0) return NBR_OK;
     for (int base = 0; base < nr; base += 16) {
@@ -105,11 +107,11 @@ int radius_features_exact(const Lattice *lat, const void *query, int dtype, int6
         const int ncol = (descriptor_mask & NBR_DESC_EXTENDED) ? NBR_COLS_EXTENDED : NBR_COLS_REFERENCE;
         dim3 grid((unsigned)ceil_div(nq, 128), rp.n);
         if (out_dtype == NBR_F32)
-            radius_features_exact_kernel<float><<<grid, 128, 0, stream>>>(lat->dev(), query, dtype, nq, rp, (float *)out,
+            radius_features_exact_kernel<float><<<grid, 128, 0, stream>>>(lat->dev(), query, dtype, perm, nq, rp, (float *)out,
                                                                            row_stride, col_offset + base * ncol,
                                                                            descriptor_mask);
         else
-            radius_features_exact_kernel<double><<<grid, 128, 0, stream>>>(lat->dev(), query, dtype, nq, rp, (double *)out,
+            radius_features_exact_kernel<double><<<grid, 128, 0, stream>>>(lat->dev(), query, dtype, perm, nq, rp, (double *)out,
                                                                             row_stride, col_offset + base * ncol,
                                                                             descriptor_mask);
         NBR_LAUNCHED();

@@ -33,18 +33,29 @@ radix_hist_kernel(const uint64_t *__restrict__ keys, int64_t n, int shift, uint3
     counts[(int64_t)threadIdx.x * tiles + blockIdx.x] = hist[threadIdx.x];
 }
 
+// stable scatter of one tile.  ranks come from warp match_any; the tile is first reordered by digit in
+// shared memory, so that the global writes of each digit are contiguous runs (coalesced).
+// dynamic shared memory: keys[SORT_TILE] (+ vals[SORT_TILE]) + warp_hist[SORT_WARPS][RADIX] + digit tables.
 template <bool HAS_VALUES>
 __global__ void __launch_bounds__(SORT_THREADS)
 radix_scatter_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ keys_out,
                      const uint32_t *__restrict__ vals_in, uint32_t *__restrict__ vals_out, int64_t n,
                      int shift, const uint32_t *__restrict__ offsets, int64_t tiles)
 {
-    __shared__ uint32_t warp_hist[SORT_WARPS][RADIX];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *s_keys = reinterpret_cast<uint64_t *>(smem_raw);
+    uint32_t *s_vals = reinterpret_cast<uint32_t *>(s_keys + SORT_TILE);
+    uint32_t *s_hist = HAS_VALUES ? s_vals + SORT_TILE : s_vals;            // [SORT_WARPS][RADIX]
+    uint32_t *s_start = s_hist + SORT_WARPS * RADIX;                        // [RADIX] first local slot of a digit
+    uint32_t *s_gbase = s_start + RADIX;                                    // [RADIX] global slot of that first one
+    __shared__ uint32_t s_scan[33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&warp_hist[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < SORT_WARPS * RADIX; i += SORT_THREADS) s_hist[i] = 0;
     __syncthreads();
 
-    const int64_t warp_base = (int64_t)blockIdx.x * SORT_TILE + (int64_t)warp * (SORT_ROUNDS * 32);
+    const int64_t tile_base = (int64_t)blockIdx.x * SORT_TILE;
+    const int64_t warp_base = tile_base + (int64_t)warp * (SORT_ROUNDS * 32);
+    const int tile_n = (int)min((int64_t)SORT_TILE, n - tile_base);
     uint64_t key[SORT_ROUNDS];
     uint16_t rank[SORT_ROUNDS];
     const uint32_t lt = lanemask_lt();
@@ -55,22 +66,27 @@ radix_scatter_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict_
         key[r] = valid ? keys_in[i] : ~0ull;
         const uint32_t d = (uint32_t)(key[r] >> shift) & (RADIX - 1);
         const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0x100u);
-        const uint32_t prev = valid ? warp_hist[warp][d] : 0u;
+        const uint32_t prev = valid ? s_hist[warp * RADIX + d] : 0u;
         __syncwarp();
-        if (valid && (peers & lt) == 0) warp_hist[warp][d] = prev + __popc(peers);
+        if (valid && (peers & lt) == 0) s_hist[warp * RADIX + d] = prev + __popc(peers);
         __syncwarp();
         rank[r] = (uint16_t)(prev + __popc(peers & lt));
     }
     __syncthreads();
     {
-        const int d = threadIdx.x;   // one digit per thread
-        uint32_t running = offsets[(int64_t)d * tiles + blockIdx.x];
+        // one digit per thread: exclusive prefix over the warps, the tile total, then the local start
+        const int d = threadIdx.x;
+        uint32_t running = 0;
 #pragma unroll
         for (int w = 0; w < SORT_WARPS; ++w) {
-            uint32_t c = warp_hist[w][d];
-            warp_hist[w][d] = running;
+            const uint32_t c = s_hist[w * RADIX + d];
+            s_hist[w * RADIX + d] = running;
             running += c;
         }
+        uint32_t total;
+        const uint32_t start = block_exclusive_scan<uint32_t>(running, s_scan, &total);
+        s_start[d] = start;
+        s_gbase[d] = offsets[(int64_t)d * tiles + blockIdx.x];
     }
     __syncthreads();
 #pragma unroll
@@ -78,11 +94,25 @@ radix_scatter_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict_
         const int64_t i = warp_base + r * 32 + lane;
         if (i < n) {
             const uint32_t d = (uint32_t)(key[r] >> shift) & (RADIX - 1);
-            const uint32_t pos = warp_hist[warp][d] + rank[r];
-            keys_out[pos] = key[r];
-            if (HAS_VALUES) vals_out[pos] = vals_in[i];
+            const uint32_t pos = s_start[d] + s_hist[warp * RADIX + d] + rank[r];
+            s_keys[pos] = key[r];
+            if (HAS_VALUES) s_vals[pos] = vals_in[i];
         }
     }
+    __syncthreads();
+    for (int pos = threadIdx.x; pos < tile_n; pos += SORT_THREADS) {
+        const uint64_t k = s_keys[pos];
+        const uint32_t d = (uint32_t)(k >> shift) & (RADIX - 1);
+        const uint32_t g = s_gbase[d] + ((uint32_t)pos - s_start[d]);
+        keys_out[g] = k;
+        if (HAS_VALUES) vals_out[g] = s_vals[pos];
+    }
+}
+
+static size_t scatter_smem(bool has_values)
+{
+    return sizeof(uint64_t) * SORT_TILE + (has_values ? sizeof(uint32_t) * SORT_TILE : 0) +
+           sizeof(uint32_t) * (SORT_WARPS * RADIX + 2 * RADIX);
 }
 
 static int radix_sort(uint64_t *keys, uint64_t *keys_tmp, uint32_t *vals, uint32_t *vals_tmp, int64_t n,
@@ -98,14 +128,23 @@ static int radix_sort(uint64_t *keys, uint64_t *keys_tmp, uint32_t *vals, uint32
     uint32_t *c = counts.as<uint32_t>();
     uint64_t *src = keys, *dst = keys_tmp;
     uint32_t *vsrc = vals, *vdst = vals_tmp;
+    const size_t smem = scatter_smem(vals != nullptr);
+    static bool configured = false;
+    if (!configured) {
+        NBR_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)scatter_smem(true)));
+        NBR_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)scatter_smem(false)));
+        configured = true;
+    }
     for (int shift = begin_bit; shift < end_bit; shift += RADIX_BITS) {
         radix_hist_kernel<<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(src, n, shift, c, tiles);
         NBR_LAUNCHED();
         NBR_TRY((exclusive_scan<uint32_t, uint32_t>(c, c, RADIX * tiles, stream)));
         if (vals)
-            radix_scatter_kernel<true><<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(src, dst, vsrc, vdst, n, shift, c, tiles);
+            radix_scatter_kernel<true><<<(unsigned)tiles, SORT_THREADS, smem, stream>>>(src, dst, vsrc, vdst, n, shift, c, tiles);
         else
-            radix_scatter_kernel<false><<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(src, dst, nullptr, nullptr, n, shift, c, tiles);
+            radix_scatter_kernel<false><<<(unsigned)tiles, SORT_THREADS, smem, stream>>>(src, dst, nullptr, nullptr, n, shift, c, tiles);
         NBR_LAUNCHED();
         uint64_t *t = src; src = dst; dst = t;
         uint32_t *vt = vsrc; vsrc = vdst; vdst = vt;
