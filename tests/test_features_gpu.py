@@ -177,3 +177,30 @@ def test_launch_counter_moves():
     pts = np.random.RandomState(0).rand(1000, 3).astype(np.float32)
     multiscale.process_single_core(pts, pts, [0.1], [0.3])
     assert _lib.lib().nbr_kernel_launches() > before
+
+
+def test_raw_ctypes_stub_from_integration_md():
+    # the binding INTEGRATION.md shows a maintainer of the reference: plain ctypes, host buffers, float64
+    import ctypes
+    from nimrud_b200 import _lib
+    g = load_golden("small")
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    lib.nbr_last_error.restype = ctypes.c_char_p
+    f64p = ctypes.POINTER(ctypes.c_double)
+    q = np.ascontiguousarray(g["query"], dtype=np.float64)
+    e = np.ascontiguousarray(g["edges"], dtype=np.float64)
+    r = np.ascontiguousarray(g["radii"], dtype=np.float64)
+    out = np.zeros((len(q), 4 * len(r)))
+    rc = lib.nbr_multiscale_features_host(
+        q.ctypes.data_as(ctypes.c_void_p), 1, ctypes.c_int64(len(q)), q.ctypes.data_as(ctypes.c_void_p), 1,
+        ctypes.c_int64(len(q)), e.ctypes.data_as(f64p), r.ctypes.data_as(f64p), ctypes.c_int32(len(r)),
+        out.ctypes.data_as(ctypes.c_void_p), 1, ctypes.c_int32(0), None)
+    assert rc == 0, lib.nbr_last_error()
+    assert_features_close(out, g["features"], g["radii"])
+    # separate query / search arrays and several batches through the pipelined host path
+    from nimrud_b200 import multiscale, synth
+    cloud = synth.urban_scene(700_000, seed=9).numpy()
+    a = multiscale.process_single_core(cloud[:300_000].copy(), cloud, (0.2, 0.4), (0.6, 1.2))
+    b = multiscale.process_single_core(torch.from_numpy(cloud[:300_000]).cuda(), torch.from_numpy(cloud).cuda(),
+                                       (0.2, 0.4), (0.6, 1.2)).cpu().numpy()
+    assert np.array_equal(a, b)
