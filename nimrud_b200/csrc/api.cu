@@ -112,7 +112,7 @@ int radius_features(const Lattice *lat, const void *query, int dtype, const uint
             for (int k = 0; k < n; ++k) cols[k] = col_offset + (base + k) * ncol;
             launch.n_lat = 1;
             launch.lat[0] = lat->dev();
-            NBR_TRY(rows_param(lat, radii + base, cols, n, &launch.rows[0]));
+            NBR_TRY(rows_param(lat, radii + base, cols, n, &launch.rows[0], stream));
             NBR_TRY(radius_rows_launch(&launch, query, dtype, perm, nq, out, out_dtype, row_stride, descriptor_mask, stream));
         }
         return NBR_OK;
@@ -231,7 +231,7 @@ int plan_run_sorted(const Plan *P, const void *sorted, int q_dtype, const uint32
         for (size_t base = 0; base < rr.size(); base += RW_MAX_RADII) {
             const int n = (int)std::min<size_t>(RW_MAX_RADII, rr.size() - base);
             launch.lat[launch.n_lat] = g.lat->dev();
-            NBR_TRY(rows_param(g.lat, rr.data() + base, cc.data() + base, n, &launch.rows[launch.n_lat]));
+            NBR_TRY(rows_param(g.lat, rr.data() + base, cc.data() + base, n, &launch.rows[launch.n_lat], stream));
             ++launch.n_lat;
             if (launch.n_lat == RW_MAX_LATTICES) NBR_TRY(flush());
         }

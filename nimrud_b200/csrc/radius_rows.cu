@@ -68,6 +68,16 @@ __device__ __noinline__ uint32_t exact_row_mask(const GridDev &g, double qx, dou
     return m;
 }
 
+// one cell, the reference's float64 expression
+__device__ __noinline__ bool exact_cell_in(const GridDev &g, double qx, double qy, double qz, long long kx, long long ky,
+                                           long long kz, double radius)
+{
+    double s = sqdiff(qx, grid_centre(g, kx, 0));
+    s = __dadd_rn(s, sqdiff(qy, grid_centre(g, ky, 1)));
+    s = __dadd_rn(s, sqdiff(qz, grid_centre(g, kz, 2)));
+    return s <= __dmul_rn(radius, radius);
+}
+
 // everything a lane needs to know about one (query, lattice)
 struct LaneCtx {
     double q[3];
@@ -193,7 +203,7 @@ __device__ __noinline__ void lane_rows(const LatticeDev &L, const RowsParam &P, 
 //           slabs whose bricks are all empty never touch the pool.
 __device__ __forceinline__ void lane_rows_w3(const LatticeDev &L, const RowsParam &P, int ri, const LaneCtx &X,
                                              bool staged, const uint32_t *win, const int lo[3], int nb0, int nb1,
-                                             const uint32_t *s_lut10, Acc &A)
+                                             const uint32_t *s_lut10, const uint4 *tab, Acc &A)
 {
     constexpr int W = 3, N = 7;
     const GridDev &g = L.g;
@@ -225,10 +235,15 @@ __device__ __forceinline__ void lane_rows_w3(const LatticeDev &L, const RowsPara
                     slot[iz][iy][ix] = ok ? L.dir[((int64_t)gz * L.nby + gy) * L.nbx + gx] : 0u;
                 }
     }
+    uint4 tnext = tab ? tab[0] : make_uint4(0, 0, 0, 0);
     for (int jz = 0; jz < N; ++jz) {
         const float dz = X.fzm - (float)jz;
         const float Tz = rho2 - dz * dz;
-        if (Tz < t_min) continue;
+        const uint4 tcur = tnext;
+        if (tab) {
+            tnext = tab[jz + 1];                                   // slab 7 is padding
+            if ((tcur.x | tcur.y | tcur.z | tcur.w) == 0) continue;   // no cell of this slab can be in the ball
+        } else if (Tz < t_min) continue;
         const int az = za + jz;
         const int wz = (az & (BRICK_Z - 1)) << BRICK_YS;
         // ---- gather the slab: bits of row jy at [7*jy, 7*jy+7)
@@ -260,9 +275,48 @@ __device__ __forceinline__ void lane_rows_w3(const LatticeDev &L, const RowsPara
             }
         }
         if (slab == 0) continue;
-        // ---- rolled walk over the rows
         uint32_t Pk = 0, Qk = 0;
         int R = 0;
+        if (tab) {
+            // ---- shell table: cells that are inside for the whole bin of f, plus the occupied cells of the
+            // uncertain shell, each decided by the reference's float64 expression
+            unsigned long long M = slab & ((unsigned long long)tcur.x | ((unsigned long long)tcur.y << 32));
+            unsigned long long U = slab & ((unsigned long long)tcur.z | ((unsigned long long)tcur.w << 32));
+            if (U) {
+                // float32 first: |d^2 - rho^2| > band decides; inside the band the reference's float64 expression does
+                const float dzf = X.fzm - (float)jz;
+                const float dz2f = dzf * dzf;
+                uint32_t ulo = (uint32_t)U, uhi = (uint32_t)(U >> 32);
+                uint32_t alo = 0, ahi = 0;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t u = half ? uhi : ulo, acc = 0;
+                    while (u) {
+                        const int b = __ffs(u) - 1;
+                        u &= u - 1;
+                        const int i = b + 32 * half;
+                        const int jy = (i * 37) >> 8, t = i - 7 * jy;
+                        const float dx = X.fxm - (float)t, dy = X.fym - (float)jy;
+                        const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz2f));
+                        bool in = d2 < rho2;
+                        if (fabsf(d2 - rho2) < 4.0e-5f)
+                            in = exact_cell_in(g, X.q[0], X.q[1], X.q[2], (long long)xa + t, (long long)ya + jy, az, P.r[ri]);
+                        acc |= in ? 1u << b : 0u;
+                    }
+                    if (half) ahi = acc; else alo = acc;
+                }
+                M |= (unsigned long long)alo | ((unsigned long long)ahi << 32);
+            }
+            if (M == 0) continue;
+#pragma unroll
+            for (int jy = 0; jy < N; ++jy) {
+                const uint32_t e = s_lut10[(uint32_t)(M >> (N * jy)) & rowmask];
+                Pk += e;
+                Qk += jy * e;
+                R += jy * jy * (int)(e & 1023u);
+            }
+        } else
+        // ---- rolled walk over the rows
 #pragma unroll 1
         for (int jy = 0; jy < N; ++jy) {
             const uint32_t bits = (uint32_t)(slab >> (N * jy)) & rowmask;
@@ -345,6 +399,13 @@ radius_rows_kernel(const RowsLaunch *__restrict__ launch, const void *__restrict
             X.fxm = (float)f[0] - 0.5f + (float)W;
             X.fym = (float)f[1] - 0.5f + (float)W;
             X.fzm = (float)f[2] - 0.5f + (float)W;
+            // bin of f for the shell tables
+            const int tq = P.tq;
+            const int tbin = (min((int)(f[2] * tq), tq - 1) * tq + min((int)(f[1] * tq), tq - 1)) * tq +
+                             min((int)(f[0] * tq), tq - 1);
+            // the bin's 128-byte line is needed after the staging wait: pull it into L1 now
+            for (int ri = 0; ri < P.n; ++ri)
+                if (P.table[ri]) asm volatile("prefetch.global.L1 [%0];" ::"l"(P.table[ri] + (size_t)tbin * 8));
 
             // ---- brick window of the whole warp
             int lo[3], nb[3];
@@ -397,7 +458,8 @@ radius_rows_kernel(const RowsLaunch *__restrict__ launch, const void *__restrict
 
             for (int ri = 0; ri < P.n; ++ri) {
                 Acc A = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-                if (W == 3)      lane_rows_w3(L, P, ri, X, staged, win, lo, nb[0], nb[1], s_lut10, A);
+                if (W == 3)      lane_rows_w3(L, P, ri, X, staged, win, lo, nb[0], nb[1], s_lut10,
+                                                  P.table[ri] ? P.table[ri] + (size_t)tbin * 8 : nullptr, A);
                 else if (staged) lane_rows<true>(L, P, ri, X, win, lo, nb[0], nb[1], s_lut, A);
                 else             lane_rows<false>(L, P, ri, X, win, lo, nb[0], nb[1], s_lut, A);
                 if (active)
@@ -409,7 +471,7 @@ radius_rows_kernel(const RowsLaunch *__restrict__ launch, const void *__restrict
     }
 }
 
-int rows_param(const Lattice *lat, const double *radii, const int *cols, int nr, RowsParam *P)
+int rows_param(const Lattice *lat, const double *radii, const int *cols, int nr, RowsParam *P, cudaStream_t stream)
 {
     const double e = lat->grid.edge;
     if (nr > RW_MAX_RADII) return fail(NBR_ERR_INVALID, "rows_param: too many radii in one group");
@@ -430,6 +492,22 @@ int rows_param(const Lattice *lat, const double *radii, const int *cols, int nr,
         P->t_min[k] = (float)(-16.0 * 5.96e-8 * mag);
     }
     P->eps_b = (float)(4.77e-7 * (weff + 1.0));
+    // shell tables for W = 3 windows.  margin (squared distance, cell units): the reference expression and the
+    // kernel's f are each off by a few ulp of the largest coordinate magnitude, scaled by 2*(W+1) cells
+    static const bool no_table = getenv("NBR_NO_BALL_TABLE") != nullptr;
+    static const int q_env = getenv("NBR_BALL_Q") ? atoi(getenv("NBR_BALL_Q")) : 0;
+    P->tq = q_env >= 1 && q_env <= 64 ? q_env : 16;
+    for (int k = 0; k < nr; ++k) P->table[k] = nullptr;
+    if (weff == 3 && !no_table) {
+        double maxabs = 0.0;
+        for (int a = 0; a < 3; ++a)
+            maxabs = std::max(maxabs, std::max(fabs(lat->grid.min_corner[a]), fabs(lat->grid.max_corner[a])));
+        const double margin = std::max(1e-11, 64.0 * 2.3e-16 * (maxabs / e + 8.0));
+        for (int k = 0; k < nr; ++k) {
+            const double rho = radii[k] / e;
+            NBR_TRY(ball_table_get(rho * rho, margin, P->tq, &P->table[k], stream));
+        }
+    }
     return NBR_OK;
 }
 

@@ -18,10 +18,11 @@ struct RowsParam {
     float t_min[RW_MAX_RADII];   // rows with T < t_min are certainly empty
     int w[RW_MAX_RADII];         // window half-width of each radius
     int col[RW_MAX_RADII];       // first output column of each radius
+    const uint4 *table[RW_MAX_RADII];   // shell table of each radius (ball_table.cu), or NULL: interval walk
     float eps_b;
     int n;
     int wmax;
-    int pad;
+    int tq;                      // bins per axis of the shell tables
 };
 
 struct RowsLaunch {
@@ -32,7 +33,8 @@ struct RowsLaunch {
     int pad;
 };
 
-int rows_param(const Lattice *lat, const double *radii, const int *cols, int nr, RowsParam *P);
+int rows_param(const Lattice *lat, const double *radii, const int *cols, int nr, RowsParam *P, cudaStream_t stream);
+int ball_table_get(double rho2, double margin, int Q, const uint4 **out, cudaStream_t stream);
 bool rows_supported(double edge, const double *radii, int nr);
 int radius_rows_launch(const RowsLaunch *launch_host, const void *query, int dtype, const uint32_t *perm, int64_t nq,
                        void *out, int out_dtype, int64_t row_stride, int descriptor_mask, cudaStream_t stream);
