@@ -104,15 +104,34 @@ int radius_features(const Lattice *lat, const void *query, int dtype, const uint
         if (!(radii[k] >= 0)) return fail(NBR_ERR_INVALID, "radius_features: radii must be >= 0");
     const int ncol = (descriptor_mask & NBR_DESC_EXTENDED) ? NBR_COLS_EXTENDED : NBR_COLS_REFERENCE;
     if (algorithm != 1 && rows_supported(lat->grid.edge, radii, nr)) {
-        for (int base = 0; base < nr; base += RW_MAX_RADII) {
+        // 7x7x7 windows go through the lean kernel, wider ones through the interval kernel
+        R3Launch r3;
+        memset(&r3, 0, sizeof(r3));
+        std::vector<double> rr;
+        std::vector<int> cc;
+        for (int k = 0; k < nr; ++k) {
+            R3Entry E;
+            int rc = NBR_OK;
+            if (rows3_entry(lat, radii[k], col_offset + k * ncol, r3.n ? &r3.e[r3.n - 1] : nullptr, &E, &r3.tq, stream, &rc)) {
+                r3.e[r3.n++] = E;
+                if (r3.n == R3_MAX_ENTRIES) {
+                    NBR_TRY(rows3_launch(&r3, query, dtype, perm, nq, out, out_dtype, row_stride, descriptor_mask, stream));
+                    r3.n = 0;
+                }
+                continue;
+            }
+            NBR_TRY(rc);
+            rr.push_back(radii[k]);
+            cc.push_back(col_offset + k * ncol);
+        }
+        NBR_TRY(rows3_launch(&r3, query, dtype, perm, nq, out, out_dtype, row_stride, descriptor_mask, stream));
+        for (size_t base = 0; base < rr.size(); base += RW_MAX_RADII) {
             RowsLaunch launch;
             memset(&launch, 0, sizeof(launch));
-            const int n = std::min(RW_MAX_RADII, nr - base);
-            int cols[RW_MAX_RADII];
-            for (int k = 0; k < n; ++k) cols[k] = col_offset + (base + k) * ncol;
+            const int n = (int)std::min<size_t>(RW_MAX_RADII, rr.size() - base);
             launch.n_lat = 1;
             launch.lat[0] = lat->dev();
-            NBR_TRY(rows_param(lat, radii + base, cols, n, &launch.rows[0], stream));
+            NBR_TRY(rows_param(lat, rr.data() + base, cc.data() + base, n, &launch.rows[0], stream));
             NBR_TRY(radius_rows_launch(&launch, query, dtype, perm, nq, out, out_dtype, row_stride, descriptor_mask, stream));
         }
         return NBR_OK;
@@ -219,10 +238,23 @@ int plan_run_sorted(const Plan *P, const void *sorted, int q_dtype, const uint32
         memset(&launch, 0, sizeof(launch));
         return r;
     };
+    R3Launch r3;
+    memset(&r3, 0, sizeof(r3));
     for (auto &g : P->groups) {
         std::vector<double> rr;
         std::vector<int> cc;
         for (int s : g.scales) {
+            R3Entry E;
+            int rc = NBR_OK;
+            if (rows3_entry(g.lat, P->radii[s], s * ncol, r3.n ? &r3.e[r3.n - 1] : nullptr, &E, &r3.tq, stream, &rc)) {
+                r3.e[r3.n++] = E;
+                if (r3.n == R3_MAX_ENTRIES) {
+                    NBR_TRY(rows3_launch(&r3, sorted, q_dtype, perm, nq, out, out_dtype, row_stride, P->descriptor_mask, stream));
+                    r3.n = 0;
+                }
+                continue;
+            }
+            NBR_TRY(rc);
             if (rows_supported(g.edge, &P->radii[s], 1)) { rr.push_back(P->radii[s]); cc.push_back(s * ncol); }
             else
                 NBR_TRY(radius_features_exact(g.lat, sorted, q_dtype, perm, nq, &P->radii[s], 1, out, out_dtype, row_stride,
@@ -236,6 +268,7 @@ int plan_run_sorted(const Plan *P, const void *sorted, int q_dtype, const uint32
             if (launch.n_lat == RW_MAX_LATTICES) NBR_TRY(flush());
         }
     }
+    NBR_TRY(rows3_launch(&r3, sorted, q_dtype, perm, nq, out, out_dtype, row_stride, P->descriptor_mask, stream));
     return flush();
 }
 

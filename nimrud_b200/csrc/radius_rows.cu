@@ -425,6 +425,7 @@ radius_rows_kernel(const RowsLaunch *__restrict__ launch, const void *__restrict
                 unsigned long long *st = launch->stats + li * 8;
                 atomicAdd(st + (staged ? 0 : 1), 1ull);
                 if (staged) atomicAdd(st + 2, (unsigned long long)vol);
+                else atomicAdd(st + (vol <= 64 ? 3 : vol <= 96 ? 4 : vol <= 128 ? 5 : vol <= 256 ? 6 : 7), 1ull);
             }
 
             if (staged) {
@@ -551,6 +552,9 @@ int radius_rows_launch(const RowsLaunch *launch_host, const void *query, int dty
             fprintf(stderr, "[nbr row stats] lattice %d edge %.3g W %d: staged warps %llu (avg %.1f bricks), direct warps %llu\n",
                     l, launch_host->lat[l].g.edge, launch_host->rows[l].wmax, h[l * 8], h[l * 8] ? (double)h[l * 8 + 2] / h[l * 8] : 0.0,
                     h[l * 8 + 1]);
+        for (int l = 0; l < launch_host->n_lat; ++l)
+            fprintf(stderr, "[nbr row stats] lattice %d direct warps by window bricks: <=64 %llu, <=96 %llu, <=128 %llu, <=256 %llu, more %llu\n",
+                    l, h[l * 8 + 3], h[l * 8 + 4], h[l * 8 + 5], h[l * 8 + 6], h[l * 8 + 7]);
     }
     return NBR_OK;
 }

@@ -33,6 +33,31 @@ struct RowsLaunch {
     int pad;
 };
 
+// ---- lean kernel for 7x7x7 windows (rows3.cu): one entry per (lattice, radius), passed in kernel parameters
+constexpr int R3_MAX_ENTRIES = 16;
+struct R3Entry {
+    double minc[3];
+    double edge, inv_edge, r;
+    const uint32_t *dir, *pool;
+    const uint4 *table;          // shell table of r/e (ball_table.cu)
+    int32_t cell_lo[3];
+    int32_t nbx, nby, nbz;
+    float rho2;
+    int32_t col;                 // first output column
+    int32_t reuse;               // same lattice as the previous entry: its window is still staged
+    int32_t pad;
+};
+struct R3Launch {
+    R3Entry e[R3_MAX_ENTRIES];
+    unsigned long long *stats;
+    int32_t n;
+    int32_t tq;                  // bins per axis of the shell tables
+};
+bool rows3_entry(const Lattice *lat, double radius, int col, const R3Entry *prev, R3Entry *E, int *tq_io,
+                 cudaStream_t stream, int *rc);
+int rows3_launch(const R3Launch *L, const void *query, int dtype, const uint32_t *perm, int64_t nq, void *out,
+                 int out_dtype, int64_t row_stride, int descriptor_mask, cudaStream_t stream);
+
 int rows_param(const Lattice *lat, const double *radii, const int *cols, int nr, RowsParam *P, cudaStream_t stream);
 int ball_table_get(double rho2, double margin, int Q, const uint4 **out, cudaStream_t stream);
 bool rows_supported(double edge, const double *radii, int nr);

@@ -1,0 +1,346 @@
+// rows3.cu -- the lean fused feature kernel for 7x7x7 windows (every scale with r/e < 3.5).
+//
+// same job as radius_rows.cu (nimrud/minimal/multiscale.py:94-122 for every scale of a call in one
+// launch: neighbor search, take, population, centroid, pca) but only the common case, so that the code
+// is small enough for the instruction cache and light enough on registers for 20+ warps per SM:
+//   * launch description in kernel parameters (constant bank), one entry per (lattice, radius);
+//   * the warp's brick window is staged by TMA bulk copies (cp.async.bulk, one 128-byte brick per
+//     copy, completion on an mbarrier); warps whose window does not fit read their rows from global
+//     memory through the directory;
+//   * membership comes from the shell tables (ball_table.cu): cells inside for the whole bin of the
+//     query's fractional position are a mask, occupied cells of the uncertain shell are tested in
+//     float32 and, inside the rounding band, with the reference's float64 expression -- neighbor sets
+//     stay bit-exact;
+//   * moments are exact integers (7-bit row table), features come out of finalize.cuh in the same
+//     kernel.
+#include "common.cuh"
+#include "finalize.cuh"
+#include "lattice.cuh"
+#include "radius_rows.cuh"
+
+#include <stdlib.h>
+
+namespace nbr {
+
+constexpr int R3_WARPS = 4;
+constexpr int R3_CAP = 48;          // staged bricks per warp (6 KB)
+constexpr int N7 = 7, W3 = 3;
+
+__device__ __forceinline__ uint32_t row7_entry(uint32_t b)
+{
+    uint32_t cnt = 0, s1 = 0, s2 = 0;
+#pragma unroll
+    for (int i = 0; i < 7; ++i)
+        if (b & (1u << i)) { cnt += 1; s1 += i; s2 += i * i; }
+    return cnt | (s1 << 10) | (s2 << 20);
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+
+__device__ __forceinline__ double r3_centre(const R3Entry &E, long long k, int a)
+{
+    return cell_centre(k + (long long)E.cell_lo[a], E.minc[a], E.edge);
+}
+
+// one cell, the reference's float64 expression ((dx^2 + dy^2) + dz^2 <= r*r, no fma)
+__device__ __noinline__ bool r3_exact_in(const R3Entry &E, double qx, double qy, double qz, int kx, int ky, int kz)
+{
+    double s = sqdiff(qx, r3_centre(E, kx, 0));
+    s = __dadd_rn(s, sqdiff(qy, r3_centre(E, ky, 1)));
+    s = __dadd_rn(s, sqdiff(qz, r3_centre(E, kz, 2)));
+    return s <= __dmul_rn(E.r, E.r);
+}
+
+template <typename OutT, bool EXT>
+__global__ void __launch_bounds__(R3_WARPS * 32, 4)
+rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query, int dtype,
+             const uint32_t *__restrict__ perm, int64_t nq, OutT *__restrict__ out, int64_t row_stride)
+{
+    __shared__ uint32_t s_lut[128];
+    __shared__ __align__(128) uint32_t s_win[R3_WARPS][R3_CAP * BRICK_WORDS];
+    __shared__ __align__(8) unsigned long long s_bar[R3_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) s_lut[i] = row7_entry(i);
+    const uint32_t *win = s_win[warp];
+    const uint32_t win_addr = (uint32_t)__cvta_generic_to_shared(win);
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[warp]);
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t parity = 0;
+    const int64_t n_groups = (nq + 31) >> 5;
+    constexpr uint32_t rowmask = 127u;
+
+    for (int64_t grp = (int64_t)blockIdx.x * R3_WARPS + warp; grp < n_groups; grp += (int64_t)gridDim.x * R3_WARPS) {
+        const int64_t slot_i = grp * 32 + lane;
+        const bool active = slot_i < nq;
+        const int64_t src = active ? slot_i : grp * 32;             // inactive lanes shadow lane 0
+        const int64_t qi = perm ? (int64_t)perm[src] : src;         // row of the output
+        double q[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) q[a] = load_coord(query, dtype, src, 3, a);
+        OutT *dst_row = out + qi * row_stride;
+
+        // state of the current lattice (kept across entries that share it)
+        int c0 = 0, c1 = 0, c2 = 0, tbin = 0;
+        float fxm = 0.f, fym = 0.f, fzm = 0.f;
+        int lo0 = 0, lo1 = 0, lo2 = 0, nb0 = 1, nb1 = 1;
+        bool staged = false;
+
+        for (int li = 0; li < P.n; ++li) {
+            const R3Entry &E = P.e[li];
+            if (!E.reuse) {
+                // ---- anchor cell, fractional position, table bin
+                double f[3];
+                int c[3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const double u = (q[a] - E.minc[a]) * E.inv_edge;
+                    double cf = floor(u);
+                    f[a] = u - cf;
+                    cf = fmin(fmax(cf - (double)E.cell_lo[a], -1.0e9), 1.0e9);
+                    c[a] = (int)cf;
+                }
+                c0 = c[0]; c1 = c[1]; c2 = c[2];
+                fxm = (float)f[0] + 2.5f; fym = (float)f[1] + 2.5f; fzm = (float)f[2] + 2.5f;
+                const int tq = P.tq;
+                tbin = (min((int)(f[2] * tq), tq - 1) * tq + min((int)(f[1] * tq), tq - 1)) * tq +
+                       min((int)(f[0] * tq), tq - 1);
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(E.table + (size_t)tbin * 8));
+
+                // ---- brick window of the whole warp
+                lo0 = (__reduce_min_sync(0xffffffffu, c0) - W3) >> BRICK_XS;
+                lo1 = (__reduce_min_sync(0xffffffffu, c1) - W3) >> BRICK_YS;
+                lo2 = (__reduce_min_sync(0xffffffffu, c2) - W3) >> BRICK_ZS;
+                const long long n0 = (long long)((__reduce_max_sync(0xffffffffu, c0) + W3) >> BRICK_XS) - lo0 + 1;
+                const long long n1 = (long long)((__reduce_max_sync(0xffffffffu, c1) + W3) >> BRICK_YS) - lo1 + 1;
+                const long long n2 = (long long)((__reduce_max_sync(0xffffffffu, c2) + W3) >> BRICK_ZS) - lo2 + 1;
+                staged = n0 <= R3_CAP && n1 <= R3_CAP && n2 <= R3_CAP && n0 * n1 * n2 <= R3_CAP;
+                nb0 = (int)n0; nb1 = (int)n1;
+                if (P.stats && lane == 0) atomicAdd(P.stats + li * 8 + (staged ? 0 : 1), 1ull);
+                if (staged) {
+                    // one TMA bulk copy per brick: brick (ix,iy,iz) -> win[((iz*nb1)+iy)*nb0+ix][32].  empty and
+                    // out-of-range bricks copy slot 0 (all zero)
+                    const int total = nb0 * nb1 * (int)n2;
+                    __syncwarp();                                  // every lane is done reading the previous window
+                    if (lane == 0) mbar_expect_tx(bar, (uint32_t)total * 128u);
+                    __syncwarp();
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        const int b = lane + 32 * t;
+                        if (b < total) {
+                            const int ix = b % nb0, iy = (b / nb0) % nb1, iz = b / (nb0 * nb1);
+                            const int gx = lo0 + ix, gy = lo1 + iy, gz = lo2 + iz;
+                            uint32_t s = 0;
+                            if (gx >= 0 && gx < E.nbx && gy >= 0 && gy < E.nby && gz >= 0 && gz < E.nbz)
+                                s = E.dir[((int64_t)gz * E.nby + gy) * E.nbx + gx];
+                            bulk_g2s(win_addr + (uint32_t)b * 128u, E.pool + (int64_t)s * BRICK_WORDS, 128u, bar);
+                        }
+                    }
+                    mbar_wait(bar, parity);
+                    parity ^= 1u;
+                }
+            } else {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(E.table + (size_t)tbin * 8));
+            }
+
+            // ---- per lane: 7 slabs of 7 rows of 7 bits
+            const uint4 *tab = E.table + (size_t)tbin * 8;
+            const int xa = c0 - W3, ya = c1 - W3, za = c2 - W3;
+            const int sh = xa & 31;
+            const bool two = sh + N7 > 32;
+            const int bx0 = xa >> BRICK_XS, by0 = ya >> BRICK_YS, bz0 = za >> BRICK_ZS;
+            const int ycross = BRICK_Y - (ya & (BRICK_Y - 1));      // rows jy >= ycross live in the next y-brick
+            int ybase = 0, ystep = 0, zstride = 0;
+            uint32_t slot[3][2][2];
+            if (staged) {
+                ybase = ((by0 - lo1) * nb0 + (bx0 - lo0)) * BRICK_WORDS + (ya & (BRICK_Y - 1));
+                ystep = nb0 * BRICK_WORDS - BRICK_Y;
+                zstride = nb1 * nb0 * BRICK_WORDS;
+            } else {
+#pragma unroll
+                for (int iz = 0; iz < 3; ++iz)
+#pragma unroll
+                    for (int iy = 0; iy < 2; ++iy)
+#pragma unroll
+                        for (int ix = 0; ix < 2; ++ix) {
+                            const int gx = bx0 + ix, gy = by0 + iy, gz = bz0 + iz;
+                            const bool ok = (ix == 0 || two) && gx >= 0 && gx < E.nbx && gy >= 0 && gy < E.nby &&
+                                            gz >= 0 && gz < E.nbz;
+                            slot[iz][iy][ix] = ok ? E.dir[((int64_t)gz * E.nby + gy) * E.nbx + gx] : 0u;
+                        }
+            }
+            int An = 0, Asx = 0, Asy = 0, Asz = 0, Asxx = 0, Asxy = 0, Asxz = 0, Asyy = 0, Asyz = 0, Aszz = 0;
+            uint4 tnext = tab[0];
+#pragma unroll 1
+            for (int jz = 0; jz < N7; ++jz) {
+                const uint4 tcur = tnext;
+                tnext = tab[jz + 1];                                   // slab 7 is padding
+                if ((tcur.x | tcur.y | tcur.z | tcur.w) == 0) continue;   // no cell of this slab can be in the ball
+                const int az = za + jz;
+                const int wz = (az & (BRICK_Z - 1)) << BRICK_YS;
+                // ---- gather the slab: bits of row jy at [7*jy, 7*jy+7)
+                unsigned long long slab = 0;
+                if (staged) {
+                    const int zoff = ((az >> BRICK_ZS) - lo2) * zstride + wz + ybase;
+#pragma unroll
+                    for (int jy = 0; jy < N7; ++jy) {
+                        const int off = zoff + jy + (jy >= ycross ? ystep : 0);
+                        const uint32_t w0 = win[off];
+                        const uint32_t w1 = two ? win[off + BRICK_WORDS] : 0u;
+                        slab |= (unsigned long long)(__funnelshift_r(w0, w1, sh) & rowmask) << (N7 * jy);
+                    }
+                } else {
+                    const int iz = (az >> BRICK_ZS) - bz0;                     // 0..2
+                    const uint32_t s00 = iz == 0 ? slot[0][0][0] : (iz == 1 ? slot[1][0][0] : slot[2][0][0]);
+                    const uint32_t s01 = iz == 0 ? slot[0][0][1] : (iz == 1 ? slot[1][0][1] : slot[2][0][1]);
+                    const uint32_t s10 = iz == 0 ? slot[0][1][0] : (iz == 1 ? slot[1][1][0] : slot[2][1][0]);
+                    const uint32_t s11 = iz == 0 ? slot[0][1][1] : (iz == 1 ? slot[1][1][1] : slot[2][1][1]);
+                    if ((s00 | s01 | s10 | s11) == 0) continue;
+#pragma unroll
+                    for (int jy = 0; jy < N7; ++jy) {
+                        const bool up = jy >= ycross;
+                        const uint32_t sa = up ? s10 : s00, sb = up ? s11 : s01;
+                        const int word = wz | ((ya + jy) & (BRICK_Y - 1));
+                        const uint32_t w0 = sa ? E.pool[(int64_t)sa * BRICK_WORDS + word] : 0u;
+                        const uint32_t w1 = sb ? E.pool[(int64_t)sb * BRICK_WORDS + word] : 0u;
+                        slab |= (unsigned long long)(__funnelshift_r(w0, w1, sh) & rowmask) << (N7 * jy);
+                    }
+                }
+                if (slab == 0) continue;
+                // ---- membership: sure cells + occupied cells of the uncertain shell
+                unsigned long long M = slab & ((unsigned long long)tcur.x | ((unsigned long long)tcur.y << 32));
+                const unsigned long long U = slab & ((unsigned long long)tcur.z | ((unsigned long long)tcur.w << 32));
+                if (U) {
+                    const float dzf = fzm - (float)jz;
+                    const float dz2f = dzf * dzf;
+                    uint32_t alo = 0, ahi = 0;
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t u = half ? (uint32_t)(U >> 32) : (uint32_t)U, acc = 0;
+                        while (u) {
+                            const int b = __ffs(u) - 1;
+                            u &= u - 1;
+                            const int i = b + 32 * half;
+                            const int jy = (i * 37) >> 8, t = i - 7 * jy;
+                            const float dx = fxm - (float)t, dy = fym - (float)jy;
+                            const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz2f));
+                            bool in = d2 < E.rho2;
+                            if (fabsf(d2 - E.rho2) < 4.0e-5f) in = r3_exact_in(E, q[0], q[1], q[2], xa + t, ya + jy, az);
+                            acc |= in ? 1u << b : 0u;
+                        }
+                        if (half) ahi = acc; else alo = acc;
+                    }
+                    M |= (unsigned long long)alo | ((unsigned long long)ahi << 32);
+                }
+                if (M == 0) continue;
+                // ---- moments of the slab
+                uint32_t Pk = 0, Qk = 0;
+                int R = 0;
+#pragma unroll
+                for (int jy = 0; jy < N7; ++jy) {
+                    const uint32_t e = s_lut[(uint32_t)(M >> (N7 * jy)) & rowmask];
+                    Pk += e;
+                    Qk += jy * e;
+                    R += jy * jy * (int)(e & 1023u);
+                }
+                const int C = Pk & 1023, SX = (Pk >> 10) & 1023, SXX = Pk >> 20;
+                const int SY = Qk & 1023, SXY = (Qk >> 10) & 1023;
+                An += C; Asx += SX; Asxx += SXX; Asy += SY; Asyy += R; Asxy += SXY;
+                Asz += jz * C; Aszz += jz * jz * C; Asxz += jz * SX; Asyz += jz * SY;
+            }
+            if (active)
+                emit_features_window<OutT>(An, Asx, Asy, Asz, Asxx, Asxy, Asxz, Asyy, Asyz, Aszz, fxm, fym, fzm, true,
+                                           E.edge, dst_row + E.col, EXT ? NBR_DESC_EXTENDED : 0);
+        }
+    }
+}
+
+// fills one entry; false if this (lattice, radius) is not a 7x7x7 window or tables are disabled
+bool rows3_entry(const Lattice *lat, double radius, int col, const R3Entry *prev, R3Entry *E, int *tq_io,
+                 cudaStream_t stream, int *rc)
+{
+    *rc = NBR_OK;
+    static const bool disabled = getenv("NBR_NO_ROWS3") != nullptr || getenv("NBR_NO_BALL_TABLE") != nullptr;
+    if (disabled) return false;
+    const double e = lat->grid.edge;
+    const double rho = radius / e;
+    if (!(rho + 0.5 + 1e-6 < 4.0)) return false;
+    static const int q_env = getenv("NBR_BALL_Q") ? atoi(getenv("NBR_BALL_Q")) : 0;
+    const int tq = q_env >= 1 && q_env <= 64 ? q_env : 16;
+    *tq_io = tq;
+    const LatticeDev d = lat->dev();
+    for (int a = 0; a < 3; ++a) { E->minc[a] = d.g.minc[a]; E->cell_lo[a] = d.g.cell_lo[a]; }
+    E->edge = d.g.edge; E->inv_edge = d.g.inv_edge; E->r = radius;
+    E->dir = d.dir; E->pool = d.pool;
+    E->nbx = d.nbx; E->nby = d.nby; E->nbz = d.nbz;
+    E->rho2 = (float)(rho * rho);
+    E->col = col;
+    E->reuse = prev && prev->pool == d.pool && prev->dir == d.dir;
+    // margin (squared distance, cell units): the reference expression and the kernel's f are each off by a
+    // few ulp of the largest coordinate magnitude, times 2*(W+1) cells
+    double maxabs = 0.0;
+    for (int a = 0; a < 3; ++a)
+        maxabs = std::max(maxabs, std::max(fabs(lat->grid.min_corner[a]), fabs(lat->grid.max_corner[a])));
+    const double margin = std::max(1e-11, 64.0 * 2.3e-16 * (maxabs / e + 8.0));
+    *rc = ball_table_get(rho * rho, margin, tq, &E->table, stream);
+    return *rc == NBR_OK;
+}
+
+int rows3_launch(const R3Launch *L, const void *query, int dtype, const uint32_t *perm, int64_t nq, void *out,
+                 int out_dtype, int64_t row_stride, int descriptor_mask, cudaStream_t stream)
+{
+    if (nq <= 0 || L->n <= 0) return NBR_OK;
+    R3Launch copy = *L;
+    Scratch stats;
+    const bool want_stats = getenv("NBR_ROW_STATS") != nullptr;
+    copy.stats = nullptr;
+    if (want_stats) {
+        NBR_TRY(stats.alloc(sizeof(unsigned long long) * 8 * R3_MAX_ENTRIES, stream));
+        NBR_CUDA(cudaMemsetAsync(stats.ptr, 0, sizeof(unsigned long long) * 8 * R3_MAX_ENTRIES, stream));
+        copy.stats = stats.as<unsigned long long>();
+    }
+    const int blocks = (int)std::min<int64_t>(ceil_div(ceil_div(nq, 32), R3_WARPS), (int64_t)device_sm_count() * 16);
+    const bool ext = (descriptor_mask & NBR_DESC_EXTENDED) != 0;
+#define R3_GO(T, X) rows3_kernel<T, X><<<blocks, R3_WARPS * 32, 0, stream>>>(copy, query, dtype, perm, nq, (T *)out, row_stride)
+    if (out_dtype == NBR_F32) { if (ext) R3_GO(float, true); else R3_GO(float, false); }
+    else                      { if (ext) R3_GO(double, true); else R3_GO(double, false); }
+#undef R3_GO
+    NBR_LAUNCHED();
+    if (want_stats) {
+        unsigned long long h[8 * R3_MAX_ENTRIES];
+        NBR_CUDA(cudaMemcpyAsync(h, stats.ptr, sizeof(h), cudaMemcpyDeviceToHost, stream));
+        NBR_CUDA(cudaStreamSynchronize(stream));
+        for (int l = 0; l < L->n; ++l)
+            fprintf(stderr, "[nbr rows3 stats] entry %d edge %.3g r %.3g: staged warps %llu, direct warps %llu\n", l,
+                    L->e[l].edge, L->e[l].r, h[l * 8], h[l * 8 + 1]);
+    }
+    return NBR_OK;
+}
+
+}  // namespace nbr
