@@ -22,9 +22,23 @@
 
 namespace nbr {
 
-constexpr int R3_WARPS = 4;
-constexpr int R3_CAP = 48;          // staged bricks per warp (6 KB)
+#ifndef R3_WARPS_N
+#define R3_WARPS_N 4
+#endif
+#ifndef R3_CAP_N
+#define R3_CAP_N 48
+#endif
+#ifndef R3_UNROLL_N
+#define R3_UNROLL_N 1
+#endif
+#ifndef R3_BLOCKS_N
+#define R3_BLOCKS_N 4
+#endif
+constexpr int R3_WARPS = R3_WARPS_N;
+constexpr int R3_UNROLL = R3_UNROLL_N;   // slabs per trip of the slab loop
+constexpr int R3_CAP = R3_CAP_N;          // staged bricks per warp (128 bytes each)
 constexpr int N7 = 7, W3 = 3;
+constexpr int R3_TAB_STRIDE = 36;   // words per lane: 128-byte line + 16 bytes of padding (conflict-free LDS.128)
 
 __device__ __forceinline__ uint32_t row7_entry(uint32_t b)
 {
@@ -75,18 +89,21 @@ __device__ __noinline__ bool r3_exact_in(const R3Entry &E, double qx, double qy,
 }
 
 template <typename OutT, bool EXT>
-__global__ void __launch_bounds__(R3_WARPS * 32, 4)
+__global__ void __launch_bounds__(R3_WARPS * 32, R3_BLOCKS_N)
 rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query, int dtype,
              const uint32_t *__restrict__ perm, int64_t nq, OutT *__restrict__ out, int64_t row_stride)
 {
     __shared__ uint32_t s_lut[128];
     __shared__ __align__(128) uint32_t s_win[R3_WARPS][R3_CAP * BRICK_WORDS];
+    __shared__ __align__(16) uint32_t s_tab[R3_WARPS][32 * R3_TAB_STRIDE];      // each lane's table line (7 slabs)
     __shared__ __align__(8) unsigned long long s_bar[R3_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < 128; i += blockDim.x) s_lut[i] = row7_entry(i);
     const uint32_t *win = s_win[warp];
     const uint32_t win_addr = (uint32_t)__cvta_generic_to_shared(win);
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[warp]);
+    const uint4 *tab = reinterpret_cast<const uint4 *>(&s_tab[warp][lane * R3_TAB_STRIDE]);
+    const uint32_t tab_addr = (uint32_t)__cvta_generic_to_shared(tab);
     if (lane == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -131,7 +148,6 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
                 const int tq = P.tq;
                 tbin = (min((int)(f[2] * tq), tq - 1) * tq + min((int)(f[1] * tq), tq - 1)) * tq +
                        min((int)(f[0] * tq), tq - 1);
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(E.table + (size_t)tbin * 8));
 
                 // ---- brick window of the whole warp
                 lo0 = (__reduce_min_sync(0xffffffffu, c0) - W3) >> BRICK_XS;
@@ -143,34 +159,35 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
                 staged = n0 <= R3_CAP && n1 <= R3_CAP && n2 <= R3_CAP && n0 * n1 * n2 <= R3_CAP;
                 nb0 = (int)n0; nb1 = (int)n1;
                 if (P.stats && lane == 0) atomicAdd(P.stats + li * 8 + (staged ? 0 : 1), 1ull);
-                if (staged) {
-                    // one TMA bulk copy per brick: brick (ix,iy,iz) -> win[((iz*nb1)+iy)*nb0+ix][32].  empty and
-                    // out-of-range bricks copy slot 0 (all zero)
-                    const int total = nb0 * nb1 * (int)n2;
-                    __syncwarp();                                  // every lane is done reading the previous window
-                    if (lane == 0) mbar_expect_tx(bar, (uint32_t)total * 128u);
-                    __syncwarp();
+                // TMA bulk copies onto the warp's mbarrier: every lane's 128-byte table line, and (window fits) one
+                // copy per brick: brick (ix,iy,iz) -> win[((iz*nb1)+iy)*nb0+ix][32].  empty and out-of-range bricks
+                // copy slot 0 (all zero)
+                const int total = staged ? nb0 * nb1 * (int)n2 : 0;
+                __syncwarp();                                      // every lane is done reading the previous window / lines
+                if (lane == 0) mbar_expect_tx(bar, (uint32_t)(total + 32) * 128u);
+                __syncwarp();
+                bulk_g2s(tab_addr, E.table + (size_t)tbin * 8, 128u, bar);
 #pragma unroll
-                    for (int t = 0; t < 2; ++t) {
-                        const int b = lane + 32 * t;
-                        if (b < total) {
-                            const int ix = b % nb0, iy = (b / nb0) % nb1, iz = b / (nb0 * nb1);
-                            const int gx = lo0 + ix, gy = lo1 + iy, gz = lo2 + iz;
-                            uint32_t s = 0;
-                            if (gx >= 0 && gx < E.nbx && gy >= 0 && gy < E.nby && gz >= 0 && gz < E.nbz)
-                                s = E.dir[((int64_t)gz * E.nby + gy) * E.nbx + gx];
-                            bulk_g2s(win_addr + (uint32_t)b * 128u, E.pool + (int64_t)s * BRICK_WORDS, 128u, bar);
-                        }
+                for (int t = 0; t < 2; ++t) {
+                    const int b = lane + 32 * t;
+                    if (b < total) {
+                        const int ix = b % nb0, iy = (b / nb0) % nb1, iz = b / (nb0 * nb1);
+                        const int gx = lo0 + ix, gy = lo1 + iy, gz = lo2 + iz;
+                        uint32_t s = 0;
+                        if (gx >= 0 && gx < E.nbx && gy >= 0 && gy < E.nby && gz >= 0 && gz < E.nbz)
+                            s = E.dir[((int64_t)gz * E.nby + gy) * E.nbx + gx];
+                        bulk_g2s(win_addr + (uint32_t)b * 128u, E.pool + (int64_t)s * BRICK_WORDS, 128u, bar);
                     }
-                    mbar_wait(bar, parity);
-                    parity ^= 1u;
                 }
             } else {
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(E.table + (size_t)tbin * 8));
+                // same lattice, another radius: only the table lines change
+                __syncwarp();
+                if (lane == 0) mbar_expect_tx(bar, 32u * 128u);
+                __syncwarp();
+                bulk_g2s(tab_addr, E.table + (size_t)tbin * 8, 128u, bar);
             }
 
             // ---- per lane: 7 slabs of 7 rows of 7 bits
-            const uint4 *tab = E.table + (size_t)tbin * 8;
             const int xa = c0 - W3, ya = c1 - W3, za = c2 - W3;
             const int sh = xa & 31;
             const bool two = sh + N7 > 32;
@@ -195,12 +212,12 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
                             slot[iz][iy][ix] = ok ? E.dir[((int64_t)gz * E.nby + gy) * E.nbx + gx] : 0u;
                         }
             }
+            mbar_wait(bar, parity);
+            parity ^= 1u;
             int An = 0, Asx = 0, Asy = 0, Asz = 0, Asxx = 0, Asxy = 0, Asxz = 0, Asyy = 0, Asyz = 0, Aszz = 0;
-            uint4 tnext = tab[0];
-#pragma unroll 1
+#pragma unroll R3_UNROLL
             for (int jz = 0; jz < N7; ++jz) {
-                const uint4 tcur = tnext;
-                tnext = tab[jz + 1];                                   // slab 7 is padding
+                const uint4 tcur = tab[jz];
                 if ((tcur.x | tcur.y | tcur.z | tcur.w) == 0) continue;   // no cell of this slab can be in the ball
                 const int az = za + jz;
                 const int wz = (az & (BRICK_Z - 1)) << BRICK_YS;
@@ -292,7 +309,7 @@ bool rows3_entry(const Lattice *lat, double radius, int col, const R3Entry *prev
     const double rho = radius / e;
     if (!(rho + 0.5 + 1e-6 < 4.0)) return false;
     static const int q_env = getenv("NBR_BALL_Q") ? atoi(getenv("NBR_BALL_Q")) : 0;
-    const int tq = q_env >= 1 && q_env <= 64 ? q_env : 16;
+    const int tq = q_env >= 1 && q_env <= 64 ? q_env : 32;
     *tq_io = tq;
     const LatticeDev d = lat->dev();
     for (int a = 0; a < 3; ++a) { E->minc[a] = d.g.minc[a]; E->cell_lo[a] = d.g.cell_lo[a]; }
