@@ -86,6 +86,8 @@ int radius_features_exact(const Lattice *lat, const void *query, int dtype, cons
                           int descriptor_mask, cudaStream_t stream);
 int morton_order(const void *xyz, int dtype, int64_t n, const double lohi[6], double cell, uint32_t *perm_out,
                  void *sorted_xyz_out, cudaStream_t stream);
+int cell_order(const void *xyz, int dtype, int64_t n, const double lohi[6], const double origin[3],
+               const double cell_in[3], uint32_t *perm_out, void *sorted_xyz_out, cudaStream_t stream);
 int radius_sets(const Lattice *lat, const void *query, int dtype, int64_t nq, double radius, int64_t *offsets,
                 int32_t *indices, cudaStream_t stream);
 
@@ -161,6 +163,8 @@ static int host_bbox(const void *xyz, int dtype, int64_t n, double *lohi_host, c
     return NBR_OK;
 }
 
+static int brick_origin(const double *lohi, const double *local_box, double finest, double origin[3]);
+
 struct Plan {
     struct Group { double edge; Lattice *lat; std::vector<int> scales; };
     std::vector<Group> groups;
@@ -168,6 +172,7 @@ struct Plan {
     int n_scales = 0, ncol = 4, descriptor_mask = 0;
     double finest = 0.0;
     double local_box[6];
+    double order_origin[3];   // brick corner of the finest lattice: the query order is aligned with it
     ~Plan() { for (auto &g : groups) delete g.lat; }
 };
 
@@ -215,6 +220,7 @@ int plan_create(Plan **out, const void *search, int s_dtype, int64_t ns, const d
             if (rc) break;
         }
     }
+    if (!rc && n_scales > 0) rc = brick_origin(lohi, global_lohi ? P->local_box : nullptr, P->finest, P->order_origin);
     if (rc) { delete P; return rc; }
     *out = P;
     return NBR_OK;
@@ -272,9 +278,22 @@ int plan_run_sorted(const Plan *P, const void *sorted, int q_dtype, const uint32
     return flush();
 }
 
-// Morton order of a cloud (cells of 4 finest voxels) + the cloud in that order
-int order_queries(const void *query, int q_dtype, int64_t nq, const double *qbox_known, double finest, Scratch &perm,
-                  Scratch &sorted, cudaStream_t stream)
+// corner of brick (0,0,0) of the lattice with edge `finest` that plan_create would build for this box
+static int brick_origin(const double *lohi, const double *local_box, double finest, double origin[3])
+{
+    nbr_grid grid;
+    GridDev d;
+    NBR_TRY(grid_from_bbox(lohi, lohi + 3, finest, 3, &grid));
+    NBR_TRY(grid_to_dev(&grid, &d, local_box));
+    for (int a = 0; a < 3; ++a) origin[a] = d.minc[a] + (double)d.cell_lo[a] * finest;
+    return NBR_OK;
+}
+
+// spatially coherent order of a cloud + the cloud in that order.  default: counting sort on cells shaped and
+// aligned like the bricks of the finest lattice (origin = its minimum corner); NBR_ORDER=morton: Z-curve of
+// cells of 4 finest voxels, radix sorted
+int order_queries(const void *query, int q_dtype, int64_t nq, const double *qbox_known, double finest,
+                  const double *origin, Scratch &perm, Scratch &sorted, cudaStream_t stream)
 {
     NBR_TRY(perm.alloc(sizeof(uint32_t) * nq, stream));
     NBR_TRY(sorted.alloc((size_t)nq * 3 * (q_dtype == NBR_F32 ? 4 : 8), stream));
@@ -282,7 +301,11 @@ int order_queries(const void *query, int q_dtype, int64_t nq, const double *qbox
     if (qbox_known) std::copy(qbox_known, qbox_known + 6, qbox);
     else NBR_TRY(host_bbox(query, q_dtype, nq, qbox, stream));
     PhaseTimer t(PHASE_ORDER, stream);
-    return morton_order(query, q_dtype, nq, qbox, 4.0 * finest, perm.as<uint32_t>(), sorted.ptr, stream);
+    static const bool use_morton = getenv("NBR_ORDER") && std::string(getenv("NBR_ORDER")) == "morton";
+    if (use_morton) return morton_order(query, q_dtype, nq, qbox, 4.0 * finest, perm.as<uint32_t>(), sorted.ptr, stream);
+    const double cell[3] = {BRICK_X * finest, BRICK_Y * finest, BRICK_Z * finest};
+    const double org[3] = {origin ? origin[0] : qbox[0], origin ? origin[1] : qbox[1], origin ? origin[2] : qbox[2]};
+    return cell_order(query, q_dtype, nq, qbox, org, cell, perm.as<uint32_t>(), sorted.ptr, stream);
 }
 
 // features of one batch of queries in arbitrary order -> rows [0, nq) of `out`
@@ -293,7 +316,7 @@ int plan_run(const Plan *P, const void *query, int q_dtype, int64_t nq, const do
     if (nq <= 0 || P->n_scales == 0) return NBR_OK;
     if (!query || !out) return fail(NBR_ERR_INVALID, "multiscale_features: null argument");
     Scratch perm, sorted;
-    NBR_TRY(order_queries(query, q_dtype, nq, qbox_known, P->finest, perm, sorted, stream));
+    NBR_TRY(order_queries(query, q_dtype, nq, qbox_known, P->finest, P->order_origin, perm, sorted, stream));
     return plan_run_sorted(P, sorted.ptr, q_dtype, perm.as<uint32_t>(), nq, out, out_dtype, stream);
 }
 
@@ -329,7 +352,9 @@ int multiscale_features(const void *query, int q_dtype, int64_t nq, const void *
         }
         NBR_TRY(host_bbox(search, s_dtype, ns, box, stream));
         Scratch perm, sorted;
-        NBR_TRY(order_queries(query, q_dtype, nq, box, finest, perm, sorted, stream));
+        double origin[3];
+        NBR_TRY(brick_origin(global_lohi ? global_lohi : box, global_lohi ? box : nullptr, finest, origin));
+        NBR_TRY(order_queries(query, q_dtype, nq, box, finest, origin, perm, sorted, stream));
         NBR_TRY(plan_create(&P, sorted.ptr, s_dtype, ns, edges, radii, n_scales, descriptor_mask, global_lohi, box, stream));
         rc = plan_run_sorted(P, sorted.ptr, q_dtype, perm.as<uint32_t>(), nq, out, out_dtype, stream);
         if (rc == NBR_OK && n_voxels_host) rc = plan_voxel_counts(P, n_voxels_host);

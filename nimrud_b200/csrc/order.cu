@@ -3,6 +3,7 @@
 // of the order are close in space at every scale, which is what lets one warp of the feature kernel
 // share a staged occupancy window.  results never depend on the order (each query is independent).
 #include "common.cuh"
+#include "scan.cuh"
 
 namespace nbr {
 
@@ -111,6 +112,119 @@ int morton_order(const void *xyz, int dtype, int64_t n, const double lohi[6], do
     NBR_TRY(sort_pairs(keys.as<uint64_t>(), keys_tmp.as<uint64_t>(), perm_out, vals_tmp.as<uint32_t>(), n, 0, total, stream));
     if (sorted_xyz_out) {
         gather_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(xyz, dtype, n, perm_out, sorted_xyz_out);
+        NBR_LAUNCHED();
+    }
+    return NBR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cell order: counting sort of the cloud on a dense grid of brick-shaped cells (32 x 8 x 4 finest voxels,
+// aligned with the bricks of the finest lattice).  every point of a cell needs the same <= 3 x 3 x 3 bricks
+// of that lattice (fewer on coarser ones), so a warp of 32 consecutive points always finds its window in
+// the staging buffer of the feature kernels.  two passes over the points (count + place) and one scan of
+// the cell counters instead of a 4-pass radix sort.  the order inside a cell is whatever the atomics
+// produce; results do not depend on it (every query is independent).
+// ------------------------------------------------------------------------------------------------
+struct CellGrid {
+    double origin[3];
+    double inv_cell[3];
+    int first[3];
+    int dims[3];
+    int bits[3];
+    int common;                   // Z-curve levels present on all three axes
+    unsigned char pos[3][21];     // position of bit l of axis a in the cell id (upper levels)
+};
+
+// cells are numbered along a Z-curve (axes with fewer cells drop out of the upper levels), so that cells
+// that follow each other in the order are neighbors in space even where most cells are empty
+__device__ __forceinline__ uint32_t cell_of(const void *xyz, int dtype, int64_t i, const CellGrid &G)
+{
+    uint32_t c[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const double u = (load_coord(xyz, dtype, i, 3, a) - G.origin[a]) * G.inv_cell[a];
+        c[a] = (uint32_t)clampi((int)floor(u) - G.first[a], 0, G.dims[a] - 1);
+    }
+    const uint32_t low = (1u << G.common) - 1u;
+    uint64_t key = spread3(c[0] & low) | (spread3(c[1] & low) << 1) | (spread3(c[2] & low) << 2);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        for (int l = G.common; l < G.bits[a]; ++l) key |= (uint64_t)((c[a] >> l) & 1u) << G.pos[a][l];
+    return (uint32_t)key;
+}
+
+__global__ void __launch_bounds__(256)
+cell_count_kernel(const void *__restrict__ xyz, int dtype, int64_t n, CellGrid G, uint32_t *__restrict__ counts,
+                  uint32_t *__restrict__ cell, uint32_t *__restrict__ rank)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t c = cell_of(xyz, dtype, i, G);
+    cell[i] = c;
+    rank[i] = atomicAdd(&counts[c], 1u);
+}
+
+__global__ void __launch_bounds__(256)
+cell_place_kernel(int64_t n, const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ cell,
+                  const uint32_t *__restrict__ rank, uint32_t *__restrict__ perm)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    perm[offsets[cell[i]] + rank[i]] = (uint32_t)i;
+}
+
+// lohi: bounding box of the cloud (host).  origin / cell: corner and edge lengths of the cell grid to align
+// with (cells are doubled until the dense counter array fits 2^26 entries).
+int cell_order(const void *xyz, int dtype, int64_t n, const double lohi[6], const double origin[3],
+               const double cell_in[3], uint32_t *perm_out, void *sorted_xyz_out, cudaStream_t stream)
+{
+    if (n <= 0) return NBR_OK;
+    if (n >= (int64_t)1 << 32) return fail(NBR_ERR_UNSUPPORTED, "cell_order: more than 2^32 points");
+    CellGrid G;
+    double cell[3] = {cell_in[0], cell_in[1], cell_in[2]};
+    int total_bits = -1;
+    for (int attempt = 0; attempt < 64; ++attempt) {
+        int bits = 0;
+        bool ok = true;
+        for (int a = 0; a < 3; ++a) {
+            G.origin[a] = origin[a];
+            G.inv_cell[a] = 1.0 / cell[a];
+            const double f = floor((lohi[a] - origin[a]) / cell[a]), l = floor((lohi[3 + a] - origin[a]) / cell[a]);
+            if (!(fabs(f) < 2.0e9 && fabs(l) < 2.0e9 && l - f + 1.0 <= 1048576.0)) { ok = false; break; }
+            G.first[a] = (int)f;
+            G.dims[a] = (int)(l - f + 1.0);
+            int b = 0;
+            while ((1 << b) < G.dims[a]) ++b;
+            G.bits[a] = b;
+            bits += b;
+        }
+        if (ok && bits <= 26) { total_bits = bits; break; }
+        for (int a = 0; a < 3; ++a) cell[a] *= 2.0;
+    }
+    if (total_bits < 0) return fail(NBR_ERR_UNSUPPORTED, "cell_order: cannot cover the cloud with a cell grid");
+    G.common = std::min(G.bits[0], std::min(G.bits[1], G.bits[2]));
+    {
+        int pos = 3 * G.common;
+        for (int l = G.common; l < 21; ++l)
+            for (int a = 0; a < 3; ++a)
+                if (l < G.bits[a]) G.pos[a][l] = (unsigned char)pos++;
+    }
+    const int64_t nc = (int64_t)1 << total_bits;
+    Scratch counts, cellid, rank;
+    NBR_TRY(counts.alloc(sizeof(uint32_t) * nc, stream));
+    NBR_TRY(cellid.alloc(sizeof(uint32_t) * n, stream));
+    NBR_TRY(rank.alloc(sizeof(uint32_t) * n, stream));
+    NBR_CUDA(cudaMemsetAsync(counts.ptr, 0, sizeof(uint32_t) * nc, stream));
+    const unsigned blocks = (unsigned)ceil_div(n, 256);
+    cell_count_kernel<<<blocks, 256, 0, stream>>>(xyz, dtype, n, G, counts.as<uint32_t>(), cellid.as<uint32_t>(),
+                                                  rank.as<uint32_t>());
+    NBR_LAUNCHED();
+    NBR_TRY((exclusive_scan<uint32_t, uint32_t>(counts.as<uint32_t>(), counts.as<uint32_t>(), nc, stream)));
+    cell_place_kernel<<<blocks, 256, 0, stream>>>(n, counts.as<uint32_t>(), cellid.as<uint32_t>(), rank.as<uint32_t>(),
+                                                  perm_out);
+    NBR_LAUNCHED();
+    if (sorted_xyz_out) {
+        gather_kernel<<<blocks, 256, 0, stream>>>(xyz, dtype, n, perm_out, sorted_xyz_out);
         NBR_LAUNCHED();
     }
     return NBR_OK;
