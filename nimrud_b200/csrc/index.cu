@@ -236,33 +236,58 @@ int unique_sorted(const uint64_t *sorted, int64_t n, uint64_t *out, int64_t *n_o
 // ------------------------------------------------------------------------------------------------
 // lattice (bit bricks)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void point_cell(const void *xyz, int dtype, int64_t i, const GridDev &g, int c[3])
+// rare path of point_cell: u = (p - minc) * (1/e) sits next to an integer, only the division tells the cell
+static __device__ __noinline__ int cell_by_division(double d, double edge)
+{
+    return (int)fmin(fmax(floor(__ddiv_rn(d, edge)), -2.0e9), 2.0e9);
+}
+
+// LOCAL cell of point i on every axis: floor((p - min_corner) / e) - cell_lo  (utils/geometry.py:107),
+// bit-identical to cell_coord_f but with one multiply, one float64 -> int conversion and a short test in
+// the common case (the quotient is only formed when the product is within a few ulp of an integer)
+template <typename T>
+__device__ __forceinline__ void point_cell(const T *__restrict__ xyz, int64_t i, const GridDev &g, int c[3])
 {
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        int v = 0;
-        if (a < g.ndim) {
-            double p = load_coord(xyz, dtype, i, g.ndim, a);
-            double k = cell_coord_fast(p, g.minc[a], g.edge, g.inv_edge) - (double)g.cell_lo[a];
-            // search points lie inside the covered range by construction; the clamp defends against a
-            // caller-supplied box that does not contain them.
-            k = fmin(fmax(k, 0.0), (double)(g.ncell[a] - 1));
-            v = (int)k;
-        }
-        c[a] = v;
+        const double d = __dsub_rn((double)xyz[i * 3 + a], g.minc[a]);
+        const double u = d * g.inv_edge;
+        int k = __double2int_rd(u);
+        const double fr = u - (double)k;                  // in [0, 1] when u is in int range
+        const double tol = 4.0e-15 * fabs(u) + 1e-300;
+        if (!(fr > tol && fr < 1.0 - tol)) k = cell_by_division(d, g.edge);
+        // search points lie inside the covered range by construction; the clamp defends against a
+        // caller-supplied box that does not contain them.
+        c[a] = clampi(k - g.cell_lo[a], 0, g.ncell[a] - 1);
     }
 }
 
+// mark / fill handle PTS points per thread with the loads of all of them in flight together: the kernels are
+// bound by the latency of the dependent directory / pool accesses, not by bandwidth
+constexpr int PTS = 4;
+
+template <typename T>
 __global__ void __launch_bounds__(256)
-brick_mark_kernel(const void *__restrict__ xyz, int dtype, int64_t n, GridDev g, int nbx, int nby,
-                  uint32_t *__restrict__ dir)
+brick_mark_kernel(const T *__restrict__ xyz, int64_t n, GridDev g, int nbx, int nby, uint32_t *__restrict__ dir)
 {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int c[3];
-    point_cell(xyz, dtype, i, g, c);
-    const int64_t b = ((int64_t)(c[2] >> BRICK_ZS) * nby + (c[1] >> BRICK_YS)) * nbx + (c[0] >> BRICK_XS);
-    if (dir[b] == 0) dir[b] = 1;   // benign race: every writer stores 1
+    const int64_t base = ((int64_t)blockIdx.x * PTS) * blockDim.x + threadIdx.x;
+    int64_t b[PTS];
+#pragma unroll
+    for (int k = 0; k < PTS; ++k) {
+        const int64_t i = base + (int64_t)k * blockDim.x;
+        b[k] = -1;
+        if (i < n) {
+            int c[3];
+            point_cell<T>(xyz, i, g, c);
+            b[k] = ((int64_t)(c[2] >> BRICK_ZS) * nby + (c[1] >> BRICK_YS)) * nbx + (c[0] >> BRICK_XS);
+        }
+    }
+    uint32_t seen[PTS];
+#pragma unroll
+    for (int k = 0; k < PTS; ++k) seen[k] = b[k] >= 0 ? dir[b[k]] : 1u;
+#pragma unroll
+    for (int k = 0; k < PTS; ++k)
+        if (seen[k] == 0) dir[b[k]] = 1;   // benign race: every writer stores 1
 }
 
 __global__ void __launch_bounds__(256)
@@ -273,20 +298,38 @@ pool_zero_kernel(uint32_t *__restrict__ pool, const uint32_t *__restrict__ n_bri
         pool[i] = 0;
 }
 
+template <typename T>
 __global__ void __launch_bounds__(256)
-brick_fill_kernel(const void *__restrict__ xyz, int dtype, int64_t n, GridDev g, int nbx, int nby,
-                  const uint32_t *__restrict__ dir, uint32_t *__restrict__ pool)
+brick_fill_kernel(const T *__restrict__ xyz, int64_t n, GridDev g, int nbx, int nby, const uint32_t *__restrict__ dir,
+                  uint32_t *__restrict__ pool)
 {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int c[3];
-    point_cell(xyz, dtype, i, g, c);
-    const int64_t b = ((int64_t)(c[2] >> BRICK_ZS) * nby + (c[1] >> BRICK_YS)) * nbx + (c[0] >> BRICK_XS);
-    const uint32_t slot = dir[b];
-    const int word = ((c[2] & (BRICK_Z - 1)) << BRICK_YS) | (c[1] & (BRICK_Y - 1));
-    const uint32_t bit = 1u << (c[0] & 31);
-    uint32_t *w = pool + (int64_t)slot * BRICK_WORDS + word;
-    if ((*w & bit) == 0) atomicOr(w, bit);
+    const int64_t base = ((int64_t)blockIdx.x * PTS) * blockDim.x + threadIdx.x;
+    int64_t b[PTS];
+    int word[PTS];
+    uint32_t bit[PTS];
+#pragma unroll
+    for (int k = 0; k < PTS; ++k) {
+        const int64_t i = base + (int64_t)k * blockDim.x;
+        b[k] = -1;
+        word[k] = 0;
+        bit[k] = 0;
+        if (i < n) {
+            int c[3];
+            point_cell<T>(xyz, i, g, c);
+            b[k] = ((int64_t)(c[2] >> BRICK_ZS) * nby + (c[1] >> BRICK_YS)) * nbx + (c[0] >> BRICK_XS);
+            word[k] = ((c[2] & (BRICK_Z - 1)) << BRICK_YS) | (c[1] & (BRICK_Y - 1));
+            bit[k] = 1u << (c[0] & 31);
+        }
+    }
+    uint32_t *w[PTS];
+#pragma unroll
+    for (int k = 0; k < PTS; ++k) w[k] = pool + (int64_t)(b[k] >= 0 ? dir[b[k]] : 0u) * BRICK_WORDS + word[k];
+    uint32_t have[PTS];
+#pragma unroll
+    for (int k = 0; k < PTS; ++k) have[k] = bit[k] ? *w[k] : ~0u;
+#pragma unroll
+    for (int k = 0; k < PTS; ++k)
+        if ((have[k] & bit[k]) == 0 && bit[k]) atomicOr(w[k], bit[k]);
 }
 
 // number of occupied voxels = popcount of the pool
@@ -352,6 +395,7 @@ int lattice_create(Lattice **out, const void *xyz, int dtype, int64_t n, const n
     if (dtype != NBR_F32 && dtype != NBR_F64) return fail(NBR_ERR_INVALID, "lattice_create: bad dtype");
     if (n < 1) return fail(NBR_ERR_TOO_FEW_POINTS, "lattice_create: empty search cloud");
     if (n >= (int64_t)1 << 31) return fail(NBR_ERR_UNSUPPORTED, "lattice_create: more than 2^31 search points");
+    if (grid->ndim != 3) return fail(NBR_ERR_INVALID, "lattice_create: 3-D grids only");
     Lattice *L = new Lattice();
     L->stream = stream;
     L->grid = *grid;
@@ -385,13 +429,20 @@ int lattice_create(Lattice **out, const void *xyz, int dtype, int64_t n, const n
     int64_t *n_unique_dev = reinterpret_cast<int64_t *>(L->counters + 16);
 
     const unsigned blocks = (unsigned)ceil_div(n, 256);
+    const unsigned pt_blocks = (unsigned)ceil_div(n, 256 * PTS);
     const int sweep_blocks = device_sm_count() * 8;
-    brick_mark_kernel<<<blocks, 256, 0, stream>>>(xyz, dtype, n, L->gdev, L->nbx, L->nby, L->dir);
+    if (dtype == NBR_F32)
+        brick_mark_kernel<float><<<pt_blocks, 256, 0, stream>>>((const float *)xyz, n, L->gdev, L->nbx, L->nby, L->dir);
+    else
+        brick_mark_kernel<double><<<pt_blocks, 256, 0, stream>>>((const double *)xyz, n, L->gdev, L->nbx, L->nby, L->dir);
     L_LAUNCHED();
     L_TRY(flags_to_slots(L->dir, L->n_dir, n_bricks_dev, stream));
     pool_zero_kernel<<<sweep_blocks, 256, 0, stream>>>(L->pool, n_bricks_dev);
     L_LAUNCHED();
-    brick_fill_kernel<<<blocks, 256, 0, stream>>>(xyz, dtype, n, L->gdev, L->nbx, L->nby, L->dir, L->pool);
+    if (dtype == NBR_F32)
+        brick_fill_kernel<float><<<pt_blocks, 256, 0, stream>>>((const float *)xyz, n, L->gdev, L->nbx, L->nby, L->dir, L->pool);
+    else
+        brick_fill_kernel<double><<<pt_blocks, 256, 0, stream>>>((const double *)xyz, n, L->gdev, L->nbx, L->nby, L->dir, L->pool);
     L_LAUNCHED();
     pool_count_kernel<<<sweep_blocks, 256, 0, stream>>>(L->pool, n_bricks_dev, n_vox_dev);
     L_LAUNCHED();
