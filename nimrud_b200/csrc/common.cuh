@@ -94,6 +94,7 @@ struct LatticeDev {
     const uint32_t *dir;          // [nbz][nby][nbx] -> slot; 0 = empty (slot 0 is an all-zero brick)
     const uint32_t *pool;         // [slots][32] occupancy words; word = (z&3)*8 + (y&7), bit = x&31
     const uint32_t *rowbase;      // [slots][32] index (np.unique order) of the first voxel of the row; or NULL
+    const uint64_t *ukeys;        // sorted unique packed addresses (np.unique order); or NULL
 };
 
 #ifdef __CUDACC__

@@ -384,7 +384,7 @@ LatticeDev Lattice::dev() const
     LatticeDev d;
     d.g = gdev;
     d.nbx = nbx; d.nby = nby; d.nbz = nbz;
-    d.dir = dir; d.pool = pool; d.rowbase = rowbase;
+    d.dir = dir; d.pool = pool; d.rowbase = rowbase; d.ukeys = ukeys;
     return d;
 }
 

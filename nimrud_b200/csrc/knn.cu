@@ -1,11 +1,18 @@
 // knn.cu -- k nearest voxels per query on the bit-brick lattice; total order (d^2 as float64, index).
 // No reference counterpart (extension, SURVEY 8c / BASELINE config 3).
 //
-// one warp per query.  the warp sweeps a cubic window of cells around the query's anchor cell: each
-// 32-cell occupancy word maps bit b -> lane b, every lane evaluates its own cell with the exact
-// float64 distance, candidates that beat the current k-th are merged into a sorted list kept in
-// shared memory.  the window doubles (and the sweep restarts) until the k-th distance is provably
-// smaller than the distance to any cell outside the window.
+// one warp per query, three steps:
+//   1. candidate ball.  the warp sweeps the bricks under a cubic window of half-width W cells around the
+//      query's anchor cell: lane b resolves brick b through the directory, every non-empty brick is then
+//      read as one coalesced 128-byte line (lane = row of the brick).  cells outside the window are at
+//      least (W + 0.5) e away, so once >= k cells lie inside a ball of that radius the k nearest are
+//      among them.  the ball test runs in float32 with a relative guard band; W grows until the ball is
+//      populated, and the ball shrinks (bisection on r^2) if it holds more candidates than the buffer.
+//   2. every candidate gets the reference's float64 squared distance ((dx^2 + dy^2) + dz^2, no fma) and
+//      its index in np.unique order (row base + popcount); records go to shared memory.
+//   3. the warp sorts the records with a bitonic network on (d^2, index) -- a strict total order, ties
+//      included -- writes the first k, and accumulates the integer moments of every k in ks for the
+//      feature columns (finalize.cuh), one lane per k.
 #include "common.cuh"
 #include "finalize.cuh"
 #include "lattice.cuh"
@@ -14,12 +21,12 @@ namespace nbr {
 
 constexpr int KNN_WARPS = 4;
 constexpr int KNN_MAX_K = 128;
-constexpr int KNN_PER_LANE = KNN_MAX_K / 32;
+constexpr int KNN_CAP = 512;            // candidate records per warp (8 KB)
 
-struct KnnEntry {
+struct __align__(16) KnnRec {
     double d2;
     int32_t idx;
-    int32_t kx, ky, kz;
+    int32_t pad;
 };
 
 struct KsParam {
@@ -27,36 +34,9 @@ struct KsParam {
     int32_t n;
 };
 
-__device__ __forceinline__ bool entry_less(double d2a, int ia, double d2b, int ib)
+__device__ __forceinline__ bool rec_less(const KnnRec &a, const KnnRec &b)
 {
-    return d2a < d2b || (d2a == d2b && ia < ib);
-}
-
-// insert e into list[0..have) (sorted ascending), keeping at most k entries.  whole warp calls.
-__device__ __forceinline__ int warp_insert(KnnEntry *list, int have, int k, const KnnEntry &e, int lane)
-{
-    // position = number of entries that sort before e
-    KnnEntry mine[KNN_PER_LANE];
-    int pos = 0;
-#pragma unroll
-    for (int t = 0; t < KNN_PER_LANE; ++t) {
-        const int p = lane + 32 * t;
-        bool before = false;
-        if (p < have) {
-            mine[t] = list[p];
-            before = entry_less(mine[t].d2, mine[t].idx, e.d2, e.idx);
-        }
-        pos += __popc(__ballot_sync(0xffffffffu, before));
-    }
-    __syncwarp();
-#pragma unroll
-    for (int t = 0; t < KNN_PER_LANE; ++t) {
-        const int p = lane + 32 * t;
-        if (p < have && p >= pos && p + 1 < k) list[p + 1] = mine[t];
-    }
-    if (lane == 0 && pos < k) list[pos] = e;
-    __syncwarp();
-    return have < k ? have + 1 : k;
+    return a.d2 < b.d2 || (a.d2 == b.d2 && a.idx < b.idx);
 }
 
 template <typename OutT>
@@ -65,9 +45,9 @@ knn_kernel(LatticeDev L, const void *__restrict__ query, int dtype, int64_t nq, 
            double *__restrict__ d2_out, KsParam ks, OutT *__restrict__ feats, int64_t row_stride, int col_offset,
            int descriptor_mask)
 {
-    extern __shared__ unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    KnnEntry *list = reinterpret_cast<KnnEntry *>(smem_raw) + (size_t)warp * k;
+    KnnRec *rec = reinterpret_cast<KnnRec *>(smem_raw) + (size_t)warp * KNN_CAP;
     const GridDev &g = L.g;
     const int ncol = (descriptor_mask & NBR_DESC_EXTENDED) ? NBR_COLS_EXTENDED : NBR_COLS_REFERENCE;
 
@@ -79,93 +59,183 @@ knn_kernel(LatticeDev L, const void *__restrict__ query, int dtype, int64_t nq, 
             q[a] = load_coord(query, dtype, qi, 3, a);
             query_anchor(q[a], g, a, c[a], f[a]);
         }
-        int have = 0;
-        long long rho = 2;
-        for (;;) {
-            have = 0;
-            int lo[3], hi[3];
+        // query position relative to the anchor cell's centre, cell units (float32 guide only)
+        const float px = (float)f[0] - 0.5f, py = (float)f[1] - 0.5f, pz = (float)f[2] - 0.5f;
+
+        // ---- 1. candidate ball
+        long long W = 1;
+        while ((2 * W + 1) * (2 * W + 1) < k) ++W;               // a populated plane holds k cells at about this width
+        if (W > 2) W = (W * 3) / 4;
+        float lo2 = 0.0f, hi2 = INFINITY, r2 = 0.0f;
+        bool ball_of_w = true;                                    // r2 is the full ball of the current window
+        int n_cand = 0;
+        for (int attempt = 0; attempt < 200; ++attempt) {
+            int wlo[3], whi[3];
             bool covers_all = true, empty = false;
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
-                long long l = (long long)c[a] - rho, h = (long long)c[a] + rho;
+                const long long l = (long long)c[a] - W, h = (long long)c[a] + W;
                 covers_all &= (l <= 0) & (h >= g.ncell[a] - 1);
-                lo[a] = (int)(l < 0 ? 0 : l);
-                hi[a] = (int)(h > g.ncell[a] - 1 ? g.ncell[a] - 1 : h);
-                empty |= lo[a] > hi[a];
+                wlo[a] = (int)(l < 0 ? 0 : l);
+                whi[a] = (int)(h > g.ncell[a] - 1 ? g.ncell[a] - 1 : h);
+                empty |= wlo[a] > whi[a];
             }
-            double worst_d2 = INFINITY;
-            int worst_idx = 0x7fffffff;
+            if (ball_of_w) {
+                const float wf = (float)W + 0.5f;
+                r2 = covers_all ? INFINITY : wf * wf * (1.0f - 1.0e-4f);
+            }
+            const float r2_sure = r2 * (1.0f - 4.0e-5f);
+            int n_sure = 0;
+            n_cand = 0;
             if (!empty) {
-                for (int kz = lo[2]; kz <= hi[2]; ++kz) {
-                    const double dz2 = sqdiff(q[2], grid_centre(g, kz, 2));
-                    for (int ky = lo[1]; ky <= hi[1]; ++ky) {
-                        const double dy2 = sqdiff(q[1], grid_centre(g, ky, 1));
-                        const int word = ((kz & (BRICK_Z - 1)) << BRICK_YS) | (ky & (BRICK_Y - 1));
-                        const int64_t rowb = ((int64_t)(kz >> BRICK_ZS) * L.nby + (ky >> BRICK_YS)) * L.nbx;
-                        for (int bx = lo[0] >> BRICK_XS; bx <= hi[0] >> BRICK_XS; ++bx) {
-                            const uint32_t slot = L.dir[rowb + bx];
-                            if (!slot) continue;
-                            const int64_t wi = (int64_t)slot * BRICK_WORDS + word;
-                            const uint32_t full = L.pool[wi];
-                            uint32_t w = full;
-                            const int x0 = bx << BRICK_XS;
-                            if (lo[0] > x0) w &= ~0u << (lo[0] - x0);
-                            if (hi[0] < x0 + 31) w &= ~0u >> (x0 + 31 - hi[0]);
-                            if (!w) continue;
-                            // bit b -> lane b
-                            KnnEntry e;
-                            bool cand = (w >> lane) & 1u;
-                            e.kx = x0 + lane; e.ky = ky; e.kz = kz;
-                            e.d2 = INFINITY; e.idx = 0;
-                            if (cand) {
-                                double s = sqdiff(q[0], grid_centre(g, e.kx, 0));
-                                s = __dadd_rn(s, dy2);
-                                s = __dadd_rn(s, dz2);
-                                e.d2 = s;
-                                e.idx = (int32_t)(L.rowbase[wi] + __popc(full & ((1u << lane) - 1u)));
-                                cand = have < k || entry_less(s, e.idx, worst_d2, worst_idx);
-                            }
-                            uint32_t todo = __ballot_sync(0xffffffffu, cand);
-                            while (todo) {
-                                const int src = __ffs(todo) - 1;
-                                todo &= todo - 1;
-                                KnnEntry b;
-                                b.d2 = __shfl_sync(0xffffffffu, e.d2, src);
-                                b.idx = __shfl_sync(0xffffffffu, e.idx, src);
-                                b.kx = x0 + src; b.ky = ky; b.kz = kz;
-                                if (have == k && !entry_less(b.d2, b.idx, worst_d2, worst_idx)) continue;
-                                have = warp_insert(list, have, k, b, lane);
-                                if (have == k) {
-                                    worst_d2 = list[k - 1].d2;
-                                    worst_idx = list[k - 1].idx;
-                                }
+                const int bx0 = wlo[0] >> BRICK_XS, by0 = wlo[1] >> BRICK_YS, bz0 = wlo[2] >> BRICK_ZS;
+                const int nbx = (whi[0] >> BRICK_XS) - bx0 + 1, nby = (whi[1] >> BRICK_YS) - by0 + 1;
+                const int nbz = (whi[2] >> BRICK_ZS) - bz0 + 1;
+                const long long nbricks = (long long)nbx * nby * nbz;
+                for (long long base = 0; base < nbricks; base += 32) {
+                    const long long b = base + lane;
+                    uint32_t slot = 0;
+                    int gx = 0, gy = 0, gz = 0;
+                    if (b < nbricks) {
+                        gx = bx0 + (int)(b % nbx);
+                        gy = by0 + (int)((b / nbx) % nby);
+                        gz = bz0 + (int)(b / ((long long)nbx * nby));
+                        slot = L.dir[((int64_t)gz * L.nby + gy) * L.nbx + gx];
+                    }
+                    uint32_t todo = __ballot_sync(0xffffffffu, slot != 0);
+                    while (todo) {
+                        const int src = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const uint32_t s = __shfl_sync(0xffffffffu, slot, src);
+                        const int x0 = __shfl_sync(0xffffffffu, gx, src) << BRICK_XS;
+                        const int ky = (__shfl_sync(0xffffffffu, gy, src) << BRICK_YS) | (lane & (BRICK_Y - 1));
+                        const int kz = (__shfl_sync(0xffffffffu, gz, src) << BRICK_ZS) | (lane >> BRICK_YS);
+                        const int64_t wi = (int64_t)s * BRICK_WORDS + lane;
+                        const uint32_t full = L.pool[wi];               // one 128-byte line per brick
+                        uint32_t w = full;
+                        if (wlo[0] > x0) w &= ~0u << (wlo[0] - x0);
+                        if (whi[0] < x0 + 31) w &= ~0u >> (x0 + 31 - whi[0]);
+                        if (ky < wlo[1] || ky > whi[1] || kz < wlo[2] || kz > whi[2]) w = 0;
+                        // float32 ball test of the row's cells
+                        const float dy = (float)(ky - c[1]) - py, dz = (float)(kz - c[2]) - pz;
+                        const float row2 = dy * dy + dz * dz;
+                        uint32_t cand = 0;
+                        int sure = 0;
+                        for (uint32_t u = w; u; u &= u - 1) {
+                            const int bit = __ffs(u) - 1;
+                            const float dx = (float)(x0 + bit - c[0]) - px;
+                            const float d2 = fmaf(dx, dx, row2);
+                            if (d2 <= r2) cand |= 1u << bit;
+                            sure += d2 <= r2_sure;
+                        }
+                        n_sure += sure;
+                        // records: position by a warp prefix sum of the per-row counts
+                        const int mine = __popc(cand);
+                        const int total = __reduce_add_sync(0xffffffffu, mine);
+                        if (total == 0) continue;
+                        int pre = mine;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int t = __shfl_up_sync(0xffffffffu, pre, o);
+                            if (lane >= o) pre += t;
+                        }
+                        int pos = n_cand + pre - mine;
+                        n_cand += total;
+                        if (cand && n_cand <= KNN_CAP) {
+                            const double dy2 = sqdiff(q[1], grid_centre(g, ky, 1));
+                            const double dz2 = sqdiff(q[2], grid_centre(g, kz, 2));
+                            const uint32_t rb = L.rowbase[wi];
+                            for (uint32_t u = cand; u; u &= u - 1) {
+                                const int bit = __ffs(u) - 1;
+                                double s2 = sqdiff(q[0], grid_centre(g, x0 + bit, 0));
+                                s2 = __dadd_rn(s2, dy2);
+                                s2 = __dadd_rn(s2, dz2);
+                                KnnRec r;
+                                r.d2 = s2;
+                                r.idx = (int32_t)(rb + __popc(full & ((1u << bit) - 1u)));
+                                r.pad = 0;
+                                rec[pos] = r;
+                                ++pos;
                             }
                         }
                     }
                 }
             }
-            if (covers_all) break;
-            if (have == k) {
-                const double bound = ((double)rho + 0.5) * g.edge * (1.0 - 1e-9);
-                if (worst_d2 < bound * bound) break;
+            n_sure = __reduce_add_sync(0xffffffffu, n_sure);
+            // ---- decide: enough sure cells, and the candidates fit?
+            // invariants: fewer than k sure cells at lo2; more than KNN_CAP candidates at hi2
+            if (n_sure >= k && n_cand <= KNN_CAP) break;
+            if (n_sure >= k) {
+                hi2 = r2;                                   // too many: shrink the ball inside the same window
+                ball_of_w = false;
+            } else if (!ball_of_w) {
+                lo2 = r2;                                   // the shrunken ball lost the k-th neighbor
+            } else if (covers_all) {
+                break;                                      // the whole lattice holds fewer than k voxels
+            } else {
+                lo2 = r2;                                   // the ball of this window is not populated: widen it
+                W = W < 4 ? W + 1 : (W * 3) / 2;
+                if (W > (1ll << 31)) break;
+                continue;
             }
-            rho *= 2;
-            if (rho > (1ll << 31)) break;
+            const float mid = hi2 < INFINITY ? 0.5f * (lo2 + hi2) : fmaxf(4.0f * lo2, 1.0f);
+            if (!(mid > lo2 && mid < hi2)) break;           // unreachable: > KNN_CAP - k cells within one ulp of distance
+            r2 = mid;
+        }
+        if (n_cand > KNN_CAP) n_cand = KNN_CAP;             // unreachable guard
+        __syncwarp();
+
+        // ---- 3. bitonic sort of the records (padded with +inf to a power of two)
+        int npow = 32;
+        while (npow < n_cand) npow <<= 1;
+        for (int p = n_cand + lane; p < npow; p += 32) {
+            KnnRec r;
+            r.d2 = INFINITY; r.idx = 0x7fffffff; r.pad = 0;
+            rec[p] = r;
         }
         __syncwarp();
-        // outputs
+        for (int size = 2; size <= npow; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int t = lane; t < (npow >> 1); t += 32) {
+                    const int i = 2 * t - (t & (stride - 1));         // lower index of the pair
+                    const int j = i + stride;
+                    const bool up = (i & size) == 0;
+                    const KnnRec a = rec[i], b = rec[j];
+                    if (rec_less(b, a) == up) { rec[i] = b; rec[j] = a; }
+                }
+                __syncwarp();
+            }
+        }
+        const int have = n_cand < k ? n_cand : k;
+
+        // ---- outputs
         for (int p = lane; p < k; p += 32) {
-            if (idx_out) idx_out[qi * k + p] = p < have ? list[p].idx : -1;
-            if (d2_out) d2_out[qi * k + p] = p < have ? list[p].d2 : INFINITY;
+            if (idx_out) idx_out[qi * k + p] = p < have ? rec[p].idx : -1;
+            if (d2_out) d2_out[qi * k + p] = p < have ? rec[p].d2 : INFINITY;
         }
         if (feats) {
+            // integer moments of the first ks[s] records; lane s finalises scale s
+            Moments mine;
+            mine.n = 0;
+#pragma unroll
+            for (int t = 0; t < 3; ++t) mine.s1[t] = 0;
+#pragma unroll
+            for (int t = 0; t < 6; ++t) mine.s2[t] = 0;
             for (int s = 0; s < ks.n; ++s) {
                 const int kk = ks.k[s] < have ? ks.k[s] : have;
                 long long acc[10];
 #pragma unroll
                 for (int t = 0; t < 10; ++t) acc[t] = 0;
                 for (int p = lane; p < kk; p += 32) {
-                    const long long jx = list[p].kx - c[0], jy = list[p].ky - c[1], jz = list[p].kz - c[2];
+                    // cell of the voxel from its packed address (utils/geometry.py:120-131), relative to the anchor
+                    const uint64_t key = L.ukeys[rec[p].idx];
+                    long long j[3];
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        const uint64_t mask = g.widths[a] >= 64 ? ~0ull : ((1ull << g.widths[a]) - 1);
+                        j[a] = (long long)((key >> g.shifts[a]) & mask) - g.cell_lo[a] - c[a];
+                    }
+                    const long long jx = j[0], jy = j[1], jz = j[2];
                     acc[0] += 1; acc[1] += jx; acc[2] += jy; acc[3] += jz;
                     acc[4] += jx * jx; acc[5] += jx * jy; acc[6] += jx * jz;
                     acc[7] += jy * jy; acc[8] += jy * jz; acc[9] += jz * jz;
@@ -174,19 +244,21 @@ knn_kernel(LatticeDev L, const void *__restrict__ query, int dtype, int64_t nq, 
                 for (int t = 0; t < 10; ++t)
 #pragma unroll
                     for (int o = 16; o; o >>= 1) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], o);
-                if (lane == 0) {
-                    Moments m;
-                    m.n = acc[0];
-                    m.s1[0] = acc[1]; m.s1[1] = acc[2]; m.s1[2] = acc[3];
+                if (lane == s) {
+                    mine.n = acc[0];
+                    mine.s1[0] = acc[1]; mine.s1[1] = acc[2]; mine.s1[2] = acc[3];
 #pragma unroll
-                    for (int t = 0; t < 6; ++t) m.s2[t] = acc[4 + t];
-                    emit_features<OutT>(m, f, g.edge, feats + qi * row_stride + col_offset + s * ncol, descriptor_mask);
+                    for (int t = 0; t < 6; ++t) mine.s2[t] = acc[4 + t];
                 }
             }
+            if (lane < ks.n)
+                emit_features<OutT>(mine, f, g.edge, feats + qi * row_stride + col_offset + lane * ncol, descriptor_mask);
         }
         __syncwarp();
     }
 }
+
+static size_t knn_smem() { return sizeof(KnnRec) * (size_t)KNN_CAP * KNN_WARPS; }
 
 int knn(const Lattice *lat, const void *query, int dtype, int64_t nq, int k, int32_t *idx_out, double *d2_out,
         const int32_t *ks, int n_k, void *feats, int out_dtype, int64_t row_stride, int col_offset, int descriptor_mask,
@@ -203,8 +275,14 @@ int knn(const Lattice *lat, const void *query, int dtype, int64_t nq, int k, int
         if (ks[i] < 1 || ks[i] > k) return fail(NBR_ERR_INVALID, "knn: every ks[i] must be in [1, k]");
         kp.k[i] = ks[i];
     }
-    const size_t smem = sizeof(KnnEntry) * (size_t)k * KNN_WARPS;
-    const int blocks = (int)std::min<int64_t>(ceil_div(nq, KNN_WARPS), (int64_t)device_sm_count() * 16);
+    const size_t smem = knn_smem();
+    static bool configured = false;
+    if (!configured) {
+        NBR_CUDA(cudaFuncSetAttribute(knn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NBR_CUDA(cudaFuncSetAttribute(knn_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int blocks = (int)std::min<int64_t>(ceil_div(nq, KNN_WARPS), (int64_t)device_sm_count() * 8);
     if (out_dtype == NBR_F32)
         knn_kernel<float><<<blocks, KNN_WARPS * 32, smem, stream>>>(lat->dev(), query, dtype, nq, k, idx_out, d2_out, kp,
                                                                      (float *)feats, row_stride, col_offset, descriptor_mask);
