@@ -58,6 +58,7 @@ static __device__ __noinline__ void eig3_near_isotropic(const double a[6], doubl
     l[0] = e0; l[2] = e2; l[1] = 1.0 - e0 - e2;
 }
 
+template <bool WANT_NORMAL>
 __device__ __forceinline__ void eig3_unit_trace(const double a[6], double l[3], double normal[3])
 {
     normal[0] = 0.0; normal[1] = 0.0; normal[2] = 1.0;
@@ -91,52 +92,71 @@ __device__ __forceinline__ void eig3_unit_trace(const double a[6], double l[3], 
     const float invf = rsqrtf(nn);
 
     // ---- float64: exact deflation around that (approximate) eigenvector.  an error d in v only
-    // enters the results at second order (spread * d^2 ~ 1e-13).
-    double v[3] = {(double)(vx * invf), (double)(vy * invf), (double)(vz * invf)};
-    const double inv = rsqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
-    v[0] *= inv; v[1] *= inv; v[2] *= inv;
+    // enters the results at second order (spread * d^2 ~ 1e-13).  v is NOT renormalised in float64: with
+    // s = v.v, u1 = e_k x v (exactly orthogonal to v, entries are copies of v's) and u2 = v x u1,
+    //     lam = v.Av / s,   m00 = u1.Au1 / nu,   m11 = u2.Au2 / (s nu),   m01^2 = (u1.Au2)^2 / (s nu^2),  nu = |u1|^2,
+    // so the only divisions are two reciprocals (float32 seed + Newton) and the only root is the
+    // discriminant's (float32 rsqrt seed + one Newton step): no float64 sqrt/rsqrt library calls.
+    const double v[3] = {(double)(vx * invf), (double)(vy * invf), (double)(vz * invf)};
+    const double s = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];      // 1 +- 1e-6
+    double rs = 2.0 - s;
+    rs = rs * (2.0 - s * rs);                                        // 1/s to 1e-24
     double av[3];
     sym_mul(a, v, av);
-    const double lam = v[0] * av[0] + v[1] * av[1] + v[2] * av[2];           // Rayleigh quotient
+    const double lam = (v[0] * av[0] + v[1] * av[1] + v[2] * av[2]) * rs;           // Rayleigh quotient
 
     double u1[3], u2[3];
-    const double ax = fabs(v[0]), ay = fabs(v[1]), az = fabs(v[2]);
-    if (ax <= ay && ax <= az) { u1[0] = 0.0; u1[1] = -v[2]; u1[2] = v[1]; }
-    else if (ay <= az)        { u1[0] = v[2]; u1[1] = 0.0; u1[2] = -v[0]; }
-    else                      { u1[0] = -v[1]; u1[1] = v[0]; u1[2] = 0.0; }
-    const double iu = rsqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
-    u1[0] *= iu; u1[1] *= iu; u1[2] *= iu;
+    const float ax = fabsf(vx), ay = fabsf(vy), az = fabsf(vz);
+    double nu;
+    if (ax <= ay && ax <= az) { u1[0] = 0.0; u1[1] = -v[2]; u1[2] = v[1]; nu = s - v[0] * v[0]; }
+    else if (ay <= az)        { u1[0] = v[2]; u1[1] = 0.0; u1[2] = -v[0]; nu = s - v[1] * v[1]; }
+    else                      { u1[0] = -v[1]; u1[1] = v[0]; u1[2] = 0.0; nu = s - v[2] * v[2]; }
     u2[0] = v[1] * u1[2] - v[2] * u1[1];
     u2[1] = v[2] * u1[0] - v[0] * u1[2];
     u2[2] = v[0] * u1[1] - v[1] * u1[0];
+    double in1 = (double)__frcp_rn((float)nu);                      // nu = |u1|^2 >= 2/3 s
+    in1 = in1 * (2.0 - nu * in1);
     double au1[3], au2[3];
     sym_mul(a, u1, au1);
     sym_mul(a, u2, au2);
-    const double m00 = u1[0] * au1[0] + u1[1] * au1[1] + u1[2] * au1[2];
-    const double m01 = u1[0] * au2[0] + u1[1] * au2[1] + u1[2] * au2[2];
-    const double m11 = u2[0] * au2[0] + u2[1] * au2[1] + u2[2] * au2[2];
+    const double m00 = (u1[0] * au1[0] + u1[1] * au1[1] + u1[2] * au1[2]) * in1;
+    const double m11 = (u2[0] * au2[0] + u2[1] * au2[1] + u2[2] * au2[2]) * in1 * rs;
+    const double c01 = (u1[0] * au2[0] + u1[1] * au2[1] + u1[2] * au2[2]) * in1;   // m01 * sqrt(s)
     const double mid = 0.5 * (m00 + m11);
     const double hd = 0.5 * (m00 - m11);
-    const double rad = sqrt(hd * hd + m01 * m01);
+    const double disc = hd * hd + c01 * c01 * rs;
+    double rad = 0.0;
+    if (disc > 1.0e-30) {                                            // below: a double root to 1e-15
+        const double y0 = (double)rsqrtf((float)disc);
+        const double y1 = y0 * (1.5 - 0.5 * disc * y0 * y0);
+        rad = disc * y1;
+    }
     const double hi = mid + rad, lo = mid - rad;
     if (top) {
         l[0] = lam; l[1] = hi; l[2] = lo;
-        // eigenvector of the 2x2 block for `lo`, mapped back
-        double w0 = m01, w1 = lo - m00;
-        if (fabs(lo - m11) > fabs(w1)) { w0 = lo - m11; w1 = m01; }
-        const double wn = w0 * w0 + w1 * w1;
-        if (wn > 0.0) {
-            const double iw = rsqrt(wn);
-            w0 *= iw; w1 *= iw;
-            normal[0] = w0 * u1[0] + w1 * u2[0];
-            normal[1] = w0 * u1[1] + w1 * u2[1];
-            normal[2] = w0 * u1[2] + w1 * u2[2];
-        } else {
-            normal[0] = u2[0]; normal[1] = u2[1]; normal[2] = u2[2];
+        if (WANT_NORMAL) {
+            // eigenvector of the 2x2 block for `lo`, mapped back through the normalised u1, u2
+            const double m01 = c01 * rsqrt(s);
+            double w0 = m01, w1 = lo - m00;
+            if (fabs(lo - m11) > fabs(w1)) { w0 = lo - m11; w1 = m01; }
+            const double wn = w0 * w0 + w1 * w1;
+            const double i1 = rsqrt(nu), i2 = rsqrt(nu * s);
+            if (wn > 0.0) {
+                const double iw = rsqrt(wn);
+                w0 *= iw * i1; w1 *= iw * i2;
+                normal[0] = w0 * u1[0] + w1 * u2[0];
+                normal[1] = w0 * u1[1] + w1 * u2[1];
+                normal[2] = w0 * u1[2] + w1 * u2[2];
+            } else {
+                normal[0] = u2[0] * i2; normal[1] = u2[1] * i2; normal[2] = u2[2] * i2;
+            }
         }
     } else {
         l[0] = hi; l[1] = lo; l[2] = lam;
-        normal[0] = v[0]; normal[1] = v[1]; normal[2] = v[2];
+        if (WANT_NORMAL) {
+            const double iv = rsqrt(s);
+            normal[0] = v[0] * iv; normal[1] = v[1] * iv; normal[2] = v[2] * iv;
+        }
     }
 }
 
@@ -185,7 +205,8 @@ __device__ __forceinline__ void emit_core(long long n_int, double centroid, doub
 #pragma unroll
             for (int i = 0; i < 6; ++i) a[i] *= it;
             double l[3], v[3];
-            eig3_unit_trace(a, l, v);
+            if (descriptor_mask & NBR_DESC_EXTENDED) eig3_unit_trace<true>(a, l, v);
+            else eig3_unit_trace<false>(a, l, v);
             l0 = l[0];
             l1 = l[1];
             if ((descriptor_mask & NBR_DESC_EXTENDED) && n_int >= 3)
