@@ -302,9 +302,19 @@ def gpu_arm(args, rank, world, local_rank):
         rho = np.zeros(ns)
     algo_bytes = float(sum(n * (28.0 + 12.0 * r) for r in rho)) if world == 1 else float(n * ns * 28.0)
     achieved = algo_bytes / (feat_ms * 1e-3) / 1e9 if feat_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "fused radius query + covariance + eigen + features (all scales of a step)",
+    traffic, traffic_src = None, None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_rows3_traffic.json")))
+        if world == 1 and n == 10_000_000:
+            traffic = float(tr["dram_bytes_read"] + tr["dram_bytes_write"])
+            traffic_src = "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel " \
+                          "on this workload (profiles/r01_rows3_traffic.json)"
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "nbr::rows3_kernel: fused radius query + covariance + eigen + features "
+                                          "(one launch for all scales of a step)",
                 "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_step": algo_bytes, "kernel_ms_per_step": feat_ms,
                 "bytes_per_point_scale": "28 + 12*rho_s (SURVEY.md 8d); rho_s = unique voxels / queries = %s"
                                          % [round(float(r), 4) for r in rho],

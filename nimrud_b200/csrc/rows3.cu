@@ -203,7 +203,11 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
                 {
                     const char *line = reinterpret_cast<const char *>(E.table + (size_t)tbin * 8);
 #pragma unroll
+#ifdef R3_ABL_TABLE1
+                    for (int j = 0; j < N7; ++j) cp_async16(tab_addr + 16u * j, line + 16 * 3);
+#else
                     for (int j = 0; j < N7; ++j) cp_async16(tab_addr + 16u * j, line + 16 * j);
+#endif
                 }
                 if (total) {
                     uint32_t slot0 = 0, slot1 = 0;
