@@ -88,6 +88,8 @@ int morton_order(const void *xyz, int dtype, int64_t n, const double lohi[6], do
                  void *sorted_xyz_out, cudaStream_t stream);
 int cell_order(const void *xyz, int dtype, int64_t n, const double lohi[6], const double origin[3],
                const double cell_in[3], uint32_t *perm_out, void *sorted_xyz_out, cudaStream_t stream);
+int compact_prefix_queries(const uint32_t *perm, const void *sorted, int dtype, int64_t n, int64_t nq, uint32_t *perm_q,
+                           void *sorted_q, cudaStream_t stream);
 int radius_sets(const Lattice *lat, const void *query, int dtype, int64_t nq, double radius, int64_t *offsets,
                 int32_t *indices, cudaStream_t stream);
 
@@ -339,24 +341,35 @@ int multiscale_features(const void *query, int q_dtype, int64_t nq, const void *
     NBR_TRY(check_cloud_dtype(s_dtype, "multiscale_features"));
     if (ns < 2) return fail(NBR_ERR_TOO_FEW_POINTS, "need at least 2 points to define a voxel grid");
     if (!search) return fail(NBR_ERR_INVALID, "multiscale_features: null argument");
-    const bool same = query == search && nq == ns && q_dtype == s_dtype && n_scales > 0 && out;
+    // query cloud == search cloud, or its first nq points (tile + halo, multi-GPU): order the search cloud once
+    // and build the lattices from the ordered copy too (coalesced directory / pool updates); the lattices do
+    // not depend on the order of the points
+    const bool same = query == search && nq <= ns && nq > 0 && q_dtype == s_dtype && n_scales > 0 && out;
     Plan *P = nullptr;
     int rc;
     if (same) {
-        // query cloud == search cloud: order it once and build the lattices from the ordered copy too
-        // (coalesced directory / pool updates); the lattices do not depend on the order of the points
         double box[6], finest = 0.0;
         for (int s = 0; s < n_scales; ++s) {
             if (!edges || !(edges[s] > 0)) return fail(NBR_ERR_INVALID, "multiscale_features: edge lengths must be > 0");
             finest = s == 0 ? edges[s] : std::min(finest, edges[s]);
         }
         NBR_TRY(host_bbox(search, s_dtype, ns, box, stream));
-        Scratch perm, sorted;
+        Scratch perm, sorted, perm_q, sorted_q;
         double origin[3];
         NBR_TRY(brick_origin(global_lohi ? global_lohi : box, global_lohi ? box : nullptr, finest, origin));
-        NBR_TRY(order_queries(query, q_dtype, nq, box, finest, origin, perm, sorted, stream));
+        NBR_TRY(order_queries(search, s_dtype, ns, box, finest, origin, perm, sorted, stream));
         NBR_TRY(plan_create(&P, sorted.ptr, s_dtype, ns, edges, radii, n_scales, descriptor_mask, global_lohi, box, stream));
-        rc = plan_run_sorted(P, sorted.ptr, q_dtype, perm.as<uint32_t>(), nq, out, out_dtype, stream);
+        if (nq < ns) {
+            rc = perm_q.alloc(sizeof(uint32_t) * nq, stream);
+            if (!rc) rc = sorted_q.alloc((size_t)nq * 3 * (q_dtype == NBR_F32 ? 4 : 8), stream);
+            if (!rc) {
+                PhaseTimer t(PHASE_ORDER, stream);
+                rc = compact_prefix_queries(perm.as<uint32_t>(), sorted.ptr, q_dtype, ns, nq, perm_q.as<uint32_t>(), sorted_q.ptr, stream);
+            }
+            if (!rc) rc = plan_run_sorted(P, sorted_q.ptr, q_dtype, perm_q.as<uint32_t>(), nq, out, out_dtype, stream);
+        } else {
+            rc = plan_run_sorted(P, sorted.ptr, q_dtype, perm.as<uint32_t>(), nq, out, out_dtype, stream);
+        }
         if (rc == NBR_OK && n_voxels_host) rc = plan_voxel_counts(P, n_voxels_host);
         delete P;
         return rc;

@@ -230,4 +230,53 @@ int cell_order(const void *xyz, int dtype, int64_t n, const double lohi[6], cons
     return NBR_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// queries = the first nq points of an ordered cloud of n points (tile + halo: the tile's points are the
+// queries, multi-GPU path).  keeps the order, drops the others: perm_q / sorted_q hold the nq entries whose
+// original index is < nq.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+prefix_flag_kernel(const uint32_t *__restrict__ perm, int64_t n, uint32_t nq, uint32_t *__restrict__ flags)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = perm[i] < nq ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256)
+prefix_compact_kernel(const uint32_t *__restrict__ perm, const void *__restrict__ sorted, int dtype, int64_t n,
+                      const uint32_t *__restrict__ slots, uint32_t *__restrict__ perm_q, void *__restrict__ sorted_q)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t s = slots[i];
+    if (!s) return;
+    const int64_t pos = (int64_t)s - 1;
+    perm_q[pos] = perm[i];
+    if (dtype == NBR_F32) {
+        const float *src = reinterpret_cast<const float *>(sorted) + i * 3;
+        float *dst = reinterpret_cast<float *>(sorted_q) + pos * 3;
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+    } else {
+        const double *src = reinterpret_cast<const double *>(sorted) + i * 3;
+        double *dst = reinterpret_cast<double *>(sorted_q) + pos * 3;
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+    }
+}
+
+int compact_prefix_queries(const uint32_t *perm, const void *sorted, int dtype, int64_t n, int64_t nq, uint32_t *perm_q,
+                           void *sorted_q, cudaStream_t stream)
+{
+    if (n <= 0 || nq <= 0) return NBR_OK;
+    Scratch flags, count;
+    NBR_TRY(flags.alloc(sizeof(uint32_t) * n, stream));
+    NBR_TRY(count.alloc(sizeof(uint32_t), stream));
+    const unsigned blocks = (unsigned)ceil_div(n, 256);
+    prefix_flag_kernel<<<blocks, 256, 0, stream>>>(perm, n, (uint32_t)nq, flags.as<uint32_t>());
+    NBR_LAUNCHED();
+    NBR_TRY(flags_to_slots(flags.as<uint32_t>(), n, count.as<uint32_t>(), stream));
+    prefix_compact_kernel<<<blocks, 256, 0, stream>>>(perm, sorted, dtype, n, flags.as<uint32_t>(), perm_q, sorted_q);
+    NBR_LAUNCHED();
+    return NBR_OK;
+}
+
 }  // namespace nbr

@@ -28,9 +28,8 @@ def halo_width(edge_lengths, radii):
 
 
 def tile_box(cloud):
-    """(lo, hi) float64 tensors (3,) on the cloud's device."""
-    c = cloud.to(torch.float64) if cloud.dtype != torch.float64 else cloud
-    return c.min(0).values, c.max(0).values
+    """(lo, hi) float64 tensors (3,) on the cloud's device (min / max are exact in the cloud's own dtype)."""
+    return cloud.min(0).values.to(torch.float64), cloud.max(0).values.to(torch.float64)
 
 
 def global_box(lo, hi, group=None):
@@ -41,9 +40,17 @@ def global_box(lo, hi, group=None):
 
 
 def select_halo(cloud, box_lo, box_hi, h):
-    """indices of the points of `cloud` inside [box_lo - h, box_hi + h] (inclusive, all three axes)."""
-    c = cloud.to(torch.float64) if cloud.dtype != torch.float64 else cloud
-    inside = ((c >= (box_lo - h)) & (c <= (box_hi + h))).all(1)
+    """indices of the points of `cloud` inside [box_lo - h, box_hi + h] (inclusive, all three axes).
+    the bounds are rounded OUTWARD to the cloud's dtype, so the test runs on the coordinates as stored
+    (no float64 copy of the cloud) and can only select a superset of the exact float64 test."""
+    lo = (box_lo - h).to(torch.float64)
+    hi = (box_hi + h).to(torch.float64)
+    if cloud.dtype != torch.float64:
+        lo_c, hi_c = lo.to(cloud.dtype), hi.to(cloud.dtype)
+        lo_c = torch.where(lo_c.to(torch.float64) > lo, torch.nextafter(lo_c, torch.full_like(lo_c, -float("inf"))), lo_c)
+        hi_c = torch.where(hi_c.to(torch.float64) < hi, torch.nextafter(hi_c, torch.full_like(hi_c, float("inf"))), hi_c)
+        lo, hi = lo_c, hi_c
+    inside = ((cloud >= lo) & (cloud <= hi)).all(1)
     return inside.nonzero(as_tuple=True)[0]
 
 
@@ -55,14 +62,19 @@ def exchange_halo(cloud, edge_lengths, radii, group=None):
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     lo, hi = tile_box(cloud)
-    g_lo, g_hi = global_box(lo, hi, group)
     boxes = [torch.empty(6, dtype=torch.float64, device=cloud.device) for _ in range(world)]
     dist.all_gather(boxes, torch.cat([lo, hi]), group=group)
+    all_boxes = torch.stack(boxes).cpu()                       # (world, 6): one small device->host copy
+    g_lo = all_boxes[:, :3].min(0).values.to(cloud.device)     # == all-reduce(min/max) of the tile boxes
+    g_hi = all_boxes[:, 3:].max(0).values.to(cloud.device)
     h = halo_width(edge_lengths, radii)
+    my_lo, my_hi = all_boxes[rank, :3], all_boxes[rank, 3:]
 
     send_parts, send_counts = [], []
     for dst in range(world):
-        if dst == rank:
+        d_lo, d_hi = all_boxes[dst, :3], all_boxes[dst, 3:]
+        # tiles whose grown box misses this tile's box get nothing
+        if dst == rank or bool(((d_lo - h) > my_hi).any()) or bool(((d_hi + h) < my_lo).any()):
             send_counts.append(0)
             continue
         idx = select_halo(cloud, boxes[dst][:3], boxes[dst][3:], h)
@@ -96,7 +108,10 @@ def process_tile(cloud, edge_lengths, radii, out=None, out_dtype=np.float32, gat
     halo, (g_lo, g_hi), _ = exchange_halo(cloud, edge_lengths, radii, group)
     search = torch.cat([cloud, halo], 0) if halo.numel() else cloud
     bbox = (g_lo.cpu().numpy(), g_hi.cpu().numpy())
-    feats = (compute or _gpu_compute)(cloud, search, edge_lengths, radii, bbox, out_dtype, out)
+    # the queries are handed over as the first rows of the search buffer: the CUDA path then orders tile + halo
+    # once, builds the lattices from the ordered copy and keeps only the tile's points as queries
+    query = search[:cloud.shape[0]]
+    feats = (compute or _gpu_compute)(query, search, edge_lengths, radii, bbox, out_dtype, out)
     if not gather:
         return feats
     world = dist.get_world_size(group)
