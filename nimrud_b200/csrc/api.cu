@@ -215,11 +215,14 @@ int plan_create(Plan **out, const void *search, int s_dtype, int64_t ns, const d
     }
     {
         PhaseTimer t(PHASE_INDEX, stream);
-        for (auto &g : P->groups) {
-            nbr_grid grid;
-            rc = grid_from_bbox(lohi, lohi + 3, g.edge, 3, &grid);
-            if (!rc) rc = lattice_create(&g.lat, search, s_dtype, ns, &grid, 0, stream, global_lohi ? P->local_box : nullptr);
-            if (rc) break;
+        // all lattices of the call in one pass over the points (batches of LATTICE_BATCH)
+        for (size_t base = 0; !rc && base < P->groups.size(); base += LATTICE_BATCH) {
+            const int nb = (int)std::min<size_t>(LATTICE_BATCH, P->groups.size() - base);
+            nbr_grid grids[LATTICE_BATCH];
+            Lattice *made[LATTICE_BATCH] = {nullptr};
+            for (int k = 0; !rc && k < nb; ++k) rc = grid_from_bbox(lohi, lohi + 3, P->groups[base + k].edge, 3, &grids[k]);
+            if (!rc) rc = lattices_create_batch(made, nb, grids, search, s_dtype, ns, stream, global_lohi ? P->local_box : nullptr);
+            if (!rc) for (int k = 0; k < nb; ++k) P->groups[base + k].lat = made[k];
         }
     }
     if (!rc && n_scales > 0) rc = brick_origin(lohi, global_lohi ? P->local_box : nullptr, P->finest, P->order_origin);
