@@ -210,13 +210,17 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
 #endif
                 }
                 if (total) {
+                    const float inv0 = __frcp_rn((float)nb0), inv01 = __frcp_rn((float)(nb0 * nb1));
                     uint32_t slot0 = 0, slot1 = 0;
 #pragma unroll
                     for (int t = 0; t < 2; ++t) {
                         const int b = lane + 32 * t;
                         uint32_t sl = 0;
                         if (b < total) {
-                            const int ix = b % nb0, iy = (b / nb0) % nb1, iz = b / (nb0 * nb1);
+                            // b < 64 and nb0 * nb1 <= 48: the float quotients are exact after truncation
+                            const int iz = (int)(((float)b + 0.5f) * inv01);
+                            const int rem = b - iz * nb0 * nb1;
+                            const int iy = (int)(((float)rem + 0.5f) * inv0), ix = rem - iy * nb0;
                             const int gx = lo0 + ix, gy = lo1 + iy, gz = lo2 + iz;
                             if (gx >= 0 && gx < E.nbx && gy >= 0 && gy < E.nby && gz >= 0 && gz < E.nbz)
                                 sl = E.dir[((int64_t)gz * E.nby + gy) * E.nbx + gx];
@@ -280,6 +284,8 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
             __syncwarp();
 #endif
             int An = 0, Asx = 0, Asy = 0, Asz = 0, Asxx = 0, Asxy = 0, Asxz = 0, Asyy = 0, Asyz = 0, Aszz = 0;
+            uint2 *ulist = reinterpret_cast<uint2 *>(const_cast<uint4 *>(tab));
+            int n_u = 0;
 #pragma unroll R3_UNROLL
             for (int jz = 0; jz < N7; ++jz) {
                 const uint4 tcur = tab[jz];
@@ -318,28 +324,10 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
                 // ---- membership: sure cells + occupied cells of the uncertain shell
                 unsigned long long M = slab & ((unsigned long long)tcur.x | ((unsigned long long)tcur.y << 32));
                 const unsigned long long U = slab & ((unsigned long long)tcur.z | ((unsigned long long)tcur.w << 32));
-                if (U) {
-                    const float dzf = fzm - (float)jz;
-                    const float dz2f = dzf * dzf;
-                    uint32_t alo = 0, ahi = 0;
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        uint32_t u = half ? (uint32_t)(U >> 32) : (uint32_t)U, acc = 0;
-                        while (u) {
-                            const int b = __ffs(u) - 1;
-                            u &= u - 1;
-                            const int i = b + 32 * half;
-                            const int jy = (i * 37) >> 8, t = i - 7 * jy;
-                            const float dx = fxm - (float)t, dy = fym - (float)jy;
-                            const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz2f));
-                            bool in = d2 < E.rho2;
-                            if (fabsf(d2 - E.rho2) < 4.0e-5f) in = r3_exact_in(E, q[0], q[1], q[2], xa + t, ya + jy, az);
-                            acc |= in ? 1u << b : 0u;
-                        }
-                        if (half) ahi = acc; else alo = acc;
-                    }
-                    M |= (unsigned long long)alo | ((unsigned long long)ahi << 32);
-                }
+                // the uncertain cells are parked in the lane's table line (slots <= jz are consumed) and decided after
+                // the slab loop in ONE loop: deciding them slab by slab made every slab wait for its slowest lane
+                if ((uint32_t)U) { ulist[n_u++] = make_uint2((uint32_t)U, (uint32_t)jz); }
+                if ((uint32_t)(U >> 32)) { ulist[n_u++] = make_uint2((uint32_t)(U >> 32), (uint32_t)jz | 256u); }
                 if (M == 0) continue;
                 // ---- moments of the slab
                 uint32_t Pk = 0, Qk = 0;
@@ -355,6 +343,36 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
                 const int SY = Qk & 1023, SXY = (Qk >> 10) & 1023;
                 An += C; Asx += SX; Asxx += SXX; Asy += SY; Asyy += R; Asxy += SXY;
                 Asz += jz * C; Aszz += jz * jz * C; Asxz += jz * SX; Asyz += jz * SY;
+            }
+            // ---- occupied cells of the uncertain shell: float32 first, |d^2 - rho^2| > band decides; inside the band
+            // the reference's float64 expression does.  accepted cells are added to the moments one by one
+            {
+                uint32_t cur = 0;
+                int k = 0, jzc = 0, half = 0;
+                float dz2f = 0.0f;
+                for (;;) {
+                    if (cur == 0) {
+                        if (k >= n_u) break;
+                        const uint2 e = ulist[k++];
+                        cur = e.x;
+                        jzc = (int)(e.y & 255u);
+                        half = (int)(e.y >> 8) * 32;
+                        const float dzf = fzm - (float)jzc;
+                        dz2f = dzf * dzf;
+                    }
+                    const int i = __ffs(cur) - 1 + half;
+                    cur &= cur - 1;
+                    const int jy = (i * 37) >> 8, t = i - 7 * jy;
+                    const float dx = fxm - (float)t, dy = fym - (float)jy;
+                    const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz2f));
+                    bool in = d2 < E.rho2;
+                    if (fabsf(d2 - E.rho2) < 4.0e-5f) in = r3_exact_in(E, q[0], q[1], q[2], xa + t, ya + jy, za + jzc);
+                    if (in) {
+                        An += 1; Asx += t; Asy += jy; Asz += jzc;
+                        Asxx += t * t; Asxy += t * jy; Asxz += t * jzc;
+                        Asyy += jy * jy; Asyz += jy * jzc; Aszz += jzc * jzc;
+                    }
+                }
             }
             if (active)
                 emit_features_window<OutT>(An, Asx, Asy, Asz, Asxx, Asxy, Asxz, Asyy, Asyz, Aszz, fxm, fym, fzm, true,
