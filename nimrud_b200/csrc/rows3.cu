@@ -41,7 +41,7 @@ constexpr int R3_WARPS = R3_WARPS_N;
 constexpr int R3_UNROLL = R3_UNROLL_N;   // slabs per trip of the slab loop
 constexpr int R3_CAP = R3_CAP_N;          // staged bricks per warp (128 bytes each)
 constexpr int N7 = 7, W3 = 3;
-constexpr int R3_TAB_STRIDE = 36;   // words per lane: 128-byte line + 16 bytes of padding (conflict-free LDS.128)
+constexpr int R3_TAB_STRIDE = R3_STAGE_TMA ? 36 : 28;   // words per lane: 7 slabs x 16 bytes (TMA: a whole 128-byte line + padding); both conflict-free for LDS.128
 constexpr int R3_WIN_BYTES = R3_CAP * BRICK_WORDS * 4;
 constexpr int R3_TAB_BYTES = 32 * R3_TAB_STRIDE * 4;
 constexpr int R3_MAX_ROW_BYTES = 256;   // output rows up to this size are assembled in shared memory
@@ -123,7 +123,9 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+#if R3_STAGE_TMA
     uint32_t parity = 0;
+#endif
     const int64_t n_groups = (nq + 31) >> 5;
     constexpr uint32_t rowmask = 127u;
 

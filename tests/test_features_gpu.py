@@ -204,3 +204,53 @@ def test_raw_ctypes_stub_from_integration_md():
     b = multiscale.process_single_core(torch.from_numpy(cloud[:300_000]).cuda(), torch.from_numpy(cloud).cuda(),
                                        (0.2, 0.4), (0.6, 1.2)).cpu().numpy()
     assert np.array_equal(a, b)
+
+
+def test_mixed_window_widths_in_one_call(c_oracle):
+    # r/e = 2, 3 (7x7x7 windows: shell-table kernel, equal edges share one staged window), r/e = 5
+    # (interval kernel) and r/e = 12 (per-candidate kernel) in ONE call: every column block comes from a
+    # different kernel, none may touch the others' columns.  device tensors and host arrays.
+    import torch
+    from nimrud_b200 import multiscale, synth
+    cloud = synth.urban_scene(150_000, seed=5).numpy()
+    q = cloud[::5].copy()
+    edges = (0.2, 0.2, 0.2, 0.1)
+    radii = (0.4, 0.6, 1.0, 1.2)
+    ref = c_oracle.process(q, cloud, edges, radii, threads=8)
+    host = multiscale.process_single_core(q, cloud, edges, radii)
+    assert_features_close(host, ref, radii)
+    dev = multiscale.process_single_core(torch.from_numpy(q).cuda(), torch.from_numpy(cloud).cuda(), edges, radii,
+                                         out_dtype=np.float32)
+    assert_features_close(dev.cpu().numpy(), ref, radii)
+
+
+def test_shell_table_exactness_on_a_dense_lattice(c_oracle):
+    # every cell of a block occupied: all 343 cells of every window are candidates, queries at arbitrary
+    # fractional positions and exactly on centres / faces / corners, radii that put many centres exactly on
+    # the sphere.  populations must match the float64 oracle exactly.
+    from nimrud_b200 import multiscale
+    rs = np.random.RandomState(11)
+    g = np.stack(np.meshgrid(np.arange(14), np.arange(14), np.arange(14), indexing="ij"), -1).reshape(-1, 3)
+    search = (g * 0.25 + 0.125).astype(np.float32)
+    inner = search[(g.min(1) >= 4) & (g.max(1) <= 9)]
+    q = np.concatenate([inner[:200], inner[:200] + 0.125, inner[:200] + np.float32(0.0625),
+                        (rs.rand(3000, 3) * 1.25 + 1.0).astype(np.float32)]).astype(np.float32)
+    for r in (0.25, 0.5, 0.75, 0.559017, 0.8291562):          # e, 2e, 3e, sqrt(5) e, sqrt(11) e
+        ref = c_oracle.process(q, search, [0.25], [r])
+        out = multiscale.process_single_core(q, search, [0.25], [r])
+        assert np.array_equal(out[:, 0], ref[:, 0]), r
+        assert_features_close(out, ref, [r])
+
+
+def test_far_and_outside_queries(c_oracle):
+    # queries outside the search cloud's box (partly or completely): windows hang over the lattice edge
+    from nimrud_b200 import multiscale, synth
+    cloud = synth.urban_scene(60_000, seed=6).numpy()
+    lo, hi = cloud.min(0), cloud.max(0)
+    rs = np.random.RandomState(4)
+    q = np.concatenate([cloud[:500], lo - rs.rand(300, 3).astype(np.float32), hi + rs.rand(300, 3).astype(np.float32),
+                        lo - 1000.0 + rs.rand(50, 3).astype(np.float32), [[1e6, -1e6, 3.0]]]).astype(np.float32)
+    edges, radii = (0.2, 0.4), (0.6, 1.2)
+    ref = c_oracle.process(q, cloud, edges, radii)
+    out = multiscale.process_single_core(q, cloud, edges, radii)
+    assert_features_close(out, ref, radii)
