@@ -165,6 +165,17 @@ int nbr_multiscale_features_host(const void *query_host, int q_dtype, int64_t n_
                                  void *out_host, int out_dtype, int32_t descriptor_mask,
                                  int64_t *n_voxels_host);
 
+/* multi-GPU halo selection (no reference counterpart; the precedent is nested_regions,
+ * nimrud/utils/geometry.py:203-253: inclusive box +- buffer radius).  boxes_host: ndst <= 8 boxes as
+ * [lo x,y,z, hi x,y,z] float64, already grown by the halo width.
+ * nbr_halo_count: counts_dev[d] (uint64, device) += number of points of xyz inside box d.
+ * nbr_halo_fill:  the points inside box d are written to rows [offsets_host[d], offsets_host[d] + count_d)
+ *                 of `out` (rows of 3, same dtype as xyz, any order); cursors_dev[ndst] must be zero on entry. */
+int nbr_halo_count(const void *xyz, int dtype, int64_t n, const double *boxes_host, int32_t ndst,
+                   uint64_t *counts_dev, void *stream);
+int nbr_halo_fill(const void *xyz, int dtype, int64_t n, const double *boxes_host, int32_t ndst,
+                  const int64_t *offsets_host, uint64_t *cursors_dev, void *out, void *stream);
+
 /* counters for tests and benches: number of kernels this library has launched in this process. */
 int64_t nbr_kernel_launches(void);
 

@@ -29,6 +29,14 @@ def halo_width(edge_lengths, radii):
 
 def tile_box(cloud):
     """(lo, hi) float64 tensors (3,) on the cloud's device (min / max are exact in the cloud's own dtype)."""
+    if cloud.is_cuda and cloud.dtype in (torch.float32, torch.float64) and cloud.is_contiguous() and cloud.shape[0] > 0:
+        from . import _lib
+        from ._util import ptr, stream_ptr
+        box = torch.empty(6, dtype=torch.float64, device=cloud.device)
+        with torch.cuda.device(cloud.device):
+            _lib.check(_lib.lib().nbr_bbox(ptr(cloud), _lib.F32 if cloud.dtype == torch.float32 else _lib.F64,
+                                           int(cloud.shape[0]), 3, ptr(box), stream_ptr(cloud.device)))
+        return box[:3], box[3:]
     return cloud.min(0).values.to(torch.float64), cloud.max(0).values.to(torch.float64)
 
 
@@ -54,6 +62,37 @@ def select_halo(cloud, box_lo, box_hi, h):
     return inside.nonzero(as_tuple=True)[0]
 
 
+def _select_halos_cuda(cloud, grown_boxes):
+    """per destination box (lo, hi float64 (3,) cpu tensors, already grown): the points of `cloud` inside it.
+    two passes of the CUDA halo kernels (count, fill) for all destinations at once -> (send buffer (m,3), counts)."""
+    import ctypes
+    from . import _lib
+    from ._util import ptr, stream_ptr
+    lib = _lib.lib()
+    code = _lib.F32 if cloud.dtype == torch.float32 else _lib.F64
+    n = int(cloud.shape[0])
+    counts = []
+    parts = []
+    with torch.cuda.device(cloud.device):
+        s = stream_ptr(cloud.device)
+        for first in range(0, len(grown_boxes), 8):
+            chunk = grown_boxes[first:first + 8]
+            flat = np.ascontiguousarray([list(lo) + list(hi) for lo, hi in chunk], dtype=np.float64).reshape(-1)
+            boxes_p = flat.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+            cnt = torch.zeros(2 * len(chunk), dtype=torch.int64, device=cloud.device)     # counts | cursors
+            _lib.check(lib.nbr_halo_count(ptr(cloud), code, n, boxes_p, len(chunk), ptr(cnt), s))
+            c = [int(v) for v in cnt[:len(chunk)].tolist()]
+            offs = np.concatenate([[0], np.cumsum(c)[:-1]]).astype(np.int64)
+            buf = torch.empty((sum(c), 3), dtype=cloud.dtype, device=cloud.device)
+            if sum(c):
+                _lib.check(lib.nbr_halo_fill(ptr(cloud), code, n, boxes_p, len(chunk),
+                                             offs.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                             ptr(cnt[len(chunk):]), ptr(buf), s))
+            counts += c
+            parts.append(buf)
+    return (torch.cat(parts, 0) if len(parts) != 1 else parts[0]), counts
+
+
 def exchange_halo(cloud, edge_lengths, radii, group=None):
     """
     -> (halo points received from the other ranks (m,3), same dtype/device as cloud,
@@ -70,21 +109,29 @@ def exchange_halo(cloud, edge_lengths, radii, group=None):
     h = halo_width(edge_lengths, radii)
     my_lo, my_hi = all_boxes[rank, :3], all_boxes[rank, 3:]
 
-    send_parts, send_counts = [], []
-    for dst in range(world):
-        d_lo, d_hi = all_boxes[dst, :3], all_boxes[dst, 3:]
-        # tiles whose grown box misses this tile's box get nothing
-        if dst == rank or bool(((d_lo - h) > my_hi).any()) or bool(((d_hi + h) < my_lo).any()):
-            send_counts.append(0)
-            continue
-        idx = select_halo(cloud, boxes[dst][:3], boxes[dst][3:], h)
-        send_parts.append(cloud[idx])
-        send_counts.append(int(idx.numel()))
+    # tiles whose grown box misses this tile's box get nothing
+    targets = [dst for dst in range(world)
+               if dst != rank and not bool(((all_boxes[dst, :3] - h) > my_hi).any())
+               and not bool(((all_boxes[dst, 3:] + h) < my_lo).any())]
+    send_counts = [0] * world
+    if cloud.is_cuda and cloud.dtype in (torch.float32, torch.float64) and cloud.is_contiguous():
+        grown = [((all_boxes[d, :3] - h).tolist(), (all_boxes[d, 3:] + h).tolist()) for d in targets]
+        send_buf, counts = _select_halos_cuda(cloud, grown) if targets else (cloud[:0], [])
+        for d, c in zip(targets, counts):
+            send_counts[d] = c
+    else:
+        # host logic on CPU tensors (gloo tests): same inclusive selection with torch ops
+        send_parts = []
+        for dst in targets:
+            idx = select_halo(cloud, boxes[dst][:3], boxes[dst][3:], h)
+            send_parts.append(cloud[idx])
+            send_counts[dst] = int(idx.numel())
+        send_buf = torch.cat(send_parts, 0) if send_parts else cloud[:0]
     counts_t = torch.tensor(send_counts, dtype=torch.int64, device=cloud.device)
     recv_counts_t = torch.empty_like(counts_t)
     dist.all_to_all_single(recv_counts_t, counts_t, group=group)
     recv_counts = [int(v) for v in recv_counts_t.tolist()]
-    send_buf = (torch.cat(send_parts, 0) if send_parts else cloud[:0]).contiguous().reshape(-1)
+    send_buf = send_buf.contiguous().reshape(-1)
     recv_buf = torch.empty(sum(recv_counts) * 3, dtype=cloud.dtype, device=cloud.device)
     dist.all_to_all_single(recv_buf, send_buf, output_split_sizes=[3 * c for c in recv_counts],
                            input_split_sizes=[3 * c for c in send_counts], group=group)

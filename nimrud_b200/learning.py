@@ -148,7 +148,7 @@ def classify_scene(cloud, labels, edge_lengths, radii, per_class=None, trials=3,
     """
     labelled scene -> GPU multiscale features -> balanced ExtraTrees -> balanced validation.
     returns dict(features, classifier, confusion_mean, confusion_std, user, producer).
-    `feats` may be supplied (e.g. the oracle's features) to classify with an existing block.
+    `feats` may be supplied to classify with an existing feature block.
     """
     rng = np.random.RandomState(seed)
     if feats is None:
