@@ -528,6 +528,9 @@ batch_fill_kernel(const T *__restrict__ xyz, int64_t n, const __grid_constant__ 
                   uint32_t *__restrict__ pool, unsigned char *__restrict__ counters)
 {
     const int64_t base = ((int64_t)blockIdx.x * PTS) * blockDim.x + threadIdx.x;
+    uint32_t pend_old[PTS], pend_bit[PTS];
+#pragma unroll
+    for (int k = 0; k < PTS; ++k) { pend_old[k] = ~0u; pend_bit[k] = 0; }
     for (int l = 0; l < B.n; ++l) {
         int64_t b[PTS];
         int word[PTS];
@@ -552,13 +555,29 @@ batch_fill_kernel(const T *__restrict__ xyz, int64_t n, const __grid_constant__ 
         uint32_t have[PTS];
 #pragma unroll
         for (int k = 0; k < PTS; ++k) have[k] = bit[k] ? *w[k] : ~0u;
+        // the atomics of the previous lattice have had this lattice's loads to complete: count its new voxels now
+        if (l > 0) {
+            int fresh = 0;
+#pragma unroll
+            for (int k = 0; k < PTS; ++k) fresh += (pend_old[k] & pend_bit[k]) == 0 && pend_bit[k];
+            fresh = __reduce_add_sync(0xffffffffu, fresh);
+            if ((threadIdx.x & 31) == 0 && fresh)
+                atomicAdd(reinterpret_cast<unsigned long long *>(counters + 64 * (l - 1) + 8), (unsigned long long)fresh);
+        }
+#pragma unroll
+        for (int k = 0; k < PTS; ++k) {
+            const bool need = (have[k] & bit[k]) == 0 && bit[k];
+            pend_old[k] = need ? atomicOr(w[k], bit[k]) : ~0u;
+            pend_bit[k] = bit[k];
+        }
+    }
+    {
         int fresh = 0;
 #pragma unroll
-        for (int k = 0; k < PTS; ++k)
-            if ((have[k] & bit[k]) == 0 && bit[k]) fresh += (atomicOr(w[k], bit[k]) & bit[k]) == 0;
+        for (int k = 0; k < PTS; ++k) fresh += (pend_old[k] & pend_bit[k]) == 0 && pend_bit[k];
         fresh = __reduce_add_sync(0xffffffffu, fresh);
-        if ((threadIdx.x & 31) == 0 && fresh)
-            atomicAdd(reinterpret_cast<unsigned long long *>(counters + 64 * l + 8), (unsigned long long)fresh);
+        if ((threadIdx.x & 31) == 0 && fresh && B.n > 0)
+            atomicAdd(reinterpret_cast<unsigned long long *>(counters + 64 * (B.n - 1) + 8), (unsigned long long)fresh);
     }
 }
 
