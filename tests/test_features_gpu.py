@@ -254,3 +254,22 @@ def test_far_and_outside_queries(c_oracle):
     ref = c_oracle.process(q, cloud, edges, radii)
     out = multiscale.process_single_core(q, cloud, edges, radii)
     assert_features_close(out, ref, radii)
+
+
+def test_queries_as_prefix_of_the_search_buffer(c_oracle):
+    # the multi-GPU tile + halo hand-off: the query tensor is a view of the first rows of the search tensor.
+    # the CUDA path then orders the whole buffer once and keeps only the prefix as queries.
+    import torch
+    from nimrud_b200 import multiscale, synth
+    cloud = synth.urban_scene(90_000, seed=8)
+    dev = cloud.cuda()
+    edges, radii = (0.2, 0.4, 0.2), (0.6, 1.2, 1.0)           # shell-table kernel + interval kernel (r/e = 5)
+    for nq in (1, 31, 60_000):
+        out = multiscale.process_single_core(dev[:nq], dev, edges, radii, out_dtype=np.float32)
+        assert out.shape == (nq, 12)
+        ref = c_oracle.process(cloud.numpy()[:nq], cloud.numpy(), edges, radii, threads=8)
+        assert_features_close(out.cpu().numpy(), ref, radii)
+    # and the same rows as the full-cloud call
+    full = multiscale.process_single_core(dev, dev, edges, radii, out_dtype=np.float32)
+    part = multiscale.process_single_core(dev[:60_000], dev, edges, radii, out_dtype=np.float32)
+    assert torch.equal(full[:60_000], part)
