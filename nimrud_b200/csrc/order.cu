@@ -130,13 +130,13 @@ struct CellGrid {
     double inv_cell[3];
     int first[3];
     int dims[3];
-    int bits[3];
-    int common;                   // Z-curve levels present on all three axes
-    unsigned char pos[3][21];     // position of bit l of axis a in the cell id (upper levels)
+    int bdims[3];                 // blocks of 8 x 8 x 8 cells
 };
 
-// cells are numbered along a Z-curve (axes with fewer cells drop out of the upper levels), so that cells
-// that follow each other in the order are neighbors in space even where most cells are empty
+// cells are numbered block by block (blocks of 8 x 8 x 8 cells, row-major) and along a Z-curve inside a block:
+// cells that follow each other in the order are neighbors in space even where most cells are empty, and the
+// dense counter array is at most a few percent larger than the grid (a Z-curve over the whole grid pads every
+// axis to a power of two: 3.2x on the config-2 scene)
 __device__ __forceinline__ uint32_t cell_of(const void *xyz, int dtype, int64_t i, const CellGrid &G)
 {
     uint32_t c[3];
@@ -145,12 +145,9 @@ __device__ __forceinline__ uint32_t cell_of(const void *xyz, int dtype, int64_t 
         const double u = (load_coord(xyz, dtype, i, 3, a) - G.origin[a]) * G.inv_cell[a];
         c[a] = (uint32_t)clampi((int)floor(u) - G.first[a], 0, G.dims[a] - 1);
     }
-    const uint32_t low = (1u << G.common) - 1u;
-    uint64_t key = spread3(c[0] & low) | (spread3(c[1] & low) << 1) | (spread3(c[2] & low) << 2);
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-        for (int l = G.common; l < G.bits[a]; ++l) key |= (uint64_t)((c[a] >> l) & 1u) << G.pos[a][l];
-    return (uint32_t)key;
+    const uint32_t block = ((c[2] >> 3) * (uint32_t)G.bdims[1] + (c[1] >> 3)) * (uint32_t)G.bdims[0] + (c[0] >> 3);
+    const uint32_t z9 = (uint32_t)(spread3(c[0] & 7u) | (spread3(c[1] & 7u) << 1) | (spread3(c[2] & 7u) << 2));
+    return block * 512u + z9;
 }
 
 __global__ void __launch_bounds__(256)
@@ -182,9 +179,9 @@ int cell_order(const void *xyz, int dtype, int64_t n, const double lohi[6], cons
     if (n >= (int64_t)1 << 32) return fail(NBR_ERR_UNSUPPORTED, "cell_order: more than 2^32 points");
     CellGrid G;
     double cell[3] = {cell_in[0], cell_in[1], cell_in[2]};
-    int total_bits = -1;
+    double total = -1;
     for (int attempt = 0; attempt < 64; ++attempt) {
-        int bits = 0;
+        double cells = 512.0;
         bool ok = true;
         for (int a = 0; a < 3; ++a) {
             G.origin[a] = origin[a];
@@ -193,23 +190,14 @@ int cell_order(const void *xyz, int dtype, int64_t n, const double lohi[6], cons
             if (!(fabs(f) < 2.0e9 && fabs(l) < 2.0e9 && l - f + 1.0 <= 1048576.0)) { ok = false; break; }
             G.first[a] = (int)f;
             G.dims[a] = (int)(l - f + 1.0);
-            int b = 0;
-            while ((1 << b) < G.dims[a]) ++b;
-            G.bits[a] = b;
-            bits += b;
+            G.bdims[a] = (G.dims[a] + 7) / 8;
+            cells *= (double)G.bdims[a];
         }
-        if (ok && bits <= 26) { total_bits = bits; break; }
+        if (ok && cells <= 67108864.0) { total = cells; break; }
         for (int a = 0; a < 3; ++a) cell[a] *= 2.0;
     }
-    if (total_bits < 0) return fail(NBR_ERR_UNSUPPORTED, "cell_order: cannot cover the cloud with a cell grid");
-    G.common = std::min(G.bits[0], std::min(G.bits[1], G.bits[2]));
-    {
-        int pos = 3 * G.common;
-        for (int l = G.common; l < 21; ++l)
-            for (int a = 0; a < 3; ++a)
-                if (l < G.bits[a]) G.pos[a][l] = (unsigned char)pos++;
-    }
-    const int64_t nc = (int64_t)1 << total_bits;
+    if (total < 0) return fail(NBR_ERR_UNSUPPORTED, "cell_order: cannot cover the cloud with a cell grid");
+    const int64_t nc = (int64_t)total;
     Scratch counts, cellid, rank;
     NBR_TRY(counts.alloc(sizeof(uint32_t) * nc, stream));
     NBR_TRY(cellid.alloc(sizeof(uint32_t) * n, stream));
