@@ -109,8 +109,9 @@ int radius_features(const Lattice *lat, const void *query, int dtype, const uint
     const int ncol = (descriptor_mask & NBR_DESC_EXTENDED) ? NBR_COLS_EXTENDED : NBR_COLS_REFERENCE;
     if (algorithm != 1 && rows_supported(lat->grid.edge, radii, nr)) {
         // 7x7x7 windows go through the lean kernel, wider ones through the interval kernel
-        R3Launch r3;
+        R3Launch r3, r5;
         memset(&r3, 0, sizeof(r3));
+        memset(&r5, 0, sizeof(r5));
         std::vector<double> rr;
         std::vector<int> cc;
         for (int k = 0; k < nr; ++k) {
@@ -125,10 +126,20 @@ int radius_features(const Lattice *lat, const void *query, int dtype, const uint
                 continue;
             }
             NBR_TRY(rc);
+            if (rows5_entry(lat, radii[k], col_offset + k * ncol, r5.n ? &r5.e[r5.n - 1] : nullptr, &E, &r5.tq, stream, &rc)) {
+                r5.e[r5.n++] = E;
+                if (r5.n == R3_MAX_ENTRIES) {
+                    NBR_TRY(rows5_launch(&r5, query, dtype, perm, nq, out, out_dtype, row_stride, descriptor_mask, stream));
+                    r5.n = 0;
+                }
+                continue;
+            }
+            NBR_TRY(rc);
             rr.push_back(radii[k]);
             cc.push_back(col_offset + k * ncol);
         }
         NBR_TRY(rows3_launch(&r3, query, dtype, perm, nq, out, out_dtype, row_stride, descriptor_mask, stream));
+        NBR_TRY(rows5_launch(&r5, query, dtype, perm, nq, out, out_dtype, row_stride, descriptor_mask, stream));
         for (size_t base = 0; base < rr.size(); base += RW_MAX_RADII) {
             RowsLaunch launch;
             memset(&launch, 0, sizeof(launch));
@@ -249,8 +260,9 @@ int plan_run_sorted(const Plan *P, const void *sorted, int q_dtype, const uint32
         memset(&launch, 0, sizeof(launch));
         return r;
     };
-    R3Launch r3;
+    R3Launch r3, r5;
     memset(&r3, 0, sizeof(r3));
+    memset(&r5, 0, sizeof(r5));
     for (auto &g : P->groups) {
         std::vector<double> rr;
         std::vector<int> cc;
@@ -261,7 +273,17 @@ int plan_run_sorted(const Plan *P, const void *sorted, int q_dtype, const uint32
                 r3.e[r3.n++] = E;
                 if (r3.n == R3_MAX_ENTRIES) {
                     NBR_TRY(rows3_launch(&r3, sorted, q_dtype, perm, nq, out, out_dtype, row_stride, P->descriptor_mask, stream));
+    NBR_TRY(rows5_launch(&r5, sorted, q_dtype, perm, nq, out, out_dtype, row_stride, P->descriptor_mask, stream));
                     r3.n = 0;
+                }
+                continue;
+            }
+            NBR_TRY(rc);
+            if (rows5_entry(g.lat, P->radii[s], s * ncol, r5.n ? &r5.e[r5.n - 1] : nullptr, &E, &r5.tq, stream, &rc)) {
+                r5.e[r5.n++] = E;
+                if (r5.n == R3_MAX_ENTRIES) {
+                    NBR_TRY(rows5_launch(&r5, sorted, q_dtype, perm, nq, out, out_dtype, row_stride, P->descriptor_mask, stream));
+                    r5.n = 0;
                 }
                 continue;
             }
@@ -280,6 +302,7 @@ int plan_run_sorted(const Plan *P, const void *sorted, int q_dtype, const uint32
         }
     }
     NBR_TRY(rows3_launch(&r3, sorted, q_dtype, perm, nq, out, out_dtype, row_stride, P->descriptor_mask, stream));
+    NBR_TRY(rows5_launch(&r5, sorted, q_dtype, perm, nq, out, out_dtype, row_stride, P->descriptor_mask, stream));
     return flush();
 }
 

@@ -58,6 +58,12 @@ bool rows3_entry(const Lattice *lat, double radius, int col, const R3Entry *prev
 int rows3_launch(const R3Launch *L, const void *query, int dtype, const uint32_t *perm, int64_t nq, void *out,
                  int out_dtype, int64_t row_stride, int descriptor_mask, cudaStream_t stream);
 
+// same for 11x11x11 windows (rows5.cu): r/e + 0.5 < 6
+bool rows5_entry(const Lattice *lat, double radius, int col, const R3Entry *prev, R3Entry *E, int *tq_io,
+                 cudaStream_t stream, int *rc);
+int rows5_launch(const R3Launch *L, const void *query, int dtype, const uint32_t *perm, int64_t nq, void *out,
+                 int out_dtype, int64_t row_stride, int descriptor_mask, cudaStream_t stream);
+
 int rows_param(const Lattice *lat, const double *radii, const int *cols, int nr, RowsParam *P, cudaStream_t stream);
 int ball_table_get(double rho2, double margin, int Q, const uint4 **out, cudaStream_t stream);
 bool rows_supported(double edge, const double *radii, int nr);
