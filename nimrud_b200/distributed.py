@@ -96,7 +96,7 @@ def _select_halos_cuda(cloud, grown_boxes):
 def exchange_halo(cloud, edge_lengths, radii, group=None):
     """
     -> (halo points received from the other ranks (m,3), same dtype/device as cloud,
-        global (lo, hi) float64 tensors, own tile (lo, hi))
+        global (lo, hi) float64 CPU tensors, own tile (lo, hi))
     """
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
@@ -104,8 +104,8 @@ def exchange_halo(cloud, edge_lengths, radii, group=None):
     boxes = [torch.empty(6, dtype=torch.float64, device=cloud.device) for _ in range(world)]
     dist.all_gather(boxes, torch.cat([lo, hi]), group=group)
     all_boxes = torch.stack(boxes).cpu()                       # (world, 6): one small device->host copy
-    g_lo = all_boxes[:, :3].min(0).values.to(cloud.device)     # == all-reduce(min/max) of the tile boxes
-    g_hi = all_boxes[:, 3:].max(0).values.to(cloud.device)
+    g_lo = all_boxes[:, :3].min(0).values                      # == all-reduce(min/max) of the tile boxes (host copy)
+    g_hi = all_boxes[:, 3:].max(0).values
     h = halo_width(edge_lengths, radii)
     my_lo, my_hi = all_boxes[rank, :3], all_boxes[rank, 3:]
 
