@@ -176,6 +176,23 @@ int nbr_halo_count(const void *xyz, int dtype, int64_t n, const double *boxes_ho
 int nbr_halo_fill(const void *xyz, int dtype, int64_t n, const double *boxes_host, int32_t ndst,
                   const int64_t *offsets_host, uint64_t *cursors_dev, void *out, void *stream);
 
+/* multi-GPU tile path in three steps, so that ordering the tile can overlap the halo exchange:
+ * nbr_brick_origin: corner of brick (0,0,0) of the lattice of edge `finest_edge` anchored on the global box whose
+ *                   directory covers local_lohi_host (NULL: the global box itself);
+ * nbr_order_cloud:  perm_out[n] / sorted_out (n,3): the cloud in the spatially coherent order of the feature kernels
+ *                   (cells aligned with that origin); lohi_host = bounding box of the cloud;
+ * nbr_multiscale_features_tile: search cloud = the ordered tile (sorted_xyz, perm) + halo_xyz, queries = the tile;
+ *                   local_lohi_host must contain every point of both; out rows in the tile's ORIGINAL order. */
+int nbr_brick_origin(const double *global_lohi_host, const double *local_lohi_host, double finest_edge,
+                     double *origin_out);
+int nbr_order_cloud(const void *xyz, int dtype, int64_t n, const double *lohi_host, const double *origin_host,
+                    double finest_edge, uint32_t *perm_out, void *sorted_out, void *stream);
+int nbr_multiscale_features_tile(const void *sorted_xyz, const uint32_t *perm, int dtype, int64_t n,
+                                 const void *halo_xyz, int64_t n_halo, const double *local_lohi_host,
+                                 const double *global_lohi_host, const double *edges_host,
+                                 const double *radii_host, int32_t n_scales, void *out, int out_dtype,
+                                 int32_t descriptor_mask, int64_t *n_voxels_host, void *stream);
+
 /* counters for tests and benches: number of kernels this library has launched in this process. */
 int64_t nbr_kernel_launches(void);
 

@@ -55,6 +55,12 @@ SIGNATURES = {
     "nbr_halo_count": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, ctypes.POINTER(c_f64), c_i32, c_vp, c_vp]),
     "nbr_halo_fill": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, ctypes.POINTER(c_f64), c_i32, ctypes.POINTER(c_i64),
                                      c_vp, c_vp, c_vp]),
+    "nbr_brick_origin": (ctypes.c_int, [ctypes.POINTER(c_f64), ctypes.POINTER(c_f64), c_f64, ctypes.POINTER(c_f64)]),
+    "nbr_order_cloud": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, ctypes.POINTER(c_f64), ctypes.POINTER(c_f64), c_f64,
+                                       c_vp, c_vp, c_vp]),
+    "nbr_multiscale_features_tile": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_i64, c_vp, c_i64, ctypes.POINTER(c_f64),
+                                                    ctypes.POINTER(c_f64), ctypes.POINTER(c_f64), ctypes.POINTER(c_f64),
+                                                    c_i32, c_vp, ctypes.c_int, c_i32, ctypes.POINTER(c_i64), c_vp]),
     "nbr_multiscale_features": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_vp, ctypes.c_int, c_i64,
                                                ctypes.POINTER(c_f64), ctypes.POINTER(c_f64), c_i32, c_vp,
                                                ctypes.c_int, c_i32, ctypes.POINTER(c_f64), ctypes.POINTER(c_i64),

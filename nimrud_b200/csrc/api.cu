@@ -191,11 +191,11 @@ struct Plan {
 
 int plan_create(Plan **out, const void *search, int s_dtype, int64_t ns, const double *edges, const double *radii,
                 int n_scales, int descriptor_mask, const double *global_lohi, const double *known_local_box,
-                cudaStream_t stream)
+                cudaStream_t stream, const void *search2 = nullptr, int64_t ns2 = 0)
 {
     NBR_TRY(check_cloud_dtype(s_dtype, "multiscale_features"));
     if (n_scales < 0) return fail(NBR_ERR_INVALID, "multiscale_features: negative number of scales");
-    if (ns < 2) return fail(NBR_ERR_TOO_FEW_POINTS, "need at least 2 points to define a voxel grid");
+    if (ns + ns2 < 2) return fail(NBR_ERR_TOO_FEW_POINTS, "need at least 2 points to define a voxel grid");
     if (!search || (n_scales > 0 && (!edges || !radii))) return fail(NBR_ERR_INVALID, "multiscale_features: null argument");
     for (int s = 0; s < n_scales; ++s) {
         if (!(edges[s] > 0)) return fail(NBR_ERR_INVALID, "multiscale_features: edge lengths must be > 0");
@@ -232,7 +232,7 @@ int plan_create(Plan **out, const void *search, int s_dtype, int64_t ns, const d
             nbr_grid grids[LATTICE_BATCH];
             Lattice *made[LATTICE_BATCH] = {nullptr};
             for (int k = 0; !rc && k < nb; ++k) rc = grid_from_bbox(lohi, lohi + 3, P->groups[base + k].edge, 3, &grids[k]);
-            if (!rc) rc = lattices_create_batch(made, nb, grids, search, s_dtype, ns, stream, global_lohi ? P->local_box : nullptr);
+            if (!rc) rc = lattices_create_batch(made, nb, grids, search, s_dtype, ns, stream, global_lohi ? P->local_box : nullptr, search2, ns2);
             if (!rc) for (int k = 0; k < nb; ++k) P->groups[base + k].lat = made[k];
         }
     }
@@ -464,6 +464,46 @@ extern "C" int nbr_multiscale_features(const void *query_xyz, int q_dtype, int64
     return multiscale_features(query_xyz, q_dtype, n_query, search_xyz, s_dtype, n_search, edges_host, radii_host,
                                n_scales, out, out_dtype, descriptor_mask, global_lohi_host, n_voxels_host,
                                (cudaStream_t)stream);
+}
+
+// ---- multi-GPU tile path: the tile's points are ordered while the halo exchange is still in flight, then the
+// lattices are built from the ordered tile plus the received halo points and the tile's points are the queries
+extern "C" int nbr_brick_origin(const double *global_lohi_host, const double *local_lohi_host, double finest_edge,
+                                double *origin_out)
+{
+    if (!global_lohi_host || !origin_out) return fail(NBR_ERR_INVALID, "nbr_brick_origin: null argument");
+    return brick_origin(global_lohi_host, local_lohi_host, finest_edge, origin_out);
+}
+
+extern "C" int nbr_order_cloud(const void *xyz, int dtype, int64_t n, const double *lohi_host, const double *origin_host,
+                               double finest_edge, uint32_t *perm_out, void *sorted_out, void *stream)
+{
+    if (!xyz || !lohi_host || !origin_host || !perm_out || !sorted_out) return fail(NBR_ERR_INVALID, "nbr_order_cloud: null argument");
+    NBR_TRY(check_cloud_dtype(dtype, "nbr_order_cloud"));
+    if (!(finest_edge > 0)) return fail(NBR_ERR_INVALID, "nbr_order_cloud: edge must be > 0");
+    if (n <= 0) return NBR_OK;
+    PhaseTimer t(PHASE_ORDER, (cudaStream_t)stream);
+    const double cell[3] = {BRICK_X * finest_edge, BRICK_Y * finest_edge, BRICK_Z * finest_edge};
+    return cell_order(xyz, dtype, n, lohi_host, origin_host, cell, perm_out, sorted_out, (cudaStream_t)stream);
+}
+
+extern "C" int nbr_multiscale_features_tile(const void *sorted_xyz, const uint32_t *perm, int dtype, int64_t n,
+                                            const void *halo_xyz, int64_t n_halo, const double *local_lohi_host,
+                                            const double *global_lohi_host, const double *edges_host,
+                                            const double *radii_host, int32_t n_scales, void *out, int out_dtype,
+                                            int32_t descriptor_mask, int64_t *n_voxels_host, void *stream)
+{
+    if (!sorted_xyz || !perm || !local_lohi_host || !global_lohi_host || !out || (n_halo > 0 && !halo_xyz))
+        return fail(NBR_ERR_INVALID, "nbr_multiscale_features_tile: null argument");
+    NBR_TRY(check_cloud_dtype(dtype, "nbr_multiscale_features_tile"));
+    if (n <= 0 || n_scales <= 0) return NBR_OK;
+    Plan *P = nullptr;
+    NBR_TRY(plan_create(&P, sorted_xyz, dtype, n, edges_host, radii_host, n_scales, descriptor_mask, global_lohi_host,
+                        local_lohi_host, (cudaStream_t)stream, halo_xyz, n_halo));
+    int rc = plan_run_sorted(P, sorted_xyz, dtype, perm, n, out, out_dtype, (cudaStream_t)stream);
+    if (rc == NBR_OK && n_voxels_host) rc = plan_voxel_counts(P, n_voxels_host);
+    delete P;
+    return rc;
 }
 
 static size_t elem_size(int dtype) { return dtype == NBR_F32 ? 4 : 8; }

@@ -582,12 +582,13 @@ batch_fill_kernel(const T *__restrict__ xyz, int64_t n, const __grid_constant__ 
 }
 
 int lattices_create_batch(Lattice **out, int n_lat, const nbr_grid *grids, const void *xyz, int dtype, int64_t n,
-                          cudaStream_t stream, const double *local_lohi)
+                          cudaStream_t stream, const double *local_lohi, const void *xyz2, int64_t n2)
 {
     if (!out || !xyz || !grids || n_lat < 1 || n_lat > LATTICE_BATCH) return fail(NBR_ERR_INVALID, "lattices_create_batch: bad argument");
     if (dtype != NBR_F32 && dtype != NBR_F64) return fail(NBR_ERR_INVALID, "lattices_create_batch: bad dtype");
     if (n < 1) return fail(NBR_ERR_TOO_FEW_POINTS, "lattices_create_batch: empty search cloud");
-    if (n >= (int64_t)1 << 31) return fail(NBR_ERR_UNSUPPORTED, "lattices_create_batch: more than 2^31 search points");
+    if (n + n2 >= (int64_t)1 << 31) return fail(NBR_ERR_UNSUPPORTED, "lattices_create_batch: more than 2^31 search points");
+    if (n2 < 0 || (n2 > 0 && !xyz2)) return fail(NBR_ERR_INVALID, "lattices_create_batch: bad second point set");
     std::vector<std::unique_ptr<Lattice>> lat(n_lat);
     BatchDev B;
     memset(&B, 0, sizeof(B));
@@ -599,7 +600,7 @@ int lattices_create_batch(Lattice **out, int n_lat, const nbr_grid *grids, const
         lat[l].reset(L);
         L->stream = stream;
         L->grid = grids[l];
-        L->n_search = n;
+        L->n_search = n + n2;
         NBR_TRY(grid_to_dev(&grids[l], &L->gdev, local_lohi));
         L->nbx = (L->gdev.ncell[0] + BRICK_X - 1) / BRICK_X;
         L->nby = (L->gdev.ncell[1] + BRICK_Y - 1) / BRICK_Y;
@@ -607,7 +608,7 @@ int lattices_create_batch(Lattice **out, int n_lat, const nbr_grid *grids, const
         const double dir_entries = (double)L->nbx * L->nby * L->nbz;
         if (dir_entries > 3.0e9) return fail(NBR_ERR_UNSUPPORTED, "brick directory would exceed 12 GB; extent / edge too large");
         L->n_dir = (int64_t)L->nbx * L->nby * L->nbz;
-        L->pool_slots = std::min<int64_t>(n, L->n_dir);
+        L->pool_slots = std::min<int64_t>(n + n2, L->n_dir);
         B.g[l] = L->gdev;
         B.dir_off[l] = dir_total;
         B.nbx[l] = L->nbx;
@@ -629,16 +630,25 @@ int lattices_create_batch(Lattice **out, int n_lat, const nbr_grid *grids, const
     unsigned char *counters = reinterpret_cast<unsigned char *>(shared->counters);
     uint32_t *n_bricks_total = reinterpret_cast<uint32_t *>(counters + 64 * n_lat);
 
-    const unsigned pt_blocks = (unsigned)ceil_div(n, 256 * PTS);
-    if (dtype == NBR_F32) batch_mark_kernel<float><<<pt_blocks, 256, 0, stream>>>((const float *)xyz, n, B, dir);
-    else                  batch_mark_kernel<double><<<pt_blocks, 256, 0, stream>>>((const double *)xyz, n, B, dir);
-    NBR_LAUNCHED();
+    const void *parts[2] = {xyz, xyz2};
+    const int64_t part_n[2] = {n, n2};
+    for (int p = 0; p < 2; ++p) {
+        if (part_n[p] <= 0) continue;
+        const unsigned pt_blocks = (unsigned)ceil_div(part_n[p], 256 * PTS);
+        if (dtype == NBR_F32) batch_mark_kernel<float><<<pt_blocks, 256, 0, stream>>>((const float *)parts[p], part_n[p], B, dir);
+        else                  batch_mark_kernel<double><<<pt_blocks, 256, 0, stream>>>((const double *)parts[p], part_n[p], B, dir);
+        NBR_LAUNCHED();
+    }
     NBR_TRY(flags_to_slots(dir, dir_total, n_bricks_total, stream));
     pool_zero_kernel<<<device_sm_count() * 8, 256, 0, stream>>>(pool, n_bricks_total);
     NBR_LAUNCHED();
-    if (dtype == NBR_F32) batch_fill_kernel<float><<<pt_blocks, 256, 0, stream>>>((const float *)xyz, n, B, dir, pool, counters);
-    else                  batch_fill_kernel<double><<<pt_blocks, 256, 0, stream>>>((const double *)xyz, n, B, dir, pool, counters);
-    NBR_LAUNCHED();
+    for (int p = 0; p < 2; ++p) {
+        if (part_n[p] <= 0) continue;
+        const unsigned pt_blocks = (unsigned)ceil_div(part_n[p], 256 * PTS);
+        if (dtype == NBR_F32) batch_fill_kernel<float><<<pt_blocks, 256, 0, stream>>>((const float *)parts[p], part_n[p], B, dir, pool, counters);
+        else                  batch_fill_kernel<double><<<pt_blocks, 256, 0, stream>>>((const double *)parts[p], part_n[p], B, dir, pool, counters);
+        NBR_LAUNCHED();
+    }
     for (int l = 0; l < n_lat; ++l) {
         Lattice *L = lat[l].get();
         L->shared = shared;

@@ -93,17 +93,24 @@ def _select_halos_cuda(cloud, grown_boxes):
     return (torch.cat(parts, 0) if len(parts) != 1 else parts[0]), counts
 
 
-def exchange_halo(cloud, edge_lengths, radii, group=None):
-    """
-    -> (halo points received from the other ranks (m,3), same dtype/device as cloud,
-        global (lo, hi) float64 CPU tensors, own tile (lo, hi))
-    """
+def gather_boxes(cloud, group=None):
+    """(world, 6) float64 CPU tensor of every rank's tile box [lo, hi], and this rank's (lo, hi) device tensors."""
     world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
     lo, hi = tile_box(cloud)
     boxes = [torch.empty(6, dtype=torch.float64, device=cloud.device) for _ in range(world)]
     dist.all_gather(boxes, torch.cat([lo, hi]), group=group)
-    all_boxes = torch.stack(boxes).cpu()                       # (world, 6): one small device->host copy
+    return torch.stack(boxes).cpu(), (lo, hi)                  # one small device->host copy
+
+
+def exchange_halo(cloud, edge_lengths, radii, group=None, gathered=None):
+    """
+    -> (halo points received from the other ranks (m,3), same dtype/device as cloud,
+        global (lo, hi) float64 CPU tensors, own tile (lo, hi))
+    gathered: the result of gather_boxes(cloud, group) if the caller already has it.
+    """
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    all_boxes, (lo, hi) = gathered if gathered is not None else gather_boxes(cloud, group)
     g_lo = all_boxes[:, :3].min(0).values                      # == all-reduce(min/max) of the tile boxes (host copy)
     g_hi = all_boxes[:, 3:].max(0).values
     h = halo_width(edge_lengths, radii)
@@ -123,7 +130,7 @@ def exchange_halo(cloud, edge_lengths, radii, group=None):
         # host logic on CPU tensors (gloo tests): same inclusive selection with torch ops
         send_parts = []
         for dst in targets:
-            idx = select_halo(cloud, boxes[dst][:3], boxes[dst][3:], h)
+            idx = select_halo(cloud, all_boxes[dst, :3].to(cloud.device), all_boxes[dst, 3:].to(cloud.device), h)
             send_parts.append(cloud[idx])
             send_counts[dst] = int(idx.numel())
         send_buf = torch.cat(send_parts, 0) if send_parts else cloud[:0]
@@ -144,6 +151,70 @@ def _gpu_compute(query, search, edge_lengths, radii, bbox, out_dtype, out):
                                           global_bbox=bbox, out=out)
 
 
+_side_streams = {}
+
+
+def _side_stream(device):
+    # one persistent side stream per device: the caching allocator keeps per-stream pools, a fresh stream per
+    # call would allocate its buffers anew every time
+    key = (device.type, device.index)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
+def _process_tile_cuda(cloud, edge_lengths, radii, out, out_dtype, group):
+    """the CUDA tile path: the tile is ordered on a side stream while the halo exchange is in flight; the
+    lattices are then built from the ordered tile + the received halo points, the tile's points are the queries."""
+    import ctypes
+    from . import _lib
+    from ._util import ptr, stream_ptr
+    from .multiscale import _out_code, _TORCH_OUT
+    lib = _lib.lib()
+    code = _lib.F32 if cloud.dtype == torch.float32 else _lib.F64
+    n = int(cloud.shape[0])
+    rank = dist.get_rank(group)
+    gathered = gather_boxes(cloud, group)
+    all_boxes = gathered[0]
+    h = halo_width(edge_lengths, radii)
+    g_lo, g_hi = all_boxes[:, :3].min(0).values, all_boxes[:, 3:].max(0).values
+    # every halo point this rank can receive lies inside its own box grown by h
+    local_lo = torch.maximum(all_boxes[rank, :3] - h, g_lo)
+    local_hi = torch.minimum(all_boxes[rank, 3:] + h, g_hi)
+    f64p = ctypes.POINTER(ctypes.c_double)
+    glob = np.ascontiguousarray(torch.cat([g_lo, g_hi]).numpy(), dtype=np.float64)
+    local = np.ascontiguousarray(torch.cat([local_lo, local_hi]).numpy(), dtype=np.float64)
+    mine = np.ascontiguousarray(all_boxes[rank].numpy(), dtype=np.float64)
+    finest = float(min(edge_lengths))
+    origin = np.zeros(3, dtype=np.float64)
+    _lib.check(lib.nbr_brick_origin(glob.ctypes.data_as(f64p), local.ctypes.data_as(f64p), finest,
+                                    origin.ctypes.data_as(f64p)))
+    np_out, out_code = _out_code(out_dtype)
+    n_scales = len(radii)
+    edges_arr, edges_p = _lib.f64_array(list(edge_lengths))
+    radii_arr, radii_p = _lib.f64_array(list(radii))
+    with torch.cuda.device(cloud.device):
+        main = torch.cuda.current_stream(cloud.device)
+        side = _side_stream(cloud.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            perm = torch.empty(n, dtype=torch.int32, device=cloud.device)
+            ordered = torch.empty_like(cloud)
+            _lib.check(lib.nbr_order_cloud(ptr(cloud), code, n, mine.ctypes.data_as(f64p), origin.ctypes.data_as(f64p),
+                                           finest, ptr(perm), ptr(ordered), ctypes.c_void_p(side.cuda_stream)))
+        halo, _, _ = exchange_halo(cloud, edge_lengths, radii, group, gathered=gathered)
+        main.wait_stream(side)
+        perm.record_stream(main)
+        ordered.record_stream(main)
+        if out is None:
+            out = torch.zeros((n, 4 * n_scales), dtype=_TORCH_OUT[np_out], device=cloud.device)
+        _lib.check(lib.nbr_multiscale_features_tile(
+            ptr(ordered), ptr(perm), code, n, ptr(halo) if halo.numel() else None, int(halo.shape[0]),
+            local.ctypes.data_as(f64p), glob.ctypes.data_as(f64p), edges_p, radii_p, n_scales, ptr(out), out_code, 0,
+            None, stream_ptr(cloud.device)))
+    return out
+
+
 def process_tile(cloud, edge_lengths, radii, out=None, out_dtype=np.float32, gather=False, group=None,
                  compute=None):
     """
@@ -152,13 +223,17 @@ def process_tile(cloud, edge_lengths, radii, out=None, out_dtype=np.float32, gat
     compute(query, search, edges, radii, (lo, hi) numpy, out_dtype, out) -> features; default = CUDA path.
     """
     assert len(edge_lengths) == len(radii), "edge_lengths and radii should be equal-length sequences."
-    halo, (g_lo, g_hi), _ = exchange_halo(cloud, edge_lengths, radii, group)
-    search = torch.cat([cloud, halo], 0) if halo.numel() else cloud
-    bbox = (g_lo.cpu().numpy(), g_hi.cpu().numpy())
-    # the queries are handed over as the first rows of the search buffer: the CUDA path then orders tile + halo
-    # once, builds the lattices from the ordered copy and keeps only the tile's points as queries
-    query = search[:cloud.shape[0]]
-    feats = (compute or _gpu_compute)(query, search, edge_lengths, radii, bbox, out_dtype, out)
+    if (compute is None and cloud.is_cuda and cloud.dtype in (torch.float32, torch.float64) and cloud.is_contiguous()
+            and cloud.shape[0] >= 2):
+        feats = _process_tile_cuda(cloud, edge_lengths, radii, out, out_dtype, group)
+    else:
+        halo, (g_lo, g_hi), _ = exchange_halo(cloud, edge_lengths, radii, group)
+        search = torch.cat([cloud, halo], 0) if halo.numel() else cloud
+        bbox = (g_lo.cpu().numpy(), g_hi.cpu().numpy())
+        # the queries are handed over as the first rows of the search buffer: the CUDA path then orders tile + halo
+        # once, builds the lattices from the ordered copy and keeps only the tile's points as queries
+        query = search[:cloud.shape[0]]
+        feats = (compute or _gpu_compute)(query, search, edge_lengths, radii, bbox, out_dtype, out)
     if not gather:
         return feats
     world = dist.get_world_size(group)
