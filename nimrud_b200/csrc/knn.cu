@@ -63,9 +63,9 @@ knn_kernel(LatticeDev L, const void *__restrict__ query, int dtype, int64_t nq, 
         const float px = (float)f[0] - 0.5f, py = (float)f[1] - 0.5f, pz = (float)f[2] - 0.5f;
 
         // ---- 1. candidate ball
-        long long W = 1;
-        while ((2 * W + 1) * (2 * W + 1) < k) ++W;               // a populated plane holds k cells at about this width
-        if (W > 2) W = (W * 3) / 4;
+        // first window: the ball of radius W + 0.5 cells cuts about k cells out of a populated plane
+        long long W = (long long)ceilf(sqrtf((float)k * 0.318309886f) - 0.2f);
+        if (W < 1) W = 1;
         float lo2 = 0.0f, hi2 = INFINITY, r2 = 0.0f;
         bool ball_of_w = true;                                    // r2 is the full ball of the current window
         int n_cand = 0;
@@ -153,7 +153,10 @@ knn_kernel(LatticeDev L, const void *__restrict__ query, int dtype, int64_t nq, 
                                 KnnRec r;
                                 r.d2 = s2;
                                 r.idx = (int32_t)(rb + __popc(full & ((1u << bit) - 1u)));
-                                r.pad = 0;
+                                // cell offset from the anchor cell, 10 bits per axis (bit 31 set: too far, use the key)
+                                const int jx = x0 + bit - c[0], jy = ky - c[1], jz = kz - c[2];
+                                const bool fits = (unsigned)(jx + 512) < 1024u && (unsigned)(jy + 512) < 1024u && (unsigned)(jz + 512) < 1024u;
+                                r.pad = fits ? (jx + 512) | ((jy + 512) << 10) | ((jz + 512) << 20) : (int)0x80000000;
                                 rec[pos] = r;
                                 ++pos;
                             }
@@ -221,34 +224,58 @@ knn_kernel(LatticeDev L, const void *__restrict__ query, int dtype, int64_t nq, 
             for (int t = 0; t < 3; ++t) mine.s1[t] = 0;
 #pragma unroll
             for (int t = 0; t < 6; ++t) mine.s2[t] = 0;
+            // ks ascending: every record is read once, the sums of [ks[s-1], ks[s]) are added to running totals
+            long long run[10];
+#pragma unroll
+            for (int t = 0; t < 10; ++t) run[t] = 0;
+            int first = 0;
             for (int s = 0; s < ks.n; ++s) {
                 const int kk = ks.k[s] < have ? ks.k[s] : have;
-                long long acc[10];
+                int acc[10];
 #pragma unroll
                 for (int t = 0; t < 10; ++t) acc[t] = 0;
-                for (int p = lane; p < kk; p += 32) {
-                    // cell of the voxel from its packed address (utils/geometry.py:120-131), relative to the anchor
-                    const uint64_t key = L.ukeys[rec[p].idx];
-                    long long j[3];
-#pragma unroll
-                    for (int a = 0; a < 3; ++a) {
-                        const uint64_t mask = g.widths[a] >= 64 ? ~0ull : ((1ull << g.widths[a]) - 1);
-                        j[a] = (long long)((key >> g.shifts[a]) & mask) - g.cell_lo[a] - c[a];
-                    }
-                    const long long jx = j[0], jy = j[1], jz = j[2];
+                bool wide = false;
+                for (int p = first + lane; p < kk; p += 32) {
+                    const int pk = rec[p].pad;
+                    wide |= pk < 0;
+                    const int jx = (pk & 1023) - 512, jy = ((pk >> 10) & 1023) - 512, jz = ((pk >> 20) & 1023) - 512;
                     acc[0] += 1; acc[1] += jx; acc[2] += jy; acc[3] += jz;
                     acc[4] += jx * jx; acc[5] += jx * jy; acc[6] += jx * jz;
                     acc[7] += jy * jy; acc[8] += jy * jz; acc[9] += jz * jz;
                 }
+                if (__any_sync(0xffffffffu, wide)) {
+                    // a window wider than 511 cells: offsets from the packed addresses (utils/geometry.py:120-131), 64-bit sums
+                    long long big[10];
 #pragma unroll
-                for (int t = 0; t < 10; ++t)
+                    for (int t = 0; t < 10; ++t) big[t] = 0;
+                    for (int p = first + lane; p < kk; p += 32) {
+                        const uint64_t key = L.ukeys[rec[p].idx];
+                        long long j[3];
 #pragma unroll
-                    for (int o = 16; o; o >>= 1) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], o);
+                        for (int a = 0; a < 3; ++a) {
+                            const uint64_t mask = g.widths[a] >= 64 ? ~0ull : ((1ull << g.widths[a]) - 1);
+                            j[a] = (long long)((key >> g.shifts[a]) & mask) - g.cell_lo[a] - c[a];
+                        }
+                        big[0] += 1; big[1] += j[0]; big[2] += j[1]; big[3] += j[2];
+                        big[4] += j[0] * j[0]; big[5] += j[0] * j[1]; big[6] += j[0] * j[2];
+                        big[7] += j[1] * j[1]; big[8] += j[1] * j[2]; big[9] += j[2] * j[2];
+                    }
+#pragma unroll
+                    for (int t = 0; t < 10; ++t) {
+#pragma unroll
+                        for (int o = 16; o; o >>= 1) big[t] += __shfl_xor_sync(0xffffffffu, big[t], o);
+                        run[t] += big[t];
+                    }
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 10; ++t) run[t] += (long long)__reduce_add_sync(0xffffffffu, acc[t]);
+                }
+                first = kk > first ? kk : first;
                 if (lane == s) {
-                    mine.n = acc[0];
-                    mine.s1[0] = acc[1]; mine.s1[1] = acc[2]; mine.s1[2] = acc[3];
+                    mine.n = run[0];
+                    mine.s1[0] = run[1]; mine.s1[1] = run[2]; mine.s1[2] = run[3];
 #pragma unroll
-                    for (int t = 0; t < 6; ++t) mine.s2[t] = acc[4 + t];
+                    for (int t = 0; t < 6; ++t) mine.s2[t] = run[4 + t];
                 }
             }
             if (lane < ks.n)
@@ -273,6 +300,7 @@ int knn(const Lattice *lat, const void *query, int dtype, int64_t nq, int k, int
     kp.n = feats ? n_k : 0;
     for (int i = 0; i < kp.n; ++i) {
         if (ks[i] < 1 || ks[i] > k) return fail(NBR_ERR_INVALID, "knn: every ks[i] must be in [1, k]");
+        if (i > 0 && ks[i] <= ks[i - 1]) return fail(NBR_ERR_INVALID, "knn: ks must be ascending");
         kp.k[i] = ks[i];
     }
     const size_t smem = knn_smem();
