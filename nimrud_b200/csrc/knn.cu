@@ -103,6 +103,9 @@ knn_kernel(LatticeDev L, const void *__restrict__ query, int dtype, int64_t nq, 
                         slot = L.dir[((int64_t)gz * L.nby + gy) * L.nbx + gx];
                     }
                     uint32_t todo = __ballot_sync(0xffffffffu, slot != 0);
+                    // the line of the next non-empty brick is requested before the current one is processed
+                    uint32_t next_full = 0;
+                    if (todo) next_full = L.pool[(int64_t)__shfl_sync(0xffffffffu, slot, __ffs(todo) - 1) * BRICK_WORDS + lane];
                     while (todo) {
                         const int src = __ffs(todo) - 1;
                         todo &= todo - 1;
@@ -111,7 +114,8 @@ knn_kernel(LatticeDev L, const void *__restrict__ query, int dtype, int64_t nq, 
                         const int ky = (__shfl_sync(0xffffffffu, gy, src) << BRICK_YS) | (lane & (BRICK_Y - 1));
                         const int kz = (__shfl_sync(0xffffffffu, gz, src) << BRICK_ZS) | (lane >> BRICK_YS);
                         const int64_t wi = (int64_t)s * BRICK_WORDS + lane;
-                        const uint32_t full = L.pool[wi];               // one 128-byte line per brick
+                        const uint32_t full = next_full;                // one 128-byte line per brick
+                        if (todo) next_full = L.pool[(int64_t)__shfl_sync(0xffffffffu, slot, __ffs(todo) - 1) * BRICK_WORDS + lane];
                         uint32_t w = full;
                         if (wlo[0] > x0) w &= ~0u << (wlo[0] - x0);
                         if (whi[0] < x0 + 31) w &= ~0u >> (x0 + 31 - whi[0]);
