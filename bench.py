@@ -56,7 +56,7 @@ class ClockSampler(object):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
             return
@@ -235,7 +235,6 @@ def gpu_arm(args, rank, world, local_rank):
     launches = lib.nbr_kernel_launches() - launches0
     lib.nbr_timing_read(phases)
     lib.nbr_timing_enable(0)
-    clocks = sampler.stop() if rank == 0 else None
     if dist is not None:
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -288,6 +287,8 @@ def gpu_arm(args, rank, world, local_rank):
                "value_float32_out": results["f32"][0], "d2h_bytes_per_step_float32_out": int(results["f32"][1]),
                "steps": e2e_steps, "timer": "host wall clock around the synchronous host-buffer call"}
 
+    # the sampler covers the device-resident timed region and the e2e region (both under load)
+    clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -344,7 +345,7 @@ def gpu_arm(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--points", type=int, default=10_000_000)
