@@ -107,6 +107,8 @@ int radius_features(const Lattice *lat, const void *query, int dtype, const uint
     for (int k = 0; k < nr; ++k)
         if (!(radii[k] >= 0)) return fail(NBR_ERR_INVALID, "radius_features: radii must be >= 0");
     const int ncol = (descriptor_mask & NBR_DESC_EXTENDED) ? NBR_COLS_EXTENDED : NBR_COLS_REFERENCE;
+    NBR_TRY(ball_tables_trim());
+    NBR_TRY(ball_tables5_trim());
     if (algorithm != 1 && rows_supported(lat->grid.edge, radii, nr)) {
         // 7x7x7 windows go through the lean kernel, wider ones through the interval kernel
         R3Launch r3, r5;
@@ -251,6 +253,8 @@ int plan_run_sorted(const Plan *P, const void *sorted, int q_dtype, const uint32
     if (nq <= 0 || P->n_scales == 0) return NBR_OK;
     const int ncol = P->ncol;
     const int64_t row_stride = (int64_t)ncol * P->n_scales;
+    NBR_TRY(ball_tables_trim());
+    NBR_TRY(ball_tables5_trim());
     PhaseTimer tm(PHASE_FEATURES, stream);
     RowsLaunch launch;
     memset(&launch, 0, sizeof(launch));

@@ -89,4 +89,16 @@ int ball_table_get(double rho2, double margin, int Q, const uint4 **out, cudaStr
     return NBR_OK;
 }
 
+// called at the start of a feature call (never between building a launch description and launching it): a
+// process that keeps asking for new r/e ratios drops every table once no kernel can be reading them
+int ball_tables_trim()
+{
+    std::lock_guard<std::mutex> lock(g_table_mutex);
+    if (g_tables.size() < 128) return NBR_OK;
+    NBR_CUDA(cudaDeviceSynchronize());
+    for (auto &kv : g_tables) cudaFree(const_cast<uint4 *>(kv.second));
+    g_tables.clear();
+    return NBR_OK;
+}
+
 }  // namespace nbr

@@ -96,6 +96,16 @@ static int ball_table5_get(double rho2, double margin, int Q, const uint32_t **o
     return NBR_OK;
 }
 
+int ball_tables5_trim()
+{
+    std::lock_guard<std::mutex> lock(g_table5_mutex);
+    if (g_tables5.size() < 128) return NBR_OK;
+    NBR_CUDA(cudaDeviceSynchronize());
+    for (auto &kv : g_tables5) cudaFree(const_cast<uint32_t *>(kv.second));
+    g_tables5.clear();
+    return NBR_OK;
+}
+
 // 11-bit row -> {count | sum(pos) << 8 | sum(pos^2) << 19,  count | sum(pos) << 12}: the first word adds up a
 // whole slab (121 cells) without overflow, the second its jy-weighted sums
 __device__ __forceinline__ uint2 row11_entry(uint32_t b)

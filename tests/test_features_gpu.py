@@ -273,3 +273,19 @@ def test_queries_as_prefix_of_the_search_buffer(c_oracle):
     full = multiscale.process_single_core(dev, dev, edges, radii, out_dtype=np.float32)
     part = multiscale.process_single_core(dev[:60_000], dev, edges, radii, out_dtype=np.float32)
     assert torch.equal(full[:60_000], part)
+
+
+def test_many_distinct_radius_ratios_recycle_the_table_caches(c_oracle):
+    # every distinct r/e builds a shell table; beyond 128 cached tables the caches are dropped and rebuilt
+    from nimrud_b200 import multiscale, synth
+    cloud = synth.urban_scene(8_000, seed=12).numpy()
+    q = cloud[:1500]
+    checked = 0
+    for i in range(150):
+        r3, r5 = 0.40 + 0.002 * i, 0.80 + 0.002 * i           # r/e in [2, 3.5) and [4, 5.5) at e = 0.2
+        out = multiscale.process_single_core(q, cloud, [0.2, 0.2], [r3, r5])
+        if i % 37 == 0 or i >= 147:
+            ref = c_oracle.process(q, cloud, [0.2, 0.2], [r3, r5])
+            assert_features_close(out, ref, [r3, r5])
+            checked += 1
+    assert checked >= 7
