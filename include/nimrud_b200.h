@@ -165,6 +165,18 @@ int nbr_multiscale_features_host(const void *query_host, int q_dtype, int64_t n_
                                  void *out_host, int out_dtype, int32_t descriptor_mask,
                                  int64_t *n_voxels_host);
 
+/* vector-field multiscale operator (extension; legacy precedent V_MSO, nimrud/prototypes/mso.py:12-257).
+ * nbr_voxel_vector_means: vectors (n_search, n_components) float32 carried by the search points are averaged
+ *   per voxel of an INDEXED lattice -> voxvec_out (n_voxels, n_components) float32, rows in np.unique order.
+ * nbr_radius_vector_means: for every query the mean of the voxel vectors over the voxels within `radius`
+ *   (inclusive float64 test, as the eigenfeature path) -> out[q * out_row_stride + col_offset + f]; 0 where the
+ *   neighborhood is empty. */
+int nbr_voxel_vector_means(const nbr_lattice *lattice, const void *search_xyz, int dtype, int64_t n_search,
+                           const float *vectors, int32_t n_components, float *voxvec_out, void *stream);
+int nbr_radius_vector_means(const nbr_lattice *lattice, const void *query_xyz, int dtype, int64_t n_query,
+                            double radius, const float *voxvec, int32_t n_components, void *out, int out_dtype,
+                            int64_t out_row_stride, int32_t col_offset, void *stream);
+
 /* multi-GPU halo selection (no reference counterpart; the precedent is nested_regions,
  * nimrud/utils/geometry.py:203-253: inclusive box +- buffer radius).  boxes_host: ndst <= 8 boxes as
  * [lo x,y,z, hi x,y,z] float64, already grown by the halo width.

@@ -292,3 +292,41 @@ def knn_features(query_cloud, search_cloud, edge_length, ks, out_dtype=np.float6
     if is_torch(query_cloud):
         return feats if query_cloud.is_cuda else feats.cpu()
     return feats.cpu().numpy()
+
+
+def vector_field_features(query_cloud, search_cloud, search_vectors, edge_length, radii, out_dtype=np.float32):
+    """
+    vector-field multiscale operator (extension; legacy precedent V_MSO, nimrud/prototypes/mso.py:12-257):
+    every search point carries a feature vector (search_vectors, (Ns, F)); the vectors are averaged per voxel
+    of the search cloud's lattice at `edge_length`, and for every query and every radius the mean of the voxel
+    vectors over the voxels within the radius (inclusive, as the eigenfeature path) is returned:
+    (Nq, F * len(radii)), scale-major; zeros where a neighborhood is empty.  numpy in -> numpy out.
+    """
+    validate_cloud(query_cloud, "query_cloud")
+    if search_cloud.ndim != 2 or search_cloud.shape[1] != 3:
+        raise ValueError("only 3D search clouds can be indexed")
+    np_out, out_code = _out_code(out_dtype)
+    index = LatticeIndex(search_cloud, edge_length, indexed=True)
+    try:
+        dev = index.device
+        vec = search_vectors if is_torch(search_vectors) else torch.from_numpy(np.ascontiguousarray(search_vectors))
+        vec = vec.to(device=dev, dtype=torch.float32).reshape(search_cloud.shape[0], -1).contiguous()
+        F = int(vec.shape[1])
+        if F < 1:
+            raise ValueError("search_vectors needs at least one component")
+        q, qc = device_cloud(query_cloud, dev)
+        radii_l = [float(r) for r in radii]
+        voxvec = torch.zeros((max(index.n_voxels, 1), F), dtype=torch.float32, device=dev)
+        out = torch.zeros((q.shape[0], F * len(radii_l)), dtype=_TORCH_OUT[np_out], device=dev)
+        with torch.cuda.device(dev):
+            s = stream_ptr(dev)
+            _lib.check(_lib.lib().nbr_voxel_vector_means(index._handle, ptr(index._search), index._code,
+                                                         index._search.shape[0], ptr(vec), F, ptr(voxvec), s))
+            for k, r in enumerate(radii_l):
+                _lib.check(_lib.lib().nbr_radius_vector_means(index._handle, ptr(q), qc, q.shape[0], r, ptr(voxvec), F,
+                                                              ptr(out), out_code, out.shape[1], k * F, s))
+    finally:
+        index.close()
+    if is_torch(query_cloud):
+        return out if query_cloud.is_cuda else out.cpu()
+    return out.cpu().numpy()
