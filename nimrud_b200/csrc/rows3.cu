@@ -391,7 +391,8 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
                 const bool row_active = grp * 32 + r < nq;
                 if (row_active) {
                     const uint4 v = *reinterpret_cast<const uint4 *>(rows + r * row_bytes + cidx * 16);
-                    *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(out) + row_q * (long long)row_bytes + cidx * 16) = v;
+                    // streaming store: the rows are never read again, they should not push bricks and tables out of L2
+                    __stcs(reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(out) + row_q * (long long)row_bytes + cidx * 16), v);
                 }
             }
             __syncwarp();

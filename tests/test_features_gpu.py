@@ -289,3 +289,23 @@ def test_many_distinct_radius_ratios_recycle_the_table_caches(c_oracle):
             assert_features_close(out, ref, [r3, r5])
             checked += 1
     assert checked >= 7
+
+
+def test_table_kernels_against_the_per_candidate_kernel_at_scale():
+    # two independent code paths on 2M queries of the 10M-point scene: the shell-table kernels decide most
+    # cells by table lookup, the per-candidate kernel evaluates the reference's float64 expression for every
+    # occupied cell of the window.  populations (neighbor set sizes) must be identical, eigen ratios equal to 1e-9.
+    import torch
+    from nimrud_b200 import multiscale, synth
+    cloud = synth.urban_scene(10_000_000, seed=20, device="cuda")
+    q = cloud[::5].contiguous()
+    for e, radii in ((0.1, (0.3,)), (0.4, (1.2, 2.0)), (1.6, (4.8, 8.0))):
+        index = multiscale.LatticeIndex(cloud, e)
+        fast = index.radius_features(q, radii, out_dtype=np.float64, algorithm=0)
+        slow = index.radius_features(q, radii, out_dtype=np.float64, algorithm=1)
+        index.close()
+        assert torch.equal(fast[:, 0::4], slow[:, 0::4]), "populations differ at e = %g" % e
+        d = (fast - slow).abs()
+        for k, r in enumerate(radii):
+            assert d[:, 4 * k + 1].max().item() <= 1e-5 * r          # centroid: float32 vs float64 finish
+            assert d[:, 4 * k + 2:4 * k + 4].max().item() <= 1e-9    # same integer moments, same eigen-solver
