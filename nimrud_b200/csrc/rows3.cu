@@ -332,17 +332,20 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
                 if ((uint32_t)(U >> 32)) { ulist[n_u++] = make_uint2((uint32_t)(U >> 32), (uint32_t)jz | 256u); }
                 if (M == 0) continue;
                 // ---- moments of the slab
-                uint32_t Pk = 0, Qk = 0;
-                int R = 0;
+                // packed sums: sum e, sum jy*e, sum jy^2*e (of the last only the count field is read: it cannot be
+                // reached by carries from above).  the row's 7 bits are extracted as a byte offset into the table
+                uint32_t Pk = 0, Qk = 0, Rk = 0;
+                const unsigned long long M4 = M << 2;
+                const char *lut_bytes = reinterpret_cast<const char *>(s_lut);
 #pragma unroll
                 for (int jy = 0; jy < N7; ++jy) {
-                    const uint32_t e = s_lut[(uint32_t)(M >> (N7 * jy)) & rowmask];
+                    const uint32_t e = *reinterpret_cast<const uint32_t *>(lut_bytes + ((uint32_t)(M4 >> (N7 * jy)) & (rowmask << 2)));
                     Pk += e;
                     Qk += jy * e;
-                    R += jy * jy * (int)(e & 1023u);
+                    Rk += jy * jy * e;
                 }
                 const int C = Pk & 1023, SX = (Pk >> 10) & 1023, SXX = Pk >> 20;
-                const int SY = Qk & 1023, SXY = (Qk >> 10) & 1023;
+                const int SY = Qk & 1023, SXY = (Qk >> 10) & 1023, R = Rk & 1023;
                 An += C; Asx += SX; Asxx += SXX; Asy += SY; Asyy += R; Asxy += SXY;
                 Asz += jz * C; Aszz += jz * jz * C; Asxz += jz * SX; Asyz += jz * SY;
             }
