@@ -40,13 +40,15 @@ extern "C" {
 
 /* descriptor_mask bits for the feature kernels.  0 = the reference's 4 columns per scale
  * [population, centroid distance, l_max/sum, l_mid/sum] (minimal/features.py:21-57).
- * NBR_DESC_EXTENDED appends 12 columns per scale (extension, not in the reference):
+ * NBR_DESC_EXTENDED appends 18 columns per scale (extension, not in the reference):
  * linearity, planarity, sphericity, omnivariance, anisotropy, eigenentropy, change of curvature,
- * verticality, normal x, y, z (nz >= 0), sum of eigenvalues (covariance trace, ddof = 1). */
+ * verticality, normal x, y, z (nz >= 0), sum of eigenvalues (covariance trace, ddof = 1), and the
+ * upper triangle of the covariance xx, xy, xz, yy, yz, zz (ddof = 1; the legacy C_MSO output,
+ * nimrud/prototypes/mso.py:1735-1746). */
 #define NBR_DESC_REFERENCE 0
 #define NBR_DESC_EXTENDED 1
 #define NBR_COLS_REFERENCE 4
-#define NBR_COLS_EXTENDED 16
+#define NBR_COLS_EXTENDED 22
 
 const char *nbr_last_error(void);
 int nbr_version(void);

@@ -160,8 +160,9 @@ __device__ __forceinline__ void eig3_unit_trace(const double a[6], double l[3], 
     }
 }
 
-// the 12 extension columns (not on the reference path; kept out of line so the hot kernels stay small)
-static __device__ __noinline__ void extended_descriptors(const double l[3], double v[3], double trace, double ext[12])
+// the 18 extension columns (not on the reference path; kept out of line so the hot kernels stay small)
+static __device__ __noinline__ void extended_descriptors(const double l[3], double v[3], double trace, const double a[6],
+                                                        double ext[18])
 {
     const double e1 = fmax(l[0], 0.0), e2 = fmax(l[1], 0.0), e3 = fmax(l[2], 0.0);
     const double i1 = 1.0 / e1;
@@ -182,10 +183,12 @@ static __device__ __noinline__ void extended_descriptors(const double l[3], doub
     ext[7] = 1.0 - fabs(v[2]);             // verticality
     ext[8] = v[0]; ext[9] = v[1]; ext[10] = v[2];
     ext[11] = trace;                       // trace of the ddof=1 covariance
+#pragma unroll
+    for (int i = 0; i < 6; ++i) ext[12 + i] = a[i] * trace;     // covariance (ddof = 1): xx xy xz yy yz zz; a has unit trace
 }
 
 // the columns from: n, the centroid distance, and the UNNORMALISED matrix a = n*S2 - S1*S1^T
-// (exact integers converted to double).  writes 4 (reference) or 16 (extended) columns at out[0..]
+// (exact integers converted to double).  writes 4 (reference) or 22 (extended) columns at out[0..]
 template <typename OutT>
 __device__ __forceinline__ void emit_core(long long n_int, double centroid, double a[6], double edge, OutT *out,
                                           int descriptor_mask)
@@ -193,9 +196,9 @@ __device__ __forceinline__ void emit_core(long long n_int, double centroid, doub
     const int ncol = (descriptor_mask & NBR_DESC_EXTENDED) ? NBR_COLS_EXTENDED : NBR_COLS_REFERENCE;
     const double n = (double)n_int;
     double l0 = 0.0, l1 = 0.0;
-    double ext[12];
+    double ext[18];
 #pragma unroll
-    for (int i = 0; i < 12; ++i) ext[i] = 0.0;
+    for (int i = 0; i < 18; ++i) ext[i] = 0.0;
     if (n_int >= 2) {
         const double tr = a[0] + a[3] + a[5];
         if (tr > 0.0) {
@@ -210,7 +213,7 @@ __device__ __forceinline__ void emit_core(long long n_int, double centroid, doub
             l0 = l[0];
             l1 = l[1];
             if ((descriptor_mask & NBR_DESC_EXTENDED) && n_int >= 3)
-                extended_descriptors(l, v, tr * edge * edge / (n * (n - 1.0)), ext);
+                extended_descriptors(l, v, tr * edge * edge / (n * (n - 1.0)), a, ext);
         }
     }
     out[0] = (OutT)n;
@@ -219,7 +222,7 @@ __device__ __forceinline__ void emit_core(long long n_int, double centroid, doub
     out[3] = (OutT)l1;
     if (ncol > 4) {
 #pragma unroll
-        for (int i = 0; i < 12; ++i) out[4 + i] = (OutT)ext[i];
+        for (int i = 0; i < 18; ++i) out[4 + i] = (OutT)ext[i];
     }
 }
 

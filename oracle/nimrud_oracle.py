@@ -214,9 +214,10 @@ def extended_row(neighbors):
       omnivariance (e1 e2 e3)^(1/3), anisotropy (e1-e3)/e1,
       eigenentropy -sum e_i ln e_i, change of curvature e3,
       normal (unit eigenvector of l3, sign fixed to nz>=0), verticality 1-|nz|.
-    returns 12 numbers: the 8 scalars then nx, ny, nz, and l-sum.  zeros if undefined.
+    returns 18 numbers: the 8 scalars, nx, ny, nz, l-sum, and the upper triangle of the covariance
+    (xx xy xz yy yz zz, numpy.cov, ddof = 1).  zeros if undefined.
     """
-    out = np.zeros(12)
+    out = np.zeros(18)
     if neighbors.shape[0] < 3:
         return out
     cov = np.cov(neighbors, rowvar=False)
@@ -234,7 +235,8 @@ def extended_row(neighbors):
         if e > 0:
             ent -= e * np.log(e)
     out[:] = [(e1 - e2) / e1, (e2 - e3) / e1, e3 / e1, np.cbrt(e1 * e2 * e3), (e1 - e3) / e1,
-              ent, e3, 1.0 - abs(normal[2]), normal[0], normal[1], normal[2], total]
+              ent, e3, 1.0 - abs(normal[2]), normal[0], normal[1], normal[2], total,
+              cov[0, 0], cov[0, 1], cov[0, 2], cov[1, 1], cov[1, 2], cov[2, 2]]
     return out
 
 

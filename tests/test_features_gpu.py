@@ -157,7 +157,7 @@ def test_extended_descriptors_against_oracle():
     s = g["search"]
     e, r = float(g["edges"][1]), float(g["radii"][1])
     out = multiscale.process_single_core(q, s, [e], [r], descriptors="extended")
-    assert out.shape == (300, 16)
+    assert out.shape == (300, 22)
     assert_features_close(out[:, :4], g["features"][:300, 4:8], [r])
     p = O.grid_params(s.astype(np.float64), e)
     _, centres = O.unique_voxels(p, s.astype(np.float64))
@@ -165,6 +165,7 @@ def test_extended_descriptors_against_oracle():
     ext = O.rows_from_sets(q.astype(np.float64), centres, off, idx, row_fn=O.extended_row)
     assert np.allclose(out[:, 4:12], ext[:, :8], rtol=1e-4, atol=1e-7)
     assert np.allclose(out[:, 15], ext[:, 11], rtol=1e-6)
+    assert np.allclose(out[:, 16:22], ext[:, 12:18], rtol=1e-6, atol=1e-12 + 1e-9 * np.abs(ext[:, 11:12]))   # covariance
     # normals: compare where the smallest eigenvalue is well separated
     sep = (ext[:, 1] > 0.05)            # planarity = (e2-e3)/e1
     dots = np.abs((out[sep, 12:15] * ext[sep, 8:11]).sum(1))
