@@ -138,7 +138,7 @@ int nbr_radius_sets(const nbr_lattice *lattice, const void *query_xyz, int dtype
 
 /* k nearest voxels, total order (squared distance as float64, index).  no reference counterpart
  * (extension).  idx_out (n_query,k) int32 padded with -1, d2_out (n_query,k) f64 padded
- * with +inf; either may be NULL.  if feats_out is non-NULL also writes the 4 (or 16) feature
+ * with +inf; either may be NULL.  if feats_out is non-NULL also writes the 4 (or 22) feature
  * columns for each k in ks_host (ascending, ks[n_k-1] == k). */
 int nbr_knn(const nbr_lattice *lattice, const void *query_xyz, int dtype, int64_t n_query, int32_t k,
             int32_t *idx_out, double *d2_out, const int32_t *ks_host, int32_t n_k, void *feats_out,
