@@ -310,3 +310,17 @@ def test_table_kernels_against_the_per_candidate_kernel_at_scale():
         for k, r in enumerate(radii):
             assert d[:, 4 * k + 1].max().item() <= 1e-5 * r          # centroid: float32 vs float64 finish
             assert d[:, 4 * k + 2:4 * k + 4].max().item() <= 1e-9    # same integer moments, same eigen-solver
+
+
+def test_many_scales_in_one_call(c_oracle):
+    # 18 scales: more entries than one launch of the table kernels holds and rows wider than the row buffer
+    from nimrud_b200 import multiscale, synth
+    cloud = synth.urban_scene(30_000, seed=15).numpy()
+    q = cloud[:2500]
+    edges = [0.1] * 6 + [0.2] * 6 + [0.4] * 6
+    radii = [e * f for e, f in zip(edges, [1.0, 1.5, 2.0, 2.5, 3.0, 3.4] * 3)]
+    ref = c_oracle.process(q, cloud, edges, radii, threads=8)
+    for dt in (np.float32, np.float64):
+        out = multiscale.process_single_core(q, cloud, edges, radii, out_dtype=dt)
+        assert out.shape == (2500, 72)
+        assert_features_close(out, ref, radii)
