@@ -291,7 +291,9 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
 #pragma unroll R3_UNROLL
             for (int jz = 0; jz < N7; ++jz) {
                 const uint4 tcur = tab[jz];
-                if ((tcur.x | tcur.y | tcur.z | tcur.w) == 0) continue;   // no cell of this slab can be in the ball
+                // every skip of this loop is warp-uniform (the body synchronises the warp): no lane's cells of this slab
+                // can be in the ball
+                if (!__any_sync(0xffffffffu, (tcur.x | tcur.y | tcur.z | tcur.w) != 0)) continue;
                 const int az = za + jz;
                 const int wz = (az & (BRICK_Z - 1)) << BRICK_YS;
                 // ---- gather the slab: bits of row jy at [7*jy, 7*jy+7)
@@ -311,26 +313,30 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
                     const uint32_t s01 = iz == 0 ? slot[0][0][1] : (iz == 1 ? slot[1][0][1] : slot[2][0][1]);
                     const uint32_t s10 = iz == 0 ? slot[0][1][0] : (iz == 1 ? slot[1][1][0] : slot[2][1][0]);
                     const uint32_t s11 = iz == 0 ? slot[0][1][1] : (iz == 1 ? slot[1][1][1] : slot[2][1][1]);
-                    if ((s00 | s01 | s10 | s11) == 0) continue;
+                    if ((s00 | s01 | s10 | s11) != 0) {
 #pragma unroll
-                    for (int jy = 0; jy < N7; ++jy) {
-                        const bool up = jy >= ycross;
-                        const uint32_t sa = up ? s10 : s00, sb = up ? s11 : s01;
-                        const int word = wz | ((ya + jy) & (BRICK_Y - 1));
-                        const uint32_t w0 = sa ? E.pool[(int64_t)sa * BRICK_WORDS + word] : 0u;
-                        const uint32_t w1 = sb ? E.pool[(int64_t)sb * BRICK_WORDS + word] : 0u;
-                        slab |= (unsigned long long)(__funnelshift_r(w0, w1, sh) & rowmask) << (N7 * jy);
+                        for (int jy = 0; jy < N7; ++jy) {
+                            const bool up = jy >= ycross;
+                            const uint32_t sa = up ? s10 : s00, sb = up ? s11 : s01;
+                            const int word = wz | ((ya + jy) & (BRICK_Y - 1));
+                            const uint32_t w0 = sa ? E.pool[(int64_t)sa * BRICK_WORDS + word] : 0u;
+                            const uint32_t w1 = sb ? E.pool[(int64_t)sb * BRICK_WORDS + word] : 0u;
+                            slab |= (unsigned long long)(__funnelshift_r(w0, w1, sh) & rowmask) << (N7 * jy);
+                        }
                     }
                 }
-                if (slab == 0) continue;
+                // warp-uniform skip only: the body below is straight-line code for every lane (an empty slab adds
+                // zeros), which lets the loads of the table lookups overlap instead of ending at divergent branches
+                if (!__any_sync(0xffffffffu, slab != 0)) continue;
                 // ---- membership: sure cells + occupied cells of the uncertain shell
                 unsigned long long M = slab & ((unsigned long long)tcur.x | ((unsigned long long)tcur.y << 32));
                 const unsigned long long U = slab & ((unsigned long long)tcur.z | ((unsigned long long)tcur.w << 32));
                 // the uncertain cells are parked in the lane's table line (slots <= jz are consumed) and decided after
                 // the slab loop in ONE loop: deciding them slab by slab made every slab wait for its slowest lane
-                if ((uint32_t)U) { ulist[n_u++] = make_uint2((uint32_t)U, (uint32_t)jz); }
-                if ((uint32_t)(U >> 32)) { ulist[n_u++] = make_uint2((uint32_t)(U >> 32), (uint32_t)jz | 256u); }
-                if (M == 0) continue;
+                ulist[n_u] = make_uint2((uint32_t)U, (uint32_t)jz);                       // slot n_u <= 2 jz + 1: consumed
+                n_u += (uint32_t)U != 0;
+                ulist[n_u] = make_uint2((uint32_t)(U >> 32), (uint32_t)jz | 256u);
+                n_u += (uint32_t)(U >> 32) != 0;
                 // ---- moments of the slab
                 // packed sums: sum e, sum jy*e, sum jy^2*e (of the last only the count field is read: it cannot be
                 // reached by carries from above).  the row's 7 bits are extracted as a byte offset into the table
