@@ -1,7 +1,9 @@
-// radius_rows.cu -- the fused radius query + covariance + eigensolve + feature kernel (hot path).
+// radius_rows.cu -- the row-interval fused radius query + covariance + eigensolve + feature kernel.
+// since rows3.cu / rows5.cu (shell tables) took over every scale with r/e < 5.5 this kernel serves
+// 5.5 <= r/e < 9.5, and everything below when the table kernels are switched off (NBR_NO_ROWS3 / NBR_NO_ROWS5).
 //
 // replaces nimrud/minimal/multiscale.py:94-122 (chunk kd-tree, query_ball_tree, take, population,
-// centroid, pca) for EVERY scale of a call in one launch.
+// centroid, pca) for EVERY such scale of a call in one launch.
 //
 // the search set of a scale is a voxel LATTICE, so a ball is a stack of x-intervals, one per (y,z) row.
 //   * one warp owns 32 consecutive queries of a spatially coherent (Morton) order and walks through
@@ -66,16 +68,6 @@ __device__ __noinline__ uint32_t exact_row_mask(const GridDev &g, double qx, dou
         if (s <= r2) m |= 1u << t;
     }
     return m;
-}
-
-// one cell, the reference's float64 expression
-__device__ __noinline__ bool exact_cell_in(const GridDev &g, double qx, double qy, double qz, long long kx, long long ky,
-                                           long long kz, double radius)
-{
-    double s = sqdiff(qx, grid_centre(g, kx, 0));
-    s = __dadd_rn(s, sqdiff(qy, grid_centre(g, ky, 1)));
-    s = __dadd_rn(s, sqdiff(qz, grid_centre(g, kz, 2)));
-    return s <= __dmul_rn(radius, radius);
 }
 
 // everything a lane needs to know about one (query, lattice)
@@ -203,7 +195,7 @@ __device__ __noinline__ void lane_rows(const LatticeDev &L, const RowsParam &P, 
 //           slabs whose bricks are all empty never touch the pool.
 __device__ __forceinline__ void lane_rows_w3(const LatticeDev &L, const RowsParam &P, int ri, const LaneCtx &X,
                                              bool staged, const uint32_t *win, const int lo[3], int nb0, int nb1,
-                                             const uint32_t *s_lut10, const uint4 *tab, Acc &A)
+                                             const uint32_t *s_lut10, Acc &A)
 {
     constexpr int W = 3, N = 7;
     const GridDev &g = L.g;
@@ -235,15 +227,10 @@ __device__ __forceinline__ void lane_rows_w3(const LatticeDev &L, const RowsPara
                     slot[iz][iy][ix] = ok ? L.dir[((int64_t)gz * L.nby + gy) * L.nbx + gx] : 0u;
                 }
     }
-    uint4 tnext = tab ? tab[0] : make_uint4(0, 0, 0, 0);
     for (int jz = 0; jz < N; ++jz) {
         const float dz = X.fzm - (float)jz;
         const float Tz = rho2 - dz * dz;
-        const uint4 tcur = tnext;
-        if (tab) {
-            tnext = tab[jz + 1];                                   // slab 7 is padding
-            if ((tcur.x | tcur.y | tcur.z | tcur.w) == 0) continue;   // no cell of this slab can be in the ball
-        } else if (Tz < t_min) continue;
+        if (Tz < t_min) continue;
         const int az = za + jz;
         const int wz = (az & (BRICK_Z - 1)) << BRICK_YS;
         // ---- gather the slab: bits of row jy at [7*jy, 7*jy+7)
@@ -275,48 +262,9 @@ __device__ __forceinline__ void lane_rows_w3(const LatticeDev &L, const RowsPara
             }
         }
         if (slab == 0) continue;
+        // ---- rolled walk over the rows
         uint32_t Pk = 0, Qk = 0;
         int R = 0;
-        if (tab) {
-            // ---- shell table: cells that are inside for the whole bin of f, plus the occupied cells of the
-            // uncertain shell, each decided by the reference's float64 expression
-            unsigned long long M = slab & ((unsigned long long)tcur.x | ((unsigned long long)tcur.y << 32));
-            unsigned long long U = slab & ((unsigned long long)tcur.z | ((unsigned long long)tcur.w << 32));
-            if (U) {
-                // float32 first: |d^2 - rho^2| > band decides; inside the band the reference's float64 expression does
-                const float dzf = X.fzm - (float)jz;
-                const float dz2f = dzf * dzf;
-                uint32_t ulo = (uint32_t)U, uhi = (uint32_t)(U >> 32);
-                uint32_t alo = 0, ahi = 0;
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t u = half ? uhi : ulo, acc = 0;
-                    while (u) {
-                        const int b = __ffs(u) - 1;
-                        u &= u - 1;
-                        const int i = b + 32 * half;
-                        const int jy = (i * 37) >> 8, t = i - 7 * jy;
-                        const float dx = X.fxm - (float)t, dy = X.fym - (float)jy;
-                        const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz2f));
-                        bool in = d2 < rho2;
-                        if (fabsf(d2 - rho2) < 4.0e-5f)
-                            in = exact_cell_in(g, X.q[0], X.q[1], X.q[2], (long long)xa + t, (long long)ya + jy, az, P.r[ri]);
-                        acc |= in ? 1u << b : 0u;
-                    }
-                    if (half) ahi = acc; else alo = acc;
-                }
-                M |= (unsigned long long)alo | ((unsigned long long)ahi << 32);
-            }
-            if (M == 0) continue;
-#pragma unroll
-            for (int jy = 0; jy < N; ++jy) {
-                const uint32_t e = s_lut10[(uint32_t)(M >> (N * jy)) & rowmask];
-                Pk += e;
-                Qk += jy * e;
-                R += jy * jy * (int)(e & 1023u);
-            }
-        } else
-        // ---- rolled walk over the rows
 #pragma unroll 1
         for (int jy = 0; jy < N; ++jy) {
             const uint32_t bits = (uint32_t)(slab >> (N * jy)) & rowmask;
@@ -399,13 +347,6 @@ radius_rows_kernel(const RowsLaunch *__restrict__ launch, const void *__restrict
             X.fxm = (float)f[0] - 0.5f + (float)W;
             X.fym = (float)f[1] - 0.5f + (float)W;
             X.fzm = (float)f[2] - 0.5f + (float)W;
-            // bin of f for the shell tables
-            const int tq = P.tq;
-            const int tbin = (min((int)(f[2] * tq), tq - 1) * tq + min((int)(f[1] * tq), tq - 1)) * tq +
-                             min((int)(f[0] * tq), tq - 1);
-            // the bin's 128-byte line is needed after the staging wait: pull it into L1 now
-            for (int ri = 0; ri < P.n; ++ri)
-                if (P.table[ri]) asm volatile("prefetch.global.L1 [%0];" ::"l"(P.table[ri] + (size_t)tbin * 8));
 
             // ---- brick window of the whole warp
             int lo[3], nb[3];
@@ -425,7 +366,6 @@ radius_rows_kernel(const RowsLaunch *__restrict__ launch, const void *__restrict
                 unsigned long long *st = launch->stats + li * 8;
                 atomicAdd(st + (staged ? 0 : 1), 1ull);
                 if (staged) atomicAdd(st + 2, (unsigned long long)vol);
-                else atomicAdd(st + (vol <= 64 ? 3 : vol <= 96 ? 4 : vol <= 128 ? 5 : vol <= 256 ? 6 : 7), 1ull);
             }
 
             if (staged) {
@@ -459,8 +399,7 @@ radius_rows_kernel(const RowsLaunch *__restrict__ launch, const void *__restrict
 
             for (int ri = 0; ri < P.n; ++ri) {
                 Acc A = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-                if (W == 3)      lane_rows_w3(L, P, ri, X, staged, win, lo, nb[0], nb[1], s_lut10,
-                                                  P.table[ri] ? P.table[ri] + (size_t)tbin * 8 : nullptr, A);
+                if (W == 3)      lane_rows_w3(L, P, ri, X, staged, win, lo, nb[0], nb[1], s_lut10, A);
                 else if (staged) lane_rows<true>(L, P, ri, X, win, lo, nb[0], nb[1], s_lut, A);
                 else             lane_rows<false>(L, P, ri, X, win, lo, nb[0], nb[1], s_lut, A);
                 if (active)
@@ -472,7 +411,7 @@ radius_rows_kernel(const RowsLaunch *__restrict__ launch, const void *__restrict
     }
 }
 
-int rows_param(const Lattice *lat, const double *radii, const int *cols, int nr, RowsParam *P, cudaStream_t stream)
+int rows_param(const Lattice *lat, const double *radii, const int *cols, int nr, RowsParam *P, cudaStream_t)
 {
     const double e = lat->grid.edge;
     if (nr > RW_MAX_RADII) return fail(NBR_ERR_INVALID, "rows_param: too many radii in one group");
@@ -493,22 +432,6 @@ int rows_param(const Lattice *lat, const double *radii, const int *cols, int nr,
         P->t_min[k] = (float)(-16.0 * 5.96e-8 * mag);
     }
     P->eps_b = (float)(4.77e-7 * (weff + 1.0));
-    // shell tables for W = 3 windows.  margin (squared distance, cell units): the reference expression and the
-    // kernel's f are each off by a few ulp of the largest coordinate magnitude, scaled by 2*(W+1) cells
-    static const bool no_table = getenv("NBR_NO_BALL_TABLE") != nullptr;
-    static const int q_env = getenv("NBR_BALL_Q") ? atoi(getenv("NBR_BALL_Q")) : 0;
-    P->tq = q_env >= 1 && q_env <= 64 ? q_env : 16;
-    for (int k = 0; k < nr; ++k) P->table[k] = nullptr;
-    if (weff == 3 && !no_table) {
-        double maxabs = 0.0;
-        for (int a = 0; a < 3; ++a)
-            maxabs = std::max(maxabs, std::max(fabs(lat->grid.min_corner[a]), fabs(lat->grid.max_corner[a])));
-        const double margin = std::max(1e-11, 64.0 * 2.3e-16 * (maxabs / e + 8.0));
-        for (int k = 0; k < nr; ++k) {
-            const double rho = radii[k] / e;
-            NBR_TRY(ball_table_get(rho * rho, margin, P->tq, &P->table[k], stream));
-        }
-    }
     return NBR_OK;
 }
 
@@ -552,9 +475,6 @@ int radius_rows_launch(const RowsLaunch *launch_host, const void *query, int dty
             fprintf(stderr, "[nbr row stats] lattice %d edge %.3g W %d: staged warps %llu (avg %.1f bricks), direct warps %llu\n",
                     l, launch_host->lat[l].g.edge, launch_host->rows[l].wmax, h[l * 8], h[l * 8] ? (double)h[l * 8 + 2] / h[l * 8] : 0.0,
                     h[l * 8 + 1]);
-        for (int l = 0; l < launch_host->n_lat; ++l)
-            fprintf(stderr, "[nbr row stats] lattice %d direct warps by window bricks: <=64 %llu, <=96 %llu, <=128 %llu, <=256 %llu, more %llu\n",
-                    l, h[l * 8 + 3], h[l * 8 + 4], h[l * 8 + 5], h[l * 8 + 6], h[l * 8 + 7]);
     }
     return NBR_OK;
 }

@@ -18,11 +18,10 @@ struct RowsParam {
     float t_min[RW_MAX_RADII];   // rows with T < t_min are certainly empty
     int w[RW_MAX_RADII];         // window half-width of each radius
     int col[RW_MAX_RADII];       // first output column of each radius
-    const uint4 *table[RW_MAX_RADII];   // shell table of each radius (ball_table.cu), or NULL: interval walk
     float eps_b;
     int n;
     int wmax;
-    int tq;                      // bins per axis of the shell tables
+    int pad;
 };
 
 struct RowsLaunch {
