@@ -277,7 +277,6 @@ int plan_run_sorted(const Plan *P, const void *sorted, int q_dtype, const uint32
                 r3.e[r3.n++] = E;
                 if (r3.n == R3_MAX_ENTRIES) {
                     NBR_TRY(rows3_launch(&r3, sorted, q_dtype, perm, nq, out, out_dtype, row_stride, P->descriptor_mask, stream));
-    NBR_TRY(rows5_launch(&r5, sorted, q_dtype, perm, nq, out, out_dtype, row_stride, P->descriptor_mask, stream));
                     r3.n = 0;
                 }
                 continue;

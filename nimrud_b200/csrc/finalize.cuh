@@ -21,6 +21,22 @@ struct Moments {
 };
 
 #ifdef __CUDACC__
+// single-instruction reciprocal / square root (MUFU, ~1 ulp, denormals flushed).  1.0f / x, sqrtf and
+// __frcp_rn all carry a correctly-rounded slow path (~15 instructions and a call each); every use below
+// either feeds a float32 guess that is refined in float64 or a column with a 1e-4 tolerance.
+__device__ __forceinline__ float rcp_fast(float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sqrt_fast(float x)
+{
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // eigenvalues (descending) of a symmetric positive semi-definite 3x3 with unit trace, and the unit
 // eigenvector of the smallest one.
 //
@@ -41,21 +57,25 @@ __device__ __forceinline__ void sym_mul(const double a[6], const double x[3], do
 // float64 closed form (trigonometric); only used when the matrix is (nearly) a multiple of the
 // identity, where the three eigenvalues are within ~1e-3 of each other and half-precision loss on a
 // double root is harmless.
-static __device__ __noinline__ void eig3_near_isotropic(const double a[6], double l[3])
+// arguments and result by value: a pointer to the caller's arrays would pin them in local memory on the hot path too.
+struct Eig3 { double l0, l1, l2; };
+static __device__ __noinline__ Eig3 eig3_near_isotropic(double a0, double a1, double a2, double a3, double a4, double a5)
 {
     const double q = 1.0 / 3.0;
-    const double p1 = a[1] * a[1] + a[2] * a[2] + a[4] * a[4];
-    const double d0 = a[0] - q, d1 = a[3] - q, d2 = a[5] - q;
+    Eig3 out = {q, q, q};
+    const double p1 = a1 * a1 + a2 * a2 + a4 * a4;
+    const double d0 = a0 - q, d1 = a3 - q, d2 = a5 - q;
     const double p2 = d0 * d0 + d1 * d1 + d2 * d2 + 2.0 * p1;
-    if (!(p2 > 1e-28)) { l[0] = l[1] = l[2] = q; return; }
+    if (!(p2 > 1e-28)) return out;
     const double p = sqrt(p2 / 6.0);
     const double ip = 1.0 / p;
-    const double b0 = d0 * ip, b1 = a[1] * ip, b2 = a[2] * ip, b3 = d1 * ip, b4 = a[4] * ip, b5 = d2 * ip;
+    const double b0 = d0 * ip, b1 = a1 * ip, b2 = a2 * ip, b3 = d1 * ip, b4 = a4 * ip, b5 = d2 * ip;
     double r = 0.5 * (b0 * (b3 * b5 - b4 * b4) - b1 * (b1 * b5 - b4 * b2) + b2 * (b1 * b4 - b3 * b2));
     r = fmin(1.0, fmax(-1.0, r));
     const double phi = acos(r) * (1.0 / 3.0);
     const double e0 = q + 2.0 * p * cos(phi), e2 = q + 2.0 * p * cos(phi + 2.0943951023931954923);
-    l[0] = e0; l[2] = e2; l[1] = 1.0 - e0 - e2;
+    out.l0 = e0; out.l2 = e2; out.l1 = 1.0 - e0 - e2;
+    return out;
 }
 
 template <bool WANT_NORMAL>
@@ -68,9 +88,10 @@ __device__ __forceinline__ void eig3_unit_trace(const double a[6], double l[3], 
                 f5 = (float)a[5];
     const float g0 = f0 - qf, g1 = f3 - qf, g2 = f5 - qf;
     const float p2 = g0 * g0 + g1 * g1 + g2 * g2 + 2.0f * (f1 * f1 + f2 * f2 + f4 * f4);
-    if (!(p2 > 1e-7f)) { eig3_near_isotropic(a, l); return; }
-    const float p = sqrtf(p2 * (1.0f / 6.0f));
-    const float ip = 1.0f / p;
+    if (!(p2 > 1e-7f)) { const Eig3 e = eig3_near_isotropic(a[0], a[1], a[2], a[3], a[4], a[5]); l[0] = e.l0; l[1] = e.l1; l[2] = e.l2; return; }
+    const float p26 = p2 * (1.0f / 6.0f);
+    const float ip = rsqrtf(p26);
+    const float p = p26 * ip;
     const float b0 = g0 * ip, b1 = f1 * ip, b2 = f2 * ip, b3 = g1 * ip, b4 = f4 * ip, b5 = g2 * ip;
     float r = 0.5f * (b0 * (b3 * b5 - b4 * b4) - b1 * (b1 * b5 - b4 * b2) + b2 * (b1 * b4 - b3 * b2));
     r = fminf(1.0f, fmaxf(-1.0f, r));
@@ -88,7 +109,7 @@ __device__ __forceinline__ void eig3_unit_trace(const double a[6], double l[3], 
     float vx = c0x, vy = c0y, vz = c0z, nn = n0;
     if (n1 > nn) { nn = n1; vx = c1x; vy = c1y; vz = c1z; }
     if (n2 > nn) { nn = n2; vx = c2x; vy = c2y; vz = c2z; }
-    if (!(nn > 1e-30f)) { eig3_near_isotropic(a, l); return; }
+    if (!(nn > 1e-30f)) { const Eig3 e = eig3_near_isotropic(a[0], a[1], a[2], a[3], a[4], a[5]); l[0] = e.l0; l[1] = e.l1; l[2] = e.l2; return; }
     const float invf = rsqrtf(nn);
 
     // ---- float64: exact deflation around that (approximate) eigenvector.  an error d in v only
@@ -114,7 +135,7 @@ __device__ __forceinline__ void eig3_unit_trace(const double a[6], double l[3], 
     u2[0] = v[1] * u1[2] - v[2] * u1[1];
     u2[1] = v[2] * u1[0] - v[0] * u1[2];
     u2[2] = v[0] * u1[1] - v[1] * u1[0];
-    double in1 = (double)__frcp_rn((float)nu);                      // nu = |u1|^2 >= 2/3 s
+    double in1 = (double)rcp_fast((float)nu);                        // nu = |u1|^2 >= 2/3 s
     in1 = in1 * (2.0 - nu * in1);
     double au1[3], au2[3];
     sym_mul(a, u1, au1);
@@ -203,7 +224,7 @@ __device__ __forceinline__ void emit_core(long long n_int, double centroid, doub
         const double tr = a[0] + a[3] + a[5];
         if (tr > 0.0) {
             // 1/tr: float32 seed + one Newton step (relative error ~1e-14)
-            const double r0 = (double)__frcp_rn((float)tr);
+            const double r0 = (double)rcp_fast((float)tr);
             const double it = r0 * (2.0 - tr * r0);
 #pragma unroll
             for (int i = 0; i < 6; ++i) a[i] *= it;
@@ -259,9 +280,9 @@ __device__ __forceinline__ void emit_features_window(int n, int sx, int sy, int 
 {
     double centroid = 0.0;
     if (n > 0) {
-        const float inv = 1.0f / (float)n;
+        const float inv = rcp_fast((float)n);
         const float dx = fxm - (float)sx * inv, dy = fym - (float)sy * inv, dz = fzm - (float)sz * inv;
-        centroid = (double)sqrtf(dx * dx + dy * dy + dz * dz) * edge;
+        centroid = (double)sqrt_fast(dx * dx + dy * dy + dz * dz) * edge;
     }
     double a[6];
     if (SMALL) {
@@ -281,10 +302,10 @@ __device__ __forceinline__ void query_anchor(double q, const GridDev &g, int a, 
 {
     // the anchor only positions the window, so a reciprocal multiply is as good as the division
     const double u = (q - g.minc[a]) * g.inv_edge;
-    double cf = floor(u);
+    const double cf = floor(u);
     f = u - cf;
-    cf = fmin(fmax(cf - (double)g.cell_lo[a], -1.0e9), 1.0e9);     // local cell coordinate
-    c = (int)cf;
+    // local cell coordinate: saturating conversion + integer clamp
+    c = max(min(__double2int_rn(cf - (double)g.cell_lo[a]), 1000000000), -1000000000);
 }
 #endif
 

@@ -4,9 +4,12 @@
 // launch: neighbor search, take, population, centroid, pca) but only the common case, so that the code
 // is small enough for the instruction cache and light enough on registers for 20+ warps per SM:
 //   * launch description in kernel parameters (constant bank), one entry per (lattice, radius);
-//   * the warp's brick window is staged by TMA bulk copies (cp.async.bulk, one 128-byte brick per
-//     copy, completion on an mbarrier); warps whose window does not fit read their rows from global
-//     memory through the directory;
+//   * the warp's brick window is staged into shared memory by 16-byte asynchronous copies (LDGSTS, 8 lanes
+//     per 128-byte brick); warps whose window does not fit read their rows from global memory through the
+//     directory.  measured and dropped: 128-byte TMA bulk copies on an mbarrier (69M tiny copies per step are
+//     bound by the small-copy rate: 5.90 vs 5.79 ms), and a row-major window layout whose scattered LDGSTS
+//     destinations (one 32-byte piece per z of a brick) congest the return path of every global load
+//     (long-scoreboard stalls x4: 6.3 vs 4.4 ms, profiles/r01_rows3_ncu_summary.md);
 //   * membership comes from the shell tables (ball_table.cu): cells inside for the whole bin of the
 //     query's fractional position are a mask, occupied cells of the uncertain shell are tested in
 //     float32 and, inside the rounding band, with the reference's float64 expression -- neighbor sets
@@ -28,8 +31,8 @@ namespace nbr {
 #ifndef R3_CAP_N
 #define R3_CAP_N 48
 #endif
-#ifndef R3_STAGE_TMA
-#define R3_STAGE_TMA 0              // 1: stage with TMA bulk copies + mbarrier instead of 16-byte cp.async
+#ifndef R3_W1_ALWAYS
+#define R3_W1_ALWAYS 1
 #endif
 #ifndef R3_UNROLL_N
 #define R3_UNROLL_N 1
@@ -41,7 +44,7 @@ constexpr int R3_WARPS = R3_WARPS_N;
 constexpr int R3_UNROLL = R3_UNROLL_N;   // slabs per trip of the slab loop
 constexpr int R3_CAP = R3_CAP_N;          // staged bricks per warp (128 bytes each)
 constexpr int N7 = 7, W3 = 3;
-constexpr int R3_TAB_STRIDE = R3_STAGE_TMA ? 36 : 28;   // words per lane: 7 slabs x 16 bytes (TMA: a whole 128-byte line + padding); both conflict-free for LDS.128
+constexpr int R3_TAB_STRIDE = 28;        // words per lane: 7 slabs x 16 bytes; conflict-free for LDS.128
 constexpr int R3_WIN_BYTES = R3_CAP * BRICK_WORDS * 4;
 constexpr int R3_TAB_BYTES = 32 * R3_TAB_STRIDE * 4;
 constexpr int R3_MAX_ROW_BYTES = 256;   // output rows up to this size are assembled in shared memory
@@ -55,34 +58,18 @@ __device__ __forceinline__ uint32_t row7_entry(uint32_t b)
     return cnt | (s1 << 10) | (s2 << 20);
 }
 
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    uint32_t done;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done)
-                     : "r"(bar), "r"(parity)
-                     : "memory");
-    } while (!done);
-}
-
 __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *gptr)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+
+// slot of brick (gx, gy, gz); 0 (the all-zero brick) outside the directory.  directories hold < 2^32 entries
+// (lattice_create refuses larger ones), so the index arithmetic is 32-bit
+__device__ __forceinline__ uint32_t dir_slot(const R3Entry &E, int gx, int gy, int gz, bool wanted = true)
+{
+    const bool ok = wanted && (uint32_t)gx < (uint32_t)E.nbx && (uint32_t)gy < (uint32_t)E.nby && (uint32_t)gz < (uint32_t)E.nbz;
+    const uint32_t idx = ((uint32_t)gz * (uint32_t)E.nby + (uint32_t)gy) * (uint32_t)E.nbx + (uint32_t)gx;
+    return ok ? E.dir[idx] : 0u;
 }
 
 __device__ __forceinline__ double r3_centre(const R3Entry &E, long long k, int a)
@@ -107,25 +94,20 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
     // dynamic shared memory, per warp: brick window | table lines | output rows (when the launch owns whole rows)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint32_t s_lut[128];
-    __shared__ __align__(8) unsigned long long s_bar[R3_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < 128; i += blockDim.x) s_lut[i] = row7_entry(i);
     const int row_bytes = stage_rows ? (int)row_stride * (int)sizeof(OutT) : 0;
     unsigned char *warp_base = smem_raw + (size_t)warp * (R3_WIN_BYTES + R3_TAB_BYTES + 32 * row_bytes);
     const uint32_t *win = reinterpret_cast<const uint32_t *>(warp_base);
     const uint32_t win_addr = (uint32_t)__cvta_generic_to_shared(win);
-    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[warp]);
     const uint4 *tab = reinterpret_cast<const uint4 *>(warp_base + R3_WIN_BYTES + lane * R3_TAB_STRIDE * 4);
     const uint32_t tab_addr = (uint32_t)__cvta_generic_to_shared(tab);
     unsigned char *rows = warp_base + R3_WIN_BYTES + R3_TAB_BYTES;       // [32][row_bytes]
-    if (lane == 0) {
-        mbar_init(bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
     __syncthreads();
-#if R3_STAGE_TMA
-    uint32_t parity = 0;
-#endif
+    // row buffer -> global: 16-byte pieces per row, and where lane's first piece sits
+    const int cpr = max(row_bytes >> 4, 1);
+    const int r_step = 32 / cpr, c_step = 32 - r_step * cpr;
+    const int r_first = lane / cpr, c_first = lane - r_first * cpr;
     const int64_t n_groups = (nq + 31) >> 5;
     constexpr uint32_t rowmask = 127u;
 
@@ -157,10 +139,11 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
 #pragma unroll
                 for (int a = 0; a < 3; ++a) {
                     const double u = (q[a] - E.minc[a]) * E.inv_edge;
-                    double cf = floor(u);
+                    const double cf = floor(u);
                     f[a] = u - cf;
-                    cf = fmin(fmax(cf - (double)E.cell_lo[a], -1.0e9), 1.0e9);
-                    c[a] = (int)cf;
+                    // local cell coordinate: the conversion saturates, the integer clamp keeps the window arithmetic
+                    // of far-away queries inside int32 (float64 min/max cost 16 instructions per axis)
+                    c[a] = max(min(__double2int_rn(cf - (double)E.cell_lo[a]), 1000000000), -1000000000);
                 }
                 c0 = c[0]; c1 = c[1]; c2 = c[2];
                 fxm = (float)f[0] + 2.5f; fym = (float)f[1] + 2.5f; fzm = (float)f[2] + 2.5f;
@@ -182,50 +165,27 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
                 // brick (ix,iy,iz) -> win[((iz*nb1)+iy)*nb0+ix][32]; empty and out-of-range bricks copy slot 0 (zeros)
                 const int total = staged ? nb0 * nb1 * (int)n2 : 0;
                 __syncwarp();                                      // every lane is done reading the previous window / lines
-#if R3_STAGE_TMA
-                // TMA bulk copies (one 128-byte copy per line / brick) completing on the warp's mbarrier
-                if (lane == 0) mbar_expect_tx(bar, (uint32_t)(total + 32) * 128u);
-                __syncwarp();
-                bulk_g2s(tab_addr, E.table + (size_t)tbin * 8, 128u, bar);
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    const int b = lane + 32 * t;
-                    if (b < total) {
-                        const int ix = b % nb0, iy = (b / nb0) % nb1, iz = b / (nb0 * nb1);
-                        const int gx = lo0 + ix, gy = lo1 + iy, gz = lo2 + iz;
-                        uint32_t s = 0;
-                        if (gx >= 0 && gx < E.nbx && gy >= 0 && gy < E.nby && gz >= 0 && gz < E.nbz)
-                            s = E.dir[((int64_t)gz * E.nby + gy) * E.nbx + gx];
-                        bulk_g2s(win_addr + (uint32_t)b * 128u, E.pool + (int64_t)s * BRICK_WORDS, 128u, bar);
-                    }
-                }
-#else
                 // 16-byte asynchronous copies (LDGSTS): 7 per lane for its table line, then 4 bricks per step
                 // (8 lanes x 16 bytes per brick).  measured: ~5x the small-copy throughput of the TMA path
                 {
                     const char *line = reinterpret_cast<const char *>(E.table + (size_t)tbin * 8);
 #pragma unroll
-#ifdef R3_ABL_TABLE1
-                    for (int j = 0; j < N7; ++j) cp_async16(tab_addr + 16u * j, line + 16 * 3);
-#else
                     for (int j = 0; j < N7; ++j) cp_async16(tab_addr + 16u * j, line + 16 * j);
-#endif
                 }
                 if (total) {
-                    const float inv0 = __frcp_rn((float)nb0), inv01 = __frcp_rn((float)(nb0 * nb1));
+                    const float inv0 = rcp_fast((float)nb0), inv01 = rcp_fast((float)(nb0 * nb1));
                     uint32_t slot0 = 0, slot1 = 0;
 #pragma unroll
                     for (int t = 0; t < 2; ++t) {
                         const int b = lane + 32 * t;
                         uint32_t sl = 0;
                         if (b < total) {
-                            // b < 64 and nb0 * nb1 <= 48: the float quotients are exact after truncation
+                            // b < 64 and nb0 * nb1 <= 48: (b + 0.5) / n is at least 0.01 away from an integer, so the float
+                            // quotients (1-ulp reciprocal) are exact after truncation
                             const int iz = (int)(((float)b + 0.5f) * inv01);
                             const int rem = b - iz * nb0 * nb1;
                             const int iy = (int)(((float)rem + 0.5f) * inv0), ix = rem - iy * nb0;
-                            const int gx = lo0 + ix, gy = lo1 + iy, gz = lo2 + iz;
-                            if (gx >= 0 && gx < E.nbx && gy >= 0 && gy < E.nby && gz >= 0 && gz < E.nbz)
-                                sl = E.dir[((int64_t)gz * E.nby + gy) * E.nbx + gx];
+                            sl = dir_slot(E, lo0 + ix, lo1 + iy, lo2 + iz);
                         }
                         if (t == 0) slot0 = sl; else slot1 = sl;
                     }
@@ -235,22 +195,15 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
                         const uint32_t sl = __shfl_sync(0xffffffffu, b < 32 ? slot0 : slot1, b & 31);
                         if (b < total)
                             cp_async16(win_addr + (uint32_t)(b * BRICK_WORDS + chunk * 4) * 4u,
-                                       E.pool + (int64_t)sl * BRICK_WORDS + chunk * 4);
+                                       E.pool + (size_t)sl * BRICK_WORDS + chunk * 4);
                     }
                 }
-#endif
             } else {
                 // same lattice, another radius: only the table lines change
                 __syncwarp();
-#if R3_STAGE_TMA
-                if (lane == 0) mbar_expect_tx(bar, 32u * 128u);
-                __syncwarp();
-                bulk_g2s(tab_addr, E.table + (size_t)tbin * 8, 128u, bar);
-#else
                 const char *line = reinterpret_cast<const char *>(E.table + (size_t)tbin * 8);
 #pragma unroll
                 for (int j = 0; j < N7; ++j) cp_async16(tab_addr + 16u * j, line + 16 * j);
-#endif
             }
 
             // ---- per lane: 7 slabs of 7 rows of 7 bits
@@ -271,20 +224,11 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
 #pragma unroll
                     for (int iy = 0; iy < 2; ++iy)
 #pragma unroll
-                        for (int ix = 0; ix < 2; ++ix) {
-                            const int gx = bx0 + ix, gy = by0 + iy, gz = bz0 + iz;
-                            const bool ok = (ix == 0 || two) && gx >= 0 && gx < E.nbx && gy >= 0 && gy < E.nby &&
-                                            gz >= 0 && gz < E.nbz;
-                            slot[iz][iy][ix] = ok ? E.dir[((int64_t)gz * E.nby + gy) * E.nbx + gx] : 0u;
-                        }
+                        for (int ix = 0; ix < 2; ++ix)
+                            slot[iz][iy][ix] = dir_slot(E, bx0 + ix, by0 + iy, bz0 + iz, ix == 0 || two);
             }
-#if R3_STAGE_TMA
-            mbar_wait(bar, parity);
-            parity ^= 1u;
-#else
             asm volatile("cp.async.wait_all;" ::: "memory");
             __syncwarp();
-#endif
             int An = 0, Asx = 0, Asy = 0, Asz = 0, Asxx = 0, Asxy = 0, Asxz = 0, Asyy = 0, Asyz = 0, Aszz = 0;
             uint2 *ulist = reinterpret_cast<uint2 *>(const_cast<uint4 *>(tab));
             int n_u = 0;
@@ -304,7 +248,11 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
                     for (int jy = 0; jy < N7; ++jy) {
                         const int off = zoff + jy + (jy >= ycross ? ystep : 0);
                         const uint32_t w0 = win[off];
+#if R3_W1_ALWAYS
+                        const uint32_t w1 = win[off + BRICK_WORDS];   // unused bits when !two; stays inside the warp's buffers
+#else
                         const uint32_t w1 = two ? win[off + BRICK_WORDS] : 0u;
+#endif
                         slab |= (unsigned long long)(__funnelshift_r(w0, w1, sh) & rowmask) << (N7 * jy);
                     }
                 } else {
@@ -392,10 +340,10 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
         if (stage_rows) {
             // row buffer -> global: consecutive lanes write consecutive 16-byte pieces of a row
             __syncwarp();
-            const int cpr = row_bytes >> 4;                           // 16-byte pieces per row
+            // piece gp = lane + 32 t is piece cidx of row r; (r, cidx) advance by (32 / cpr, 32 % cpr) per trip
             const int pieces = 32 * cpr;
+            int r = r_first, cidx = c_first;
             for (int gp = lane; gp < pieces; gp += 32) {
-                const int r = gp / cpr, cidx = gp - r * cpr;
                 const long long row_q = __shfl_sync(0xffffffffu, (long long)qi, r);
                 const bool row_active = grp * 32 + r < nq;
                 if (row_active) {
@@ -403,6 +351,8 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
                     // streaming store: the rows are never read again, they should not push bricks and tables out of L2
                     __stcs(reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(out) + row_q * (long long)row_bytes + cidx * 16), v);
                 }
+                r += r_step; cidx += c_step;
+                if (cidx >= cpr) { cidx -= cpr; r += 1; }
             }
             __syncwarp();
         }

@@ -203,10 +203,10 @@ rows5_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
 #pragma unroll
                 for (int a = 0; a < 3; ++a) {
                     const double u = (q[a] - E.minc[a]) * E.inv_edge;
-                    double cf = floor(u);
+                    const double cf = floor(u);
                     f[a] = u - cf;
-                    cf = fmin(fmax(cf - (double)E.cell_lo[a], -1.0e9), 1.0e9);
-                    c[a] = (int)cf;
+                    // saturating conversion + integer clamp (see rows3.cu)
+                    c[a] = max(min(__double2int_rn(cf - (double)E.cell_lo[a]), 1000000000), -1000000000);
                 }
                 c0 = c[0]; c1 = c[1]; c2 = c[2];
                 fxm = (float)f[0] + 4.5f; fym = (float)f[1] + 4.5f; fzm = (float)f[2] + 4.5f;
@@ -228,7 +228,7 @@ rows5_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
                 if (staged) {
                     // brick (ix,iy,iz) -> win[((iz*nb1)+iy)*nb0+ix][32]; empty and out-of-range bricks copy slot 0 (zeros)
                     const int total = nb0 * nb1 * (int)n2;
-                    const float inv0 = __frcp_rn((float)nb0), inv01 = __frcp_rn((float)(nb0 * nb1));
+                    const float inv0 = rcp_fast((float)nb0), inv01 = rcp_fast((float)(nb0 * nb1));
                     uint32_t slot0 = 0, slot1 = 0;
 #pragma unroll
                     for (int t = 0; t < 2; ++t) {
