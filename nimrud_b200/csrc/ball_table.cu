@@ -3,8 +3,9 @@
 // a query sits at fractional position f in [0,1)^3 of its anchor cell; the 7x7x7 cells of its window
 // are at integer offsets.  which of them lie in the ball of radius rho = r/e depends on f only, and for
 // a small BIN of f (1/Q of a cell per axis) almost every cell is either inside for the whole bin or
-// outside for the whole bin.  per (rho, bin) the table stores, per z-slab of the window, two 49-bit
-// masks (bit 7*jy + t <-> cell (t, jy)):
+// outside for the whole bin.  per (rho, bin) the table stores, per z-slab of the window, two masks of 49
+// cells (bit row_bits*jy + t <-> cell (t, jy); row_bits = 8 puts every row in its own byte, rows 0..3 in
+// the low word, 4..6 in the high word; 7 packs them):
 //     in   cells that are inside the ball for EVERY f of the bin (with a safety margin)
 //     unc  cells that may be on either side -- the kernel evaluates those, and only those that are
 //          occupied, with the reference's own float64 expression (nimrud/minimal/multiscale.py:103,
@@ -22,7 +23,7 @@
 namespace nbr {
 
 __global__ void __launch_bounds__(256)
-ball_table_kernel(uint4 *__restrict__ table, int Q, double rho2, double margin)
+ball_table_kernel(uint4 *__restrict__ table, int Q, double rho2, double margin, int row_bits)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= Q * Q * Q * 8) return;
@@ -51,7 +52,7 @@ ball_table_kernel(uint4 *__restrict__ table, int Q, double rho2, double margin)
             axis(0, t, xmin, xmax);
             const double d2min = xmin * xmin + ymin * ymin + zmin * zmin;
             const double d2max = xmax * xmax + ymax * ymax + zmax * zmax;
-            const unsigned long long bit = 1ull << (7 * jy + t);
+            const unsigned long long bit = 1ull << (row_bits * jy + t);
             if (d2max <= rho2 - margin) in |= bit;
             else if (!(d2min > rho2 + margin)) unc |= bit;
         }
@@ -60,11 +61,11 @@ ball_table_kernel(uint4 *__restrict__ table, int Q, double rho2, double margin)
 }
 
 static std::mutex g_table_mutex;
-static std::map<std::tuple<int, int, uint64_t, uint64_t>, const uint4 *> g_tables;
+static std::map<std::tuple<int, int, int, uint64_t, uint64_t>, const uint4 *> g_tables;
 
 // margin: absolute slack on squared distances in cell units (covers the rounding of the reference
 // expression and of the kernel's own f); rounded up to a power of two so that the cache key is stable
-int ball_table_get(double rho2, double margin, int Q, const uint4 **out, cudaStream_t stream)
+int ball_table_get(double rho2, double margin, int Q, int row_bits, const uint4 **out, cudaStream_t stream)
 {
     int dev = 0;
     NBR_CUDA(cudaGetDevice(&dev));
@@ -74,14 +75,14 @@ int ball_table_get(double rho2, double margin, int Q, const uint4 **out, cudaStr
     uint64_t kr, km;
     memcpy(&kr, &rho2, 8);
     memcpy(&km, &margin, 8);
-    const auto key = std::make_tuple(dev, Q, kr, km);
+    const auto key = std::make_tuple(dev, Q, row_bits, kr, km);
     std::lock_guard<std::mutex> lock(g_table_mutex);
     auto it = g_tables.find(key);
     if (it != g_tables.end()) { *out = it->second; return NBR_OK; }
     uint4 *t = nullptr;
     const size_t n = (size_t)Q * Q * Q * 8;
     NBR_CUDA(cudaMalloc(&t, n * sizeof(uint4)));
-    ball_table_kernel<<<(unsigned)ceil_div((int64_t)n, 256), 256, 0, stream>>>(t, Q, rho2, margin);
+    ball_table_kernel<<<(unsigned)ceil_div((int64_t)n, 256), 256, 0, stream>>>(t, Q, rho2, margin, row_bits);
     NBR_LAUNCHED();
     NBR_CUDA(cudaStreamSynchronize(stream));       // once per distinct (rho, margin): later callers may be on other streams
     g_tables[key] = t;

@@ -64,7 +64,7 @@ int rows5_launch(const R3Launch *L, const void *query, int dtype, const uint32_t
                  int out_dtype, int64_t row_stride, int descriptor_mask, cudaStream_t stream);
 
 int rows_param(const Lattice *lat, const double *radii, const int *cols, int nr, RowsParam *P, cudaStream_t stream);
-int ball_table_get(double rho2, double margin, int Q, const uint4 **out, cudaStream_t stream);
+int ball_table_get(double rho2, double margin, int Q, int row_bits, const uint4 **out, cudaStream_t stream);
 int ball_tables_trim();      // bound the table caches; only at the start of a feature call
 int ball_tables5_trim();
 bool rows_supported(double edge, const double *radii, int nr);

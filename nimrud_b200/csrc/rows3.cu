@@ -34,6 +34,9 @@ namespace nbr {
 #ifndef R3_W1_ALWAYS
 #define R3_W1_ALWAYS 1
 #endif
+#ifndef R3_ROW_BITS
+#define R3_ROW_BITS 8               // bits per window row in the slab words and the shell tables (7: packed, 8: one byte per row)
+#endif
 #ifndef R3_UNROLL_N
 #define R3_UNROLL_N 1
 #endif
@@ -240,8 +243,16 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
                 if (!__any_sync(0xffffffffu, (tcur.x | tcur.y | tcur.z | tcur.w) != 0)) continue;
                 const int az = za + jz;
                 const int wz = (az & (BRICK_Z - 1)) << BRICK_YS;
-                // ---- gather the slab: bits of row jy at [7*jy, 7*jy+7)
+                // ---- gather the slab: bits of row jy at [R3_ROW_BITS * jy, + 7)
+#if R3_ROW_BITS == 8
+                uint32_t v[N7];                                              // row jy in the low 7 bits, neighbours' bits above
+#pragma unroll
+                for (int jy = 0; jy < N7; ++jy) v[jy] = 0u;
+#define R3_PUT_ROW(jy, bits) v[jy] = (bits)
+#else
                 unsigned long long slab = 0;
+#define R3_PUT_ROW(jy, bits) slab |= (unsigned long long)((bits) & rowmask) << (N7 * (jy))
+#endif
                 if (staged) {
                     const int zoff = ((az >> BRICK_ZS) - lo2) * zstride + wz + ybase;
 #pragma unroll
@@ -253,7 +264,7 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
 #else
                         const uint32_t w1 = two ? win[off + BRICK_WORDS] : 0u;
 #endif
-                        slab |= (unsigned long long)(__funnelshift_r(w0, w1, sh) & rowmask) << (N7 * jy);
+                        R3_PUT_ROW(jy, __funnelshift_r(w0, w1, sh));
                     }
                 } else {
                     const int iz = (az >> BRICK_ZS) - bz0;                     // 0..2
@@ -269,31 +280,48 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
                             const int word = wz | ((ya + jy) & (BRICK_Y - 1));
                             const uint32_t w0 = sa ? E.pool[(int64_t)sa * BRICK_WORDS + word] : 0u;
                             const uint32_t w1 = sb ? E.pool[(int64_t)sb * BRICK_WORDS + word] : 0u;
-                            slab |= (unsigned long long)(__funnelshift_r(w0, w1, sh) & rowmask) << (N7 * jy);
+                            R3_PUT_ROW(jy, __funnelshift_r(w0, w1, sh));
                         }
                     }
                 }
+#undef R3_PUT_ROW
+                // ---- membership: sure cells + occupied cells of the uncertain shell (low word: rows 0..3, high word: 4..6)
+#if R3_ROW_BITS == 8
+                // one byte per row: 5 byte permutes assemble the slab; bit 7 of every byte and byte 3 of the high word
+                // carry other cells' bits, the table masks are zero there
+                const uint32_t slab_lo = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+                const uint32_t slab_hi = __byte_perm(__byte_perm(v[4], v[5], 0x0040), v[6], 0x0410);
+#else
+                const uint32_t slab_lo = (uint32_t)slab, slab_hi = (uint32_t)(slab >> 32);
+#endif
+                const uint32_t Mlo = slab_lo & tcur.x, Mhi = slab_hi & tcur.y, Ulo = slab_lo & tcur.z, Uhi = slab_hi & tcur.w;
                 // warp-uniform skip only: the body below is straight-line code for every lane (an empty slab adds
                 // zeros), which lets the loads of the table lookups overlap instead of ending at divergent branches
-                if (!__any_sync(0xffffffffu, slab != 0)) continue;
-                // ---- membership: sure cells + occupied cells of the uncertain shell
-                unsigned long long M = slab & ((unsigned long long)tcur.x | ((unsigned long long)tcur.y << 32));
-                const unsigned long long U = slab & ((unsigned long long)tcur.z | ((unsigned long long)tcur.w << 32));
+                if (!__any_sync(0xffffffffu, (Mlo | Mhi | Ulo | Uhi) != 0)) continue;
                 // the uncertain cells are parked in the lane's table line (slots <= jz are consumed) and decided after
                 // the slab loop in ONE loop: deciding them slab by slab made every slab wait for its slowest lane
-                ulist[n_u] = make_uint2((uint32_t)U, (uint32_t)jz);                       // slot n_u <= 2 jz + 1: consumed
-                n_u += (uint32_t)U != 0;
-                ulist[n_u] = make_uint2((uint32_t)(U >> 32), (uint32_t)jz | 256u);
-                n_u += (uint32_t)(U >> 32) != 0;
+                ulist[n_u] = make_uint2(Ulo, (uint32_t)jz);                               // slot n_u <= 2 jz + 1: consumed
+                n_u += Ulo != 0;
+                ulist[n_u] = make_uint2(Uhi, (uint32_t)jz | 256u);
+                n_u += Uhi != 0;
                 // ---- moments of the slab
                 // packed sums: sum e, sum jy*e, sum jy^2*e (of the last only the count field is read: it cannot be
                 // reached by carries from above).  the row's 7 bits are extracted as a byte offset into the table
                 uint32_t Pk = 0, Qk = 0, Rk = 0;
-                const unsigned long long M4 = M << 2;
                 const char *lut_bytes = reinterpret_cast<const char *>(s_lut);
+#if R3_ROW_BITS != 8
+                const unsigned long long M4 = ((unsigned long long)Mlo | ((unsigned long long)Mhi << 32)) << 2;
+#endif
 #pragma unroll
                 for (int jy = 0; jy < N7; ++jy) {
-                    const uint32_t e = *reinterpret_cast<const uint32_t *>(lut_bytes + ((uint32_t)(M4 >> (N7 * jy)) & (rowmask << 2)));
+#if R3_ROW_BITS == 8
+                    const uint32_t mw = jy < 4 ? Mlo : Mhi;
+                    const int sb = 8 * (jy & 3) - 2;                     // byte jy & 3 of the word, times 4
+                    const uint32_t boff = (sb < 0 ? mw << 2 : mw >> sb) & (rowmask << 2);
+#else
+                    const uint32_t boff = (uint32_t)(M4 >> (N7 * jy)) & (rowmask << 2);
+#endif
+                    const uint32_t e = *reinterpret_cast<const uint32_t *>(lut_bytes + boff);
                     Pk += e;
                     Qk += jy * e;
                     Rk += jy * jy * e;
@@ -307,7 +335,7 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
             // the reference's float64 expression does.  accepted cells are added to the moments one by one
             {
                 uint32_t cur = 0;
-                int k = 0, jzc = 0, half = 0;
+                int k = 0, jzc = 0, half = 0;                               // half: first row (8-bit rows) / first bit (7-bit rows) of the word
                 float dz2f = 0.0f;
                 for (;;) {
                     if (cur == 0) {
@@ -315,13 +343,19 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
                         const uint2 e = ulist[k++];
                         cur = e.x;
                         jzc = (int)(e.y & 255u);
-                        half = (int)(e.y >> 8) * 32;
+                        half = (int)(e.y >> 8) * (R3_ROW_BITS == 8 ? 4 : 32);
                         const float dzf = fzm - (float)jzc;
                         dz2f = dzf * dzf;
                     }
+#if R3_ROW_BITS == 8
+                    const int i = __ffs(cur) - 1;
+                    cur &= cur - 1;
+                    const int jy = (i >> 3) + half, t = i & 7;
+#else
                     const int i = __ffs(cur) - 1 + half;
                     cur &= cur - 1;
                     const int jy = (i * 37) >> 8, t = i - 7 * jy;
+#endif
                     const float dx = fxm - (float)t, dy = fym - (float)jy;
                     const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz2f));
                     bool in = d2 < E.rho2;
@@ -386,7 +420,7 @@ bool rows3_entry(const Lattice *lat, double radius, int col, const R3Entry *prev
     for (int a = 0; a < 3; ++a)
         maxabs = std::max(maxabs, std::max(fabs(lat->grid.min_corner[a]), fabs(lat->grid.max_corner[a])));
     const double margin = std::max(1e-11, 64.0 * 2.3e-16 * (maxabs / e + 8.0));
-    *rc = ball_table_get(rho * rho, margin, tq, &E->table, stream);
+    *rc = ball_table_get(rho * rho, margin, tq, R3_ROW_BITS, &E->table, stream);
     return *rc == NBR_OK;
 }
 
