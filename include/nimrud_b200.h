@@ -16,6 +16,10 @@
  *     last failure on the calling thread.
  *   - scratch memory comes from the stream-ordered CUDA pool (cudaMallocAsync); the caller owns
  *     every input and output buffer.
+ *   - the device that holds the buffers (and owns `stream`) must be the CURRENT device of the calling
+ *     thread (cudaSetDevice) for every call, including nbr_lattice_destroy / nbr_lattice_info: kernels,
+ *     scratch and cached tables are created on the current device.  one process may drive several
+ *     devices in turn (kernel attributes and table caches are kept per device).
  */
 #ifndef NIMRUD_B200_H
 #define NIMRUD_B200_H

@@ -43,19 +43,29 @@ void Scratch::release()
 
 int device_sm_count()
 {
-    static int sms = 0;
+    static std::atomic<int> sms_of[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int sms = sms_of[dev].load(std::memory_order_relaxed);
     if (!sms) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-            sms = 148;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
         // keep freed scratch in the pool: the path allocates the same sizes on every call
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
             uint64_t keep = ~0ull;
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
+        sms_of[dev].store(sms, std::memory_order_relaxed);
     }
     return sms;
+}
+
+bool first_use_on_device(std::atomic<uint64_t> &seen)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;      // unknown: configure again
+    const uint64_t bit = 1ull << dev;
+    return (seen.fetch_or(bit) & bit) == 0;
 }
 
 // ---------------------------------------------------------------------------------------------

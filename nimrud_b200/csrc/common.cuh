@@ -56,6 +56,9 @@ struct Scratch {
 };
 
 int device_sm_count();
+// true the first time it is called with this flag word on the current device (kernel attributes such as the
+// dynamic shared memory limit are per device: a process that drives several GPUs has to set them on each)
+bool first_use_on_device(std::atomic<uint64_t> &seen);
 
 // optional per-phase device timing (CUDA events on the launching stream); see nbr_timing_*
 enum Phase { PHASE_BBOX = 0, PHASE_INDEX = 1, PHASE_ORDER = 2, PHASE_FEATURES = 3, PHASE_COUNT = 4 };

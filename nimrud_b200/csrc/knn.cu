@@ -308,11 +308,10 @@ int knn(const Lattice *lat, const void *query, int dtype, int64_t nq, int k, int
         kp.k[i] = ks[i];
     }
     const size_t smem = knn_smem();
-    static bool configured = false;
-    if (!configured) {
+    static std::atomic<uint64_t> configured{0};
+    if (first_use_on_device(configured)) {
         NBR_CUDA(cudaFuncSetAttribute(knn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         NBR_CUDA(cudaFuncSetAttribute(knn_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
     }
     const int blocks = (int)std::min<int64_t>(ceil_div(nq, KNN_WARPS), (int64_t)device_sm_count() * 8);
     if (out_dtype == NBR_F32)

@@ -446,14 +446,13 @@ int rows3_launch(const R3Launch *L, const void *query, int dtype, const uint32_t
     const int stage_rows = !no_stage && (int64_t)L->n * ncol == row_stride && row_bytes <= R3_MAX_ROW_BYTES && row_bytes % 16 == 0 &&
                            ((uintptr_t)out & 15) == 0;
     const size_t smem = (size_t)R3_WARPS * (R3_WIN_BYTES + R3_TAB_BYTES + (stage_rows ? 32 * row_bytes : 0));
-    static bool configured = false;
-    if (!configured) {
+    static std::atomic<uint64_t> configured{0};
+    if (first_use_on_device(configured)) {
         const int max_smem = R3_WARPS * (R3_WIN_BYTES + R3_TAB_BYTES + 32 * R3_MAX_ROW_BYTES);
         NBR_CUDA(cudaFuncSetAttribute(rows3_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         NBR_CUDA(cudaFuncSetAttribute(rows3_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         NBR_CUDA(cudaFuncSetAttribute(rows3_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         NBR_CUDA(cudaFuncSetAttribute(rows3_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        configured = true;
     }
 #define R3_GO(T, X) rows3_kernel<T, X><<<blocks, R3_WARPS * 32, smem, stream>>>(copy, query, dtype, perm, nq, (T *)out, row_stride, stage_rows)
     if (out_dtype == NBR_F32) { if (ext) R3_GO(float, true); else R3_GO(float, false); }

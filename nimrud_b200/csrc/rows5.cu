@@ -402,13 +402,12 @@ int rows5_launch(const R3Launch *L, const void *query, int dtype, const uint32_t
     const int blocks = (int)std::min<int64_t>(ceil_div(ceil_div(nq, 32), R5_WARPS), (int64_t)device_sm_count() * 12);
     const bool ext = (descriptor_mask & NBR_DESC_EXTENDED) != 0;
     const size_t smem = (size_t)R5_WARPS * (R5_WIN_BYTES + R5_ULIST_BYTES);
-    static bool configured = false;
-    if (!configured) {
+    static std::atomic<uint64_t> configured{0};
+    if (first_use_on_device(configured)) {
         NBR_CUDA(cudaFuncSetAttribute(rows5_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         NBR_CUDA(cudaFuncSetAttribute(rows5_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         NBR_CUDA(cudaFuncSetAttribute(rows5_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         NBR_CUDA(cudaFuncSetAttribute(rows5_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
     }
 #define R5_GO(T, X) rows5_kernel<T, X><<<blocks, R5_WARPS * 32, smem, stream>>>(copy, query, dtype, perm, nq, (T *)out, row_stride)
     if (out_dtype == NBR_F32) { if (ext) R5_GO(float, true); else R5_GO(float, false); }

@@ -129,13 +129,12 @@ static int radix_sort(uint64_t *keys, uint64_t *keys_tmp, uint32_t *vals, uint32
     uint64_t *src = keys, *dst = keys_tmp;
     uint32_t *vsrc = vals, *vdst = vals_tmp;
     const size_t smem = scatter_smem(vals != nullptr);
-    static bool configured = false;
-    if (!configured) {
+    static std::atomic<uint64_t> configured{0};
+    if (first_use_on_device(configured)) {
         NBR_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)scatter_smem(true)));
         NBR_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)scatter_smem(false)));
-        configured = true;
     }
     for (int shift = begin_bit; shift < end_bit; shift += RADIX_BITS) {
         radix_hist_kernel<<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(src, n, shift, c, tiles);

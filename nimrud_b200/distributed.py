@@ -62,17 +62,17 @@ def select_halo(cloud, box_lo, box_hi, h):
     return inside.nonzero(as_tuple=True)[0]
 
 
-def _select_halos_cuda(cloud, grown_boxes):
-    """per destination box (lo, hi float64 (3,) cpu tensors, already grown): the points of `cloud` inside it.
-    two passes of the CUDA halo kernels (count, fill) for all destinations at once -> (send buffer (m,3), counts)."""
+def _count_halos_cuda(cloud, grown_boxes):
+    """first pass of the CUDA halo selection: per destination box (lo, hi float64 lists, already grown) the number
+    of points of `cloud` inside it, as a DEVICE tensor (no host synchronisation), plus what the fill pass needs."""
     import ctypes
     from . import _lib
     from ._util import ptr, stream_ptr
     lib = _lib.lib()
     code = _lib.F32 if cloud.dtype == torch.float32 else _lib.F64
     n = int(cloud.shape[0])
+    state = []
     counts = []
-    parts = []
     with torch.cuda.device(cloud.device):
         s = stream_ptr(cloud.device)
         for first in range(0, len(grown_boxes), 8):
@@ -81,16 +81,34 @@ def _select_halos_cuda(cloud, grown_boxes):
             boxes_p = flat.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
             cnt = torch.zeros(2 * len(chunk), dtype=torch.int64, device=cloud.device)     # counts | cursors
             _lib.check(lib.nbr_halo_count(ptr(cloud), code, n, boxes_p, len(chunk), ptr(cnt), s))
-            c = [int(v) for v in cnt[:len(chunk)].tolist()]
+            state.append((flat, cnt, len(chunk)))
+            counts.append(cnt[:len(chunk)])
+    return (torch.cat(counts) if len(counts) != 1 else counts[0]), state
+
+
+def _fill_halos_cuda(cloud, state, counts_host):
+    """second pass: the selected points of every destination, destination by destination -> (m, 3)."""
+    import ctypes
+    from . import _lib
+    from ._util import ptr, stream_ptr
+    lib = _lib.lib()
+    code = _lib.F32 if cloud.dtype == torch.float32 else _lib.F64
+    n = int(cloud.shape[0])
+    parts = []
+    at = 0
+    with torch.cuda.device(cloud.device):
+        s = stream_ptr(cloud.device)
+        for flat, cnt, m in state:
+            c = counts_host[at:at + m]
+            at += m
             offs = np.concatenate([[0], np.cumsum(c)[:-1]]).astype(np.int64)
-            buf = torch.empty((sum(c), 3), dtype=cloud.dtype, device=cloud.device)
+            buf = torch.empty((int(sum(c)), 3), dtype=cloud.dtype, device=cloud.device)
             if sum(c):
-                _lib.check(lib.nbr_halo_fill(ptr(cloud), code, n, boxes_p, len(chunk),
+                _lib.check(lib.nbr_halo_fill(ptr(cloud), code, n, flat.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), m,
                                              offs.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
-                                             ptr(cnt[len(chunk):]), ptr(buf), s))
-            counts += c
+                                             ptr(cnt[m:]), ptr(buf), s))
             parts.append(buf)
-    return (torch.cat(parts, 0) if len(parts) != 1 else parts[0]), counts
+    return torch.cat(parts, 0) if len(parts) != 1 else parts[0]
 
 
 def gather_boxes(cloud, group=None):
@@ -122,10 +140,19 @@ def exchange_halo(cloud, edge_lengths, radii, group=None, gathered=None):
                and not bool(((all_boxes[dst, 3:] + h) < my_lo).any())]
     send_counts = [0] * world
     if cloud.is_cuda and cloud.dtype in (torch.float32, torch.float64) and cloud.is_contiguous():
-        grown = [((all_boxes[d, :3] - h).tolist(), (all_boxes[d, 3:] + h).tolist()) for d in targets]
-        send_buf, counts = _select_halos_cuda(cloud, grown) if targets else (cloud[:0], [])
-        for d, c in zip(targets, counts):
-            send_counts[d] = c
+        # count on the device, exchange the counts device to device, and read both directions with ONE host
+        # synchronisation; the fill pass and the point exchange follow
+        counts_t = torch.zeros(world, dtype=torch.int64, device=cloud.device)
+        state = None
+        if targets:
+            grown = [((all_boxes[d, :3] - h).tolist(), (all_boxes[d, 3:] + h).tolist()) for d in targets]
+            cnt_dev, state = _count_halos_cuda(cloud, grown)
+            counts_t[torch.tensor(targets, device=cloud.device)] = cnt_dev
+        recv_counts_t = torch.empty_like(counts_t)
+        dist.all_to_all_single(recv_counts_t, counts_t, group=group)
+        both = torch.stack([counts_t, recv_counts_t]).tolist()
+        send_counts, recv_counts = [int(v) for v in both[0]], [int(v) for v in both[1]]
+        send_buf = _fill_halos_cuda(cloud, state, [send_counts[d] for d in targets]) if targets else cloud[:0]
     else:
         # host logic on CPU tensors (gloo tests): same inclusive selection with torch ops
         send_parts = []
@@ -134,10 +161,10 @@ def exchange_halo(cloud, edge_lengths, radii, group=None, gathered=None):
             send_parts.append(cloud[idx])
             send_counts[dst] = int(idx.numel())
         send_buf = torch.cat(send_parts, 0) if send_parts else cloud[:0]
-    counts_t = torch.tensor(send_counts, dtype=torch.int64, device=cloud.device)
-    recv_counts_t = torch.empty_like(counts_t)
-    dist.all_to_all_single(recv_counts_t, counts_t, group=group)
-    recv_counts = [int(v) for v in recv_counts_t.tolist()]
+        counts_t = torch.tensor(send_counts, dtype=torch.int64, device=cloud.device)
+        recv_counts_t = torch.empty_like(counts_t)
+        dist.all_to_all_single(recv_counts_t, counts_t, group=group)
+        recv_counts = [int(v) for v in recv_counts_t.tolist()]
     send_buf = send_buf.contiguous().reshape(-1)
     recv_buf = torch.empty(sum(recv_counts) * 3, dtype=cloud.dtype, device=cloud.device)
     dist.all_to_all_single(recv_buf, send_buf, output_split_sizes=[3 * c for c in recv_counts],

@@ -32,7 +32,8 @@ def cloud_bbox(points_dev, dtype_code):
     """(lo, hi) float64 numpy arrays of a CUDA (n, ndim) cloud."""
     n, ndim = points_dev.shape
     out = torch.empty(6, dtype=torch.float64, device=points_dev.device)
-    _lib.check(_lib.lib().nbr_bbox(ptr(points_dev), dtype_code, n, ndim, ptr(out), stream_ptr(points_dev.device)))
+    with torch.cuda.device(points_dev.device):     # every library call runs with the data's device current
+        _lib.check(_lib.lib().nbr_bbox(ptr(points_dev), dtype_code, n, ndim, ptr(out), stream_ptr(points_dev.device)))
     box = out.cpu().numpy()
     return box[:ndim].copy(), box[3:3 + ndim].copy()
 
@@ -103,8 +104,9 @@ class VoxelFilter(object):
         n = dev.shape[0]
         addr = torch.empty(n, dtype=torch.int64, device=dev.device)
         oob = torch.zeros(1, dtype=torch.int32, device=dev.device)
-        _lib.check(_lib.lib().nbr_voxel_addresses(ptr(dev), code, n, ctypes.byref(self._grid), ptr(addr), ptr(oob),
-                                                  stream_ptr(dev.device)))
+        with torch.cuda.device(dev.device):
+            _lib.check(_lib.lib().nbr_voxel_addresses(ptr(dev), code, n, ctypes.byref(self._grid), ptr(addr), ptr(oob),
+                                                      stream_ptr(dev.device)))
         if int(oob.item()) != 0:
             raise ValueError("some points fall outside filter bounding region")   # utils/geometry.py:96-97
         return addr
@@ -118,8 +120,9 @@ class VoxelFilter(object):
     def _centres_dev(self, addr_dev):
         n = addr_dev.shape[0]
         out = torch.empty((n, self._ndim), dtype=torch.float64, device=addr_dev.device)
-        _lib.check(_lib.lib().nbr_voxel_centres(ptr(addr_dev), n, ctypes.byref(self._grid), ptr(out),
-                                                stream_ptr(addr_dev.device)))
+        with torch.cuda.device(addr_dev.device):
+            _lib.check(_lib.lib().nbr_voxel_centres(ptr(addr_dev), n, ctypes.byref(self._grid), ptr(out),
+                                                    stream_ptr(addr_dev.device)))
         return out
 
     def address_to_coordinate(self, addresses):
@@ -136,9 +139,10 @@ class VoxelFilter(object):
         tmp = torch.empty_like(addr)
         bits = int(self.widths.sum())
         s = stream_ptr(addr.device)
-        _lib.check(_lib.lib().nbr_sort_u64(ptr(addr), ptr(tmp), n, 0, bits, s))
         count = torch.zeros(1, dtype=torch.int64, device=addr.device)
-        _lib.check(_lib.lib().nbr_unique_u64(ptr(addr), n, ptr(tmp), ptr(count), s))
+        with torch.cuda.device(addr.device):
+            _lib.check(_lib.lib().nbr_sort_u64(ptr(addr), ptr(tmp), n, 0, bits, s))
+            _lib.check(_lib.lib().nbr_unique_u64(ptr(addr), n, ptr(tmp), ptr(count), s))
         return tmp[:int(count.item())]
 
     def unique_addresses(self, points):

@@ -187,7 +187,8 @@ class LatticeIndex(object):
 
     def close(self):
         if getattr(self, "_handle", None):
-            _lib.lib().nbr_lattice_destroy(self._handle)
+            with torch.cuda.device(self.device):       # frees are ordered on this device's stream
+                _lib.lib().nbr_lattice_destroy(self._handle)
             self._handle = None
 
     def __del__(self):
@@ -199,7 +200,8 @@ class LatticeIndex(object):
     def _info(self):
         if self._counts is None:
             nv, nb = ctypes.c_int64(), ctypes.c_int64()
-            _lib.check(_lib.lib().nbr_lattice_info(self._handle, ctypes.byref(nv), ctypes.byref(nb)))
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().nbr_lattice_info(self._handle, ctypes.byref(nv), ctypes.byref(nb)))
             self._counts = (nv.value, nb.value)
         return self._counts
 

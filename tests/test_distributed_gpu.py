@@ -48,3 +48,23 @@ def test_two_gpu_tiles_match_single_gpu(tmp_path):
     ref = whole[order.cuda()].cpu().numpy()
     assert got.shape == ref.shape
     assert np.array_equal(got, ref)     # same voxels, same integer moments, same arithmetic -> identical
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_devices_in_one_process():
+    """kernel attributes (dynamic shared memory limits) and table caches are per device: one process may
+    call the path on cuda:0 and then on cuda:1 (radius kernels of every window size, kNN, radix sort)."""
+    from nimrud_b200 import multiscale, synth
+    cloud = synth.urban_scene(60_000, seed=5, device="cpu")
+    edges, radii = (0.2, 0.2, 0.2), (0.6, 1.0, 1.4)          # 7x7x7, 11x11x11 and interval kernels
+    outs, knns = [], []
+    for d in (0, 1):
+        c = cloud.to("cuda:%d" % d)
+        outs.append(multiscale.process_single_core(c, c, edges, radii, out_dtype=np.float32).cpu())
+        knns.append(multiscale.knn_features(c, c, 0.2, (5, 10), out_dtype=np.float32).cpu())
+    assert torch.equal(outs[0], outs[1])
+    assert torch.equal(knns[0], knns[1])
+    # the voxel filter (bbox, addresses, radix sort + unique, centres) on the second device
+    from nimrud_b200.geometry import VoxelFilter
+    cen = [VoxelFilter(cloud.to("cuda:%d" % d), 0.4).unique_voxels(cloud.to("cuda:%d" % d)).cpu() for d in (0, 1)]
+    assert torch.equal(cen[0], cen[1])
