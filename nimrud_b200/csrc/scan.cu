@@ -101,13 +101,27 @@ scan_lookback_kernel(const uint32_t *in, uint32_t *out, int64_t n, unsigned long
     const int64_t base = tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
     uint32_t v[SCAN_ITEMS];
     uint32_t acc = 0;
+    // a thread owns SCAN_ITEMS consecutive items: 16-byte loads / stores when the arrays are aligned and the
+    // thread's chunk is whole (scalar accesses touch every 32-byte sector SCAN_ITEMS times)
+    static_assert(SCAN_ITEMS % 4 == 0, "vector path");
+    const bool vec = (((uintptr_t)in | (uintptr_t)out) & 15) == 0 && base + SCAN_ITEMS <= n;
+    if (vec) {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k += 4) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(in + base + k);
+            v[k] = q.x; v[k + 1] = q.y; v[k + 2] = q.z; v[k + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            const int64_t i = base + k;
+            v[k] = i < n ? in[i] : 0u;
+        }
+    }
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; ++k) {
-        const int64_t i = base + k;
-        uint32_t x = i < n ? in[i] : 0u;
-        if (FLAGS) x = x ? 1u : 0u;
-        v[k] = x;
-        acc += x;
+        if (FLAGS) v[k] = v[k] ? 1u : 0u;
+        acc += v[k];
     }
     uint32_t total;
     uint32_t prefix = block_exclusive_scan<uint32_t>(acc, smem, &total);
@@ -142,11 +156,20 @@ scan_lookback_kernel(const uint32_t *in, uint32_t *out, int64_t n, unsigned long
     }
     __syncthreads();
     prefix += s_prefix;
+    uint32_t r[SCAN_ITEMS];
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; ++k) {
-        const int64_t i = base + k;
-        if (i < n) out[i] = FLAGS ? (v[k] ? prefix + 1 : 0u) : prefix;
+        r[k] = FLAGS ? (v[k] ? prefix + 1 : 0u) : prefix;
         prefix += v[k];
+    }
+    if (vec) {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k += 4)
+            *reinterpret_cast<uint4 *>(out + base + k) = make_uint4(r[k], r[k + 1], r[k + 2], r[k + 3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k)
+            if (base + k < n) out[base + k] = r[k];
     }
 }
 
