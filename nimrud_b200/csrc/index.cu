@@ -267,7 +267,10 @@ __device__ __forceinline__ void point_cell(const T *__restrict__ xyz, int64_t i,
 
 // mark / fill handle PTS points per thread with the loads of all of them in flight together: the kernels are
 // bound by the latency of the dependent directory / pool accesses, not by bandwidth
-constexpr int PTS = 4;
+#ifndef NBR_PTS
+#define NBR_PTS 4
+#endif
+constexpr int PTS = NBR_PTS;
 
 template <typename T>
 __global__ void __launch_bounds__(256)
