@@ -44,15 +44,17 @@ extern "C" {
 
 /* descriptor_mask bits for the feature kernels.  0 = the reference's 4 columns per scale
  * [population, centroid distance, l_max/sum, l_mid/sum] (minimal/features.py:21-57).
- * NBR_DESC_EXTENDED appends 18 columns per scale (extension, not in the reference):
+ * NBR_DESC_EXTENDED appends 22 columns per scale (extension, not in the reference):
  * linearity, planarity, sphericity, omnivariance, anisotropy, eigenentropy, change of curvature,
- * verticality, normal x, y, z (nz >= 0), sum of eigenvalues (covariance trace, ddof = 1), and the
+ * verticality, normal x, y, z (nz >= 0), sum of eigenvalues (covariance trace, ddof = 1), the
  * upper triangle of the covariance xx, xy, xz, yy, yz, zz (ddof = 1; the legacy C_MSO output,
- * nimrud/prototypes/mso.py:1735-1746). */
+ * nimrud/prototypes/mso.py:1735-1746), and x, y of the unit eigenvectors of the largest and of the
+ * middle eigenvalue (sign: x > 0, else y > 0, else z > 0; the legacy OG_MSO keeps the first two
+ * components of two eigenvectors, nimrud/prototypes/mso.py:1498-1539). */
 #define NBR_DESC_REFERENCE 0
 #define NBR_DESC_EXTENDED 1
 #define NBR_COLS_REFERENCE 4
-#define NBR_COLS_EXTENDED 22
+#define NBR_COLS_EXTENDED 26
 
 const char *nbr_last_error(void);
 int nbr_version(void);
@@ -142,7 +144,7 @@ int nbr_radius_sets(const nbr_lattice *lattice, const void *query_xyz, int dtype
 
 /* k nearest voxels, total order (squared distance as float64, index).  no reference counterpart
  * (extension).  idx_out (n_query,k) int32 padded with -1, d2_out (n_query,k) f64 padded
- * with +inf; either may be NULL.  if feats_out is non-NULL also writes the 4 (or 22) feature
+ * with +inf; either may be NULL.  if feats_out is non-NULL also writes the 4 (or 26) feature
  * columns for each k in ks_host (ascending, ks[n_k-1] == k). */
 int nbr_knn(const nbr_lattice *lattice, const void *query_xyz, int dtype, int64_t n_query, int32_t k,
             int32_t *idx_out, double *d2_out, const int32_t *ks_host, int32_t n_k, void *feats_out,

@@ -78,10 +78,12 @@ static __device__ __noinline__ Eig3 eig3_near_isotropic(double a0, double a1, do
     return out;
 }
 
+// WANT_NORMAL: also the unit eigenvectors of the smallest (normal) and of the largest (lead) eigenvalue
 template <bool WANT_NORMAL>
-__device__ __forceinline__ void eig3_unit_trace(const double a[6], double l[3], double normal[3])
+__device__ __forceinline__ void eig3_unit_trace(const double a[6], double l[3], double normal[3], double lead[3])
 {
     normal[0] = 0.0; normal[1] = 0.0; normal[2] = 1.0;
+    lead[0] = 1.0; lead[1] = 0.0; lead[2] = 0.0;
     // ---- float32: which eigenvalue is isolated, and its eigenvector to ~1e-6
     const float qf = 1.0f / 3.0f;
     const float f0 = (float)a[0], f1 = (float)a[1], f2 = (float)a[2], f3 = (float)a[3], f4 = (float)a[4],
@@ -171,19 +173,42 @@ __device__ __forceinline__ void eig3_unit_trace(const double a[6], double l[3], 
             } else {
                 normal[0] = u2[0] * i2; normal[1] = u2[1] * i2; normal[2] = u2[2] * i2;
             }
+            const double iv = rsqrt(s);
+            lead[0] = v[0] * iv; lead[1] = v[1] * iv; lead[2] = v[2] * iv;
         }
     } else {
         l[0] = hi; l[1] = lo; l[2] = lam;
         if (WANT_NORMAL) {
             const double iv = rsqrt(s);
             normal[0] = v[0] * iv; normal[1] = v[1] * iv; normal[2] = v[2] * iv;
+            // eigenvector of the 2x2 block for `hi`, mapped back through the normalised u1, u2
+            const double m01 = c01 * iv;
+            double w0 = m01, w1 = hi - m00;
+            if (fabs(hi - m11) > fabs(w1)) { w0 = hi - m11; w1 = m01; }
+            const double wn = w0 * w0 + w1 * w1;
+            const double i1 = rsqrt(nu), i2 = rsqrt(nu * s);
+            if (wn > 0.0) {
+                const double iw = rsqrt(wn);
+                w0 *= iw * i1; w1 *= iw * i2;
+                lead[0] = w0 * u1[0] + w1 * u2[0];
+                lead[1] = w0 * u1[1] + w1 * u2[1];
+                lead[2] = w0 * u1[2] + w1 * u2[2];
+            } else {
+                lead[0] = u1[0] * i1; lead[1] = u1[1] * i1; lead[2] = u1[2] * i1;
+            }
         }
     }
 }
 
-// the 18 extension columns (not on the reference path; kept out of line so the hot kernels stay small)
-static __device__ __noinline__ void extended_descriptors(const double l[3], double v[3], double trace, const double a[6],
-                                                        double ext[18])
+// x > 0, else x == 0 and y > 0, else z > 0: the sign convention of the emitted leading eigenvectors
+__device__ __forceinline__ void canonical_sign_xy(double w[3])
+{
+    if (w[0] < 0 || (w[0] == 0 && (w[1] < 0 || (w[1] == 0 && w[2] < 0)))) { w[0] = -w[0]; w[1] = -w[1]; w[2] = -w[2]; }
+}
+
+// the 22 extension columns (not on the reference path; kept out of line so the hot kernels stay small)
+static __device__ __noinline__ void extended_descriptors(const double l[3], double v[3], double lead[3], double trace,
+                                                        const double a[6], double ext[NBR_COLS_EXTENDED - 4])
 {
     const double e1 = fmax(l[0], 0.0), e2 = fmax(l[1], 0.0), e3 = fmax(l[2], 0.0);
     const double i1 = 1.0 / e1;
@@ -206,10 +231,16 @@ static __device__ __noinline__ void extended_descriptors(const double l[3], doub
     ext[11] = trace;                       // trace of the ddof=1 covariance
 #pragma unroll
     for (int i = 0; i < 6; ++i) ext[12 + i] = a[i] * trace;     // covariance (ddof = 1): xx xy xz yy yz zz; a has unit trace
+    // x, y of the unit eigenvectors of the largest and the middle eigenvalue (the legacy OG_MSO keeps the first two
+    // components of two eigenvectors, nimrud/prototypes/mso.py:1498-1539); middle = normal x lead
+    double second[3] = {v[1] * lead[2] - v[2] * lead[1], v[2] * lead[0] - v[0] * lead[2], v[0] * lead[1] - v[1] * lead[0]};
+    canonical_sign_xy(lead);
+    canonical_sign_xy(second);
+    ext[18] = lead[0]; ext[19] = lead[1]; ext[20] = second[0]; ext[21] = second[1];
 }
 
 // the columns from: n, the centroid distance, and the UNNORMALISED matrix a = n*S2 - S1*S1^T
-// (exact integers converted to double).  writes 4 (reference) or 22 (extended) columns at out[0..]
+// (exact integers converted to double).  writes 4 (reference) or 26 (extended) columns at out[0..]
 template <typename OutT>
 __device__ __forceinline__ void emit_core(long long n_int, double centroid, double a[6], double edge, OutT *out,
                                           int descriptor_mask)
@@ -217,9 +248,10 @@ __device__ __forceinline__ void emit_core(long long n_int, double centroid, doub
     const int ncol = (descriptor_mask & NBR_DESC_EXTENDED) ? NBR_COLS_EXTENDED : NBR_COLS_REFERENCE;
     const double n = (double)n_int;
     double l0 = 0.0, l1 = 0.0;
-    double ext[18];
+    constexpr int NEXT = NBR_COLS_EXTENDED - NBR_COLS_REFERENCE;
+    double ext[NEXT];
 #pragma unroll
-    for (int i = 0; i < 18; ++i) ext[i] = 0.0;
+    for (int i = 0; i < NEXT; ++i) ext[i] = 0.0;
     if (n_int >= 2) {
         const double tr = a[0] + a[3] + a[5];
         if (tr > 0.0) {
@@ -228,13 +260,13 @@ __device__ __forceinline__ void emit_core(long long n_int, double centroid, doub
             const double it = r0 * (2.0 - tr * r0);
 #pragma unroll
             for (int i = 0; i < 6; ++i) a[i] *= it;
-            double l[3], v[3];
-            if (descriptor_mask & NBR_DESC_EXTENDED) eig3_unit_trace<true>(a, l, v);
-            else eig3_unit_trace<false>(a, l, v);
+            double l[3], v[3], lead[3];
+            if (descriptor_mask & NBR_DESC_EXTENDED) eig3_unit_trace<true>(a, l, v, lead);
+            else eig3_unit_trace<false>(a, l, v, lead);
             l0 = l[0];
             l1 = l[1];
             if ((descriptor_mask & NBR_DESC_EXTENDED) && n_int >= 3)
-                extended_descriptors(l, v, tr * edge * edge / (n * (n - 1.0)), a, ext);
+                extended_descriptors(l, v, lead, tr * edge * edge / (n * (n - 1.0)), a, ext);
         }
     }
     out[0] = (OutT)n;
@@ -243,7 +275,7 @@ __device__ __forceinline__ void emit_core(long long n_int, double centroid, doub
     out[3] = (OutT)l1;
     if (ncol > 4) {
 #pragma unroll
-        for (int i = 0; i < 18; ++i) out[4 + i] = (OutT)ext[i];
+        for (int i = 0; i < NEXT; ++i) out[4 + i] = (OutT)ext[i];
     }
 }
 

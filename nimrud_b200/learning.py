@@ -31,7 +31,7 @@ from ._util import is_torch
 def scaleset_features(query_cloud, search_cloud, scaleset, out_dtype=np.float32, descriptors="reference"):
     """
     scaleset = [(voxel_edge, [radius, ...]), ...]  ->  (N, C * total_scales) features, scale-major in the
-    caller's order (C = 4 reference columns, or 22 with descriptors="extended").  every radius of a group
+    caller's order (C = 4 reference columns, or 26 with descriptors="extended").  every radius of a group
     shares the group's voxel lattice: one index build and one staged window per group on the device.
     """
     edges, radii = [], []

@@ -45,7 +45,7 @@ def _ncol(descriptors):
     if descriptors in ("reference", 0, None):
         return 4, _lib.DESC_REFERENCE
     if descriptors in ("extended", 1):
-        return 22, _lib.DESC_EXTENDED
+        return 26, _lib.DESC_EXTENDED
     raise ValueError("descriptors must be 'reference' or 'extended'")
 
 
@@ -72,7 +72,7 @@ def process_single_core(query_cloud, search_cloud, edge_lengths, radii, verbose=
 
     extras beyond the reference signature (keyword only in spirit, defaults = reference behaviour):
       out_dtype            float64 (drop-in) or float32
-      descriptors          "reference" (4 columns per scale) or "extended" (22 columns per scale)
+      descriptors          "reference" (4 columns per scale) or "extended" (26 columns per scale)
       return_voxel_counts  also return the number of unique search voxels per scale
       global_bbox          (lo, hi) of the WHOLE search cloud when `search_cloud` is only a tile of it
                            (+ halo): the voxel lattices are anchored on that box, so every tile sees the

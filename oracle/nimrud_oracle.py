@@ -214,10 +214,12 @@ def extended_row(neighbors):
       omnivariance (e1 e2 e3)^(1/3), anisotropy (e1-e3)/e1,
       eigenentropy -sum e_i ln e_i, change of curvature e3,
       normal (unit eigenvector of l3, sign fixed to nz>=0), verticality 1-|nz|.
-    returns 18 numbers: the 8 scalars, nx, ny, nz, l-sum, and the upper triangle of the covariance
-    (xx xy xz yy yz zz, numpy.cov, ddof = 1).  zeros if undefined.
+    returns 22 numbers: the 8 scalars, nx, ny, nz, l-sum, the upper triangle of the covariance
+    (xx xy xz yy yz zz, numpy.cov, ddof = 1), and x, y of the unit eigenvectors of l1 and l2 (sign: x > 0, else
+    y > 0, else z > 0; the legacy OG_MSO keeps two components of two eigenvectors, prototypes/mso.py:1498-1539).
+    zeros if undefined.
     """
-    out = np.zeros(18)
+    out = np.zeros(22)
     if neighbors.shape[0] < 3:
         return out
     cov = np.cov(neighbors, rowvar=False)
@@ -234,9 +236,15 @@ def extended_row(neighbors):
     for e in (e1, e2, e3):
         if e > 0:
             ent -= e * np.log(e)
+    def canonical(w):
+        if w[0] < 0 or (w[0] == 0 and (w[1] < 0 or (w[1] == 0 and w[2] < 0))):
+            return -w
+        return w
+    lead, second = canonical(v[:, 2]), canonical(v[:, 1])
     out[:] = [(e1 - e2) / e1, (e2 - e3) / e1, e3 / e1, np.cbrt(e1 * e2 * e3), (e1 - e3) / e1,
               ent, e3, 1.0 - abs(normal[2]), normal[0], normal[1], normal[2], total,
-              cov[0, 0], cov[0, 1], cov[0, 2], cov[1, 1], cov[1, 2], cov[2, 2]]
+              cov[0, 0], cov[0, 1], cov[0, 2], cov[1, 1], cov[1, 2], cov[2, 2],
+              lead[0], lead[1], second[0], second[1]]
     return out
 
 

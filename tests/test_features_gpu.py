@@ -157,7 +157,7 @@ def test_extended_descriptors_against_oracle():
     s = g["search"]
     e, r = float(g["edges"][1]), float(g["radii"][1])
     out = multiscale.process_single_core(q, s, [e], [r], descriptors="extended")
-    assert out.shape == (300, 22)
+    assert out.shape == (300, 26)
     assert_features_close(out[:, :4], g["features"][:300, 4:8], [r])
     p = O.grid_params(s.astype(np.float64), e)
     _, centres = O.unique_voxels(p, s.astype(np.float64))
@@ -170,6 +170,14 @@ def test_extended_descriptors_against_oracle():
     sep = (ext[:, 1] > 0.05)            # planarity = (e2-e3)/e1
     dots = np.abs((out[sep, 12:15] * ext[sep, 8:11]).sum(1))
     assert (dots > 1 - 1e-6).all()
+    # x, y of the eigenvectors of the largest and the middle eigenvalue: where all three eigenvalues are well
+    # separated and the sign convention (x > 0) is not decided by rounding
+    clear = (ext[:, 0] > 0.05) & (ext[:, 1] > 0.05)
+    lead_ok = clear & (np.abs(ext[:, 18]) > 1e-3)
+    second_ok = clear & (np.abs(ext[:, 20]) > 1e-3)
+    assert lead_ok.sum() > 50 and second_ok.sum() > 50
+    assert np.allclose(out[lead_ok, 22:24], ext[lead_ok, 18:20], atol=1e-4)
+    assert np.allclose(out[second_ok, 24:26], ext[second_ok, 20:22], atol=1e-4)
 
 
 def test_launch_counter_moves():
