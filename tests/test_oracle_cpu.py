@@ -158,3 +158,29 @@ def test_sharding_invariance(c_oracle):
     whole = O.process(q[:200], q, g["edges"][:1], g["radii"][:1])
     parts = np.concatenate([O.process(q[a:a + 50], q, g["edges"][:1], g["radii"][:1]) for a in range(0, 200, 50)])
     assert np.array_equal(whole, parts)
+
+
+def test_extended_row_is_self_consistent():
+    """the extension descriptors have no reference code (parity unpinned): check the oracle against the
+    definitions -- eigen-decomposition identities and the sign conventions of the emitted vectors."""
+    from oracle import nimrud_oracle as O
+    rs = np.random.RandomState(3)
+    for _ in range(50):
+        nb = rs.rand(rs.randint(4, 40), 3) * [1.0, 0.6, 0.2]
+        row = O.extended_row(nb)
+        assert row.shape == (22,)
+        cov = np.cov(nb, rowvar=False)
+        w, v = np.linalg.eigh(cov)
+        e = w[::-1] / w.sum()
+        assert np.allclose(row[:3], [(e[0] - e[1]) / e[0], (e[1] - e[2]) / e[0], e[2] / e[0]], rtol=1e-9, atol=1e-12)
+        assert np.isclose(row[11], np.trace(cov))
+        assert np.allclose(row[12:18], cov[np.triu_indices(3)])
+        normal = row[8:11]
+        assert normal[2] >= 0 and np.isclose(np.linalg.norm(normal), 1.0)
+        assert np.allclose(cov @ normal, w[0] * normal, atol=1e-9)
+        # x, y of the eigenvectors of the largest / middle eigenvalue, sign x > 0
+        assert row[18] >= 0 and row[20] >= 0
+        for cols, k in ((row[18:20], 2), (row[20:22], 1)):
+            full = v[:, k] if v[0, k] >= 0 else -v[:, k]
+            assert np.allclose(cols, full[:2], atol=1e-12)
+    assert not O.extended_row(np.zeros((2, 3))).any()          # undefined -> zeros
