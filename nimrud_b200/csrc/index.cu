@@ -271,6 +271,9 @@ __device__ __forceinline__ void point_cell(const T *__restrict__ xyz, int64_t i,
 #define NBR_PTS 4
 #endif
 constexpr int PTS = NBR_PTS;
+#ifndef NBR_FILL_AGGREGATE
+#define NBR_FILL_AGGREGATE 1
+#endif
 
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -562,22 +565,39 @@ batch_fill_kernel(const T *__restrict__ xyz, int64_t n, const __grid_constant__ 
         if (l > 0) {
             int fresh = 0;
 #pragma unroll
-            for (int k = 0; k < PTS; ++k) fresh += (pend_old[k] & pend_bit[k]) == 0 && pend_bit[k];
+            for (int k = 0; k < PTS; ++k) fresh += __popc(pend_bit[k] & ~pend_old[k]);
             fresh = __reduce_add_sync(0xffffffffu, fresh);
             if ((threadIdx.x & 31) == 0 && fresh)
                 atomicAdd(reinterpret_cast<unsigned long long *>(counters + 64 * (l - 1) + 8), (unsigned long long)fresh);
         }
 #pragma unroll
         for (int k = 0; k < PTS; ++k) {
-            const bool need = (have[k] & bit[k]) == 0 && bit[k];
-            pend_old[k] = need ? atomicOr(w[k], bit[k]) : ~0u;
-            pend_bit[k] = bit[k];
+#if NBR_FILL_AGGREGATE
+            // the points are in cell order: on the coarser lattices the 32 points of a warp usually share one
+            // occupancy word.  then one lane sets all their bits with a single atomic (same-address atomics
+            // serialise in L2) and owns the voxels that were new
+            int same = 0;
+            __match_all_sync(0xffffffffu, (unsigned long long)w[k], &same);
+            if (same) {
+                const uint32_t bits = __reduce_or_sync(0xffffffffu, bit[k]);
+                const uint32_t seen = __reduce_and_sync(0xffffffffu, have[k]);      // every lane read the same word
+                const bool lead = (threadIdx.x & 31) == 0;
+                const bool need = lead && (bits & ~seen) != 0;
+                pend_old[k] = need ? atomicOr(w[k], bits) : ~0u;
+                pend_bit[k] = lead ? bits : 0u;
+            } else
+#endif
+            {
+                const bool need = (have[k] & bit[k]) == 0 && bit[k];
+                pend_old[k] = need ? atomicOr(w[k], bit[k]) : ~0u;
+                pend_bit[k] = bit[k];
+            }
         }
     }
     {
         int fresh = 0;
 #pragma unroll
-        for (int k = 0; k < PTS; ++k) fresh += (pend_old[k] & pend_bit[k]) == 0 && pend_bit[k];
+        for (int k = 0; k < PTS; ++k) fresh += __popc(pend_bit[k] & ~pend_old[k]);
         fresh = __reduce_add_sync(0xffffffffu, fresh);
         if ((threadIdx.x & 31) == 0 && fresh && B.n > 0)
             atomicAdd(reinterpret_cast<unsigned long long *>(counters + 64 * (B.n - 1) + 8), (unsigned long long)fresh);
