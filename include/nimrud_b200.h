@@ -128,7 +128,7 @@ int nbr_lattice_export(const nbr_lattice *lattice, int64_t *addresses, double *c
  * ---------------------------------------------------------------------------------------------- */
 /* fused radius query + covariance + eigensolve + feature emission for the scales that share this
  * lattice's edge (replaces minimal/multiscale.py:94-122 and minimal/features.py:14-57).
- * for radius j, row i, writes cols [col_offset + j*C, col_offset + (j+1)*C) of out, C = 4 or 16 by
+ * for radius j, row i, writes cols [col_offset + j*C, col_offset + (j+1)*C) of out, C = 4 or 26 by
  * descriptor_mask; out has `out_row_stride` elements per row and dtype out_dtype.
  * algorithm: 0 = automatic, 1 = exact per-candidate kernel, 2 = row-interval kernel. */
 int nbr_radius_features(const nbr_lattice *lattice, const void *query_xyz, int dtype, int64_t n_query,
@@ -212,6 +212,50 @@ int nbr_multiscale_features_tile(const void *sorted_xyz, const uint32_t *perm, i
                                  const double *global_lohi_host, const double *edges_host,
                                  const double *radii_host, int32_t n_scales, void *out, int out_dtype,
                                  int32_t descriptor_mask, int64_t *n_voxels_host, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * multi-GPU halo exchange over peer-mapped memory (NVLink / NVSwitch): no NCCL call, no count hand-shake.
+ * no reference counterpart; what it selects is nested_regions' search-space rule (inclusive box +- buffer
+ * radius, nimrud/utils/geometry.py:203-253, pinned by utils/tests/geometry_tests.py:353-389).
+ * every rank owns a MAILBOX (one cudaMalloc allocation: header + capacity_rows rows of 3 coordinates) that
+ * the other ranks map: through CUDA IPC between processes (nbr_mailbox_ipc_handle -> 64 bytes, exchanged by
+ * the host code -> nbr_mailbox_connect_ipc), or directly when several tiles live in one process
+ * (nbr_mailbox_connect_local; this is how the single-GPU tests drive the path).  world <= 16.
+ * one step, every call collective over the ranks and stream-ordered:
+ *   nbr_tile_box_publish  bounding box of this rank's tile (n may be 0) -> every peer's box table
+ *   nbr_tile_boxes_wait   all boxes of the step -> boxes_host[world][8] = lo[3], hi[3], n_points, 0.
+ *                         SYNCHRONISES the stream (the only host synchronisation of the exchange)
+ *   nbr_halo_push         one pass over the tile: the points inside peer d's box grown by h (inclusive) are
+ *                         stored into d's mailbox (remote atomic cursor + remote stores), then d is signalled
+ *   nbr_halo_wait         stream-ordered wait for every peer's signal; afterwards nbr_mailbox_rows() holds
+ *                         *nbr_mailbox_count_dev() rows (device-side count).  nbr_multiscale_features_tile_mb
+ *                         does this wait itself, after it has marked the tile's own bricks.
+ * rows that do not fit the destination's capacity are dropped and counted: the next nbr_tile_boxes_wait fails
+ * with NBR_ERR_UNSUPPORTED, nbr_mailbox_status reports {timeout, rows dropped, rows pushed last step}. */
+typedef struct nbr_mailbox nbr_mailbox;
+int nbr_mailbox_create(nbr_mailbox **out, int32_t rank, int32_t world, int dtype, int64_t capacity_rows);
+void nbr_mailbox_destroy(nbr_mailbox *mailbox);
+int nbr_mailbox_ipc_handle(const nbr_mailbox *mailbox, void *handle_out_64);
+int nbr_mailbox_connect_ipc(nbr_mailbox *mailbox, int32_t peer, const void *handle_64);
+int nbr_mailbox_connect_local(nbr_mailbox *mailbox, int32_t peer, const nbr_mailbox *peer_mailbox);
+int nbr_mailbox_set_peer_capacity(nbr_mailbox *mailbox, int32_t peer, int64_t capacity_rows);
+int nbr_tile_box_publish(nbr_mailbox *mailbox, const void *xyz, int dtype, int64_t n, void *stream);
+int nbr_tile_boxes_wait(nbr_mailbox *mailbox, double *boxes_host, void *stream);
+int nbr_halo_push(nbr_mailbox *mailbox, const void *xyz, int dtype, int64_t n, const double *boxes_host, double h,
+                  void *stream);
+int nbr_halo_wait(nbr_mailbox *mailbox, void *stream);
+const void *nbr_mailbox_rows(const nbr_mailbox *mailbox);
+const uint64_t *nbr_mailbox_count_dev(const nbr_mailbox *mailbox);
+int nbr_mailbox_status(const nbr_mailbox *mailbox, uint64_t *status3_host);
+/* tests / debugging: copies min(count, max_rows) rows of the last completed step to dst_dev, *n_rows_host = count.
+ * synchronises the stream. */
+int nbr_mailbox_read(const nbr_mailbox *mailbox, void *dst_dev, int64_t max_rows, int64_t *n_rows_host, void *stream);
+/* nbr_multiscale_features_tile with the halo taken from this rank's mailbox */
+int nbr_multiscale_features_tile_mb(const void *sorted_xyz, const uint32_t *perm, int dtype, int64_t n,
+                                    nbr_mailbox *mailbox, const double *local_lohi_host,
+                                    const double *global_lohi_host, const double *edges_host,
+                                    const double *radii_host, int32_t n_scales, void *out, int out_dtype,
+                                    int32_t descriptor_mask, int64_t *n_voxels_host, void *stream);
 
 /* counters for tests and benches: number of kernels this library has launched in this process. */
 int64_t nbr_kernel_launches(void);

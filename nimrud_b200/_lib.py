@@ -64,6 +64,23 @@ SIGNATURES = {
     "nbr_multiscale_features_tile": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_i64, c_vp, c_i64, ctypes.POINTER(c_f64),
                                                     ctypes.POINTER(c_f64), ctypes.POINTER(c_f64), ctypes.POINTER(c_f64),
                                                     c_i32, c_vp, ctypes.c_int, c_i32, ctypes.POINTER(c_i64), c_vp]),
+    "nbr_mailbox_create": (ctypes.c_int, [ctypes.POINTER(c_vp), c_i32, c_i32, ctypes.c_int, c_i64]),
+    "nbr_mailbox_destroy": (None, [c_vp]),
+    "nbr_mailbox_ipc_handle": (ctypes.c_int, [c_vp, c_vp]),
+    "nbr_mailbox_connect_ipc": (ctypes.c_int, [c_vp, c_i32, c_vp]),
+    "nbr_mailbox_connect_local": (ctypes.c_int, [c_vp, c_i32, c_vp]),
+    "nbr_mailbox_set_peer_capacity": (ctypes.c_int, [c_vp, c_i32, c_i64]),
+    "nbr_tile_box_publish": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_i64, c_vp]),
+    "nbr_tile_boxes_wait": (ctypes.c_int, [c_vp, ctypes.POINTER(c_f64), c_vp]),
+    "nbr_halo_push": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_i64, ctypes.POINTER(c_f64), c_f64, c_vp]),
+    "nbr_halo_wait": (ctypes.c_int, [c_vp, c_vp]),
+    "nbr_mailbox_rows": (c_vp, [c_vp]),
+    "nbr_mailbox_count_dev": (c_vp, [c_vp]),
+    "nbr_mailbox_read": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.POINTER(c_i64), c_vp]),
+    "nbr_mailbox_status": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_uint64)]),
+    "nbr_multiscale_features_tile_mb": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_i64, c_vp, ctypes.POINTER(c_f64),
+                                                       ctypes.POINTER(c_f64), ctypes.POINTER(c_f64), ctypes.POINTER(c_f64),
+                                                       c_i32, c_vp, ctypes.c_int, c_i32, ctypes.POINTER(c_i64), c_vp]),
     "nbr_multiscale_features": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_vp, ctypes.c_int, c_i64,
                                                ctypes.POINTER(c_f64), ctypes.POINTER(c_f64), c_i32, c_vp,
                                                ctypes.c_int, c_i32, ctypes.POINTER(c_f64), ctypes.POINTER(c_i64),

@@ -7,6 +7,7 @@
 
 #include "common.cuh"
 #include "lattice.cuh"
+#include "mailbox.cuh"
 #include "radius_rows.cuh"
 
 namespace nbr {
@@ -102,6 +103,7 @@ int compact_prefix_queries(const uint32_t *perm, const void *sorted, int dtype, 
                            void *sorted_q, cudaStream_t stream);
 int radius_sets(const Lattice *lat, const void *query, int dtype, int64_t nq, double radius, int64_t *offsets,
                 int32_t *indices, cudaStream_t stream);
+int halo_wait(Mailbox *M, cudaStream_t stream);
 
 static int check_cloud_dtype(int dtype, const char *who)
 {
@@ -203,11 +205,11 @@ struct Plan {
 
 int plan_create(Plan **out, const void *search, int s_dtype, int64_t ns, const double *edges, const double *radii,
                 int n_scales, int descriptor_mask, const double *global_lohi, const double *known_local_box,
-                cudaStream_t stream, const void *search2 = nullptr, int64_t ns2 = 0)
+                cudaStream_t stream, const void *search2 = nullptr, int64_t ns2 = 0, Mailbox *mailbox = nullptr)
 {
     NBR_TRY(check_cloud_dtype(s_dtype, "multiscale_features"));
     if (n_scales < 0) return fail(NBR_ERR_INVALID, "multiscale_features: negative number of scales");
-    if (ns + ns2 < 2) return fail(NBR_ERR_TOO_FEW_POINTS, "need at least 2 points to define a voxel grid");
+    if (ns + ns2 < 2 && !mailbox) return fail(NBR_ERR_TOO_FEW_POINTS, "need at least 2 points to define a voxel grid");
     if (!search || (n_scales > 0 && (!edges || !radii))) return fail(NBR_ERR_INVALID, "multiscale_features: null argument");
     for (int s = 0; s < n_scales; ++s) {
         if (!(edges[s] > 0)) return fail(NBR_ERR_INVALID, "multiscale_features: edge lengths must be > 0");
@@ -244,7 +246,7 @@ int plan_create(Plan **out, const void *search, int s_dtype, int64_t ns, const d
             nbr_grid grids[LATTICE_BATCH];
             Lattice *made[LATTICE_BATCH] = {nullptr};
             for (int k = 0; !rc && k < nb; ++k) rc = grid_from_bbox(lohi, lohi + 3, P->groups[base + k].edge, 3, &grids[k]);
-            if (!rc) rc = lattices_create_batch(made, nb, grids, search, s_dtype, ns, stream, global_lohi ? P->local_box : nullptr, search2, ns2);
+            if (!rc) rc = lattices_create_batch(made, nb, grids, search, s_dtype, ns, stream, global_lohi ? P->local_box : nullptr, search2, ns2, mailbox);
             if (!rc) for (int k = 0; k < nb; ++k) P->groups[base + k].lat = made[k];
         }
     }
@@ -513,6 +515,28 @@ extern "C" int nbr_multiscale_features_tile(const void *sorted_xyz, const uint32
     Plan *P = nullptr;
     NBR_TRY(plan_create(&P, sorted_xyz, dtype, n, edges_host, radii_host, n_scales, descriptor_mask, global_lohi_host,
                         local_lohi_host, (cudaStream_t)stream, halo_xyz, n_halo));
+    int rc = plan_run_sorted(P, sorted_xyz, dtype, perm, n, out, out_dtype, (cudaStream_t)stream);
+    if (rc == NBR_OK && n_voxels_host) rc = plan_voxel_counts(P, n_voxels_host);
+    delete P;
+    return rc;
+}
+
+// same, the halo comes from this rank's mailbox (mailbox.cu): the wait for the peers' pushes is stream-ordered
+// inside the lattice build and the number of halo points never visits the host
+extern "C" int nbr_multiscale_features_tile_mb(const void *sorted_xyz, const uint32_t *perm, int dtype, int64_t n,
+                                               nbr_mailbox *mailbox, const double *local_lohi_host,
+                                               const double *global_lohi_host, const double *edges_host,
+                                               const double *radii_host, int32_t n_scales, void *out, int out_dtype,
+                                               int32_t descriptor_mask, int64_t *n_voxels_host, void *stream)
+{
+    if (!mailbox || !local_lohi_host || !global_lohi_host || (n > 0 && (!sorted_xyz || !perm || !out)))
+        return fail(NBR_ERR_INVALID, "nbr_multiscale_features_tile_mb: null argument");
+    NBR_TRY(check_cloud_dtype(dtype, "nbr_multiscale_features_tile_mb"));
+    Mailbox *M = reinterpret_cast<Mailbox *>(mailbox);
+    if (n <= 0 || n_scales <= 0) return halo_wait(M, (cudaStream_t)stream);      // an empty tile still drains its mailbox
+    Plan *P = nullptr;
+    NBR_TRY(plan_create(&P, sorted_xyz, dtype, n, edges_host, radii_host, n_scales, descriptor_mask, global_lohi_host,
+                        local_lohi_host, (cudaStream_t)stream, nullptr, 0, M));
     int rc = plan_run_sorted(P, sorted_xyz, dtype, perm, n, out, out_dtype, (cudaStream_t)stream);
     if (rc == NBR_OK && n_voxels_host) rc = plan_voxel_counts(P, n_voxels_host);
     delete P;

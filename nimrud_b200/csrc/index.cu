@@ -10,6 +10,7 @@
 
 #include "common.cuh"
 #include "lattice.cuh"
+#include "mailbox.cuh"
 #include "scan.cuh"
 
 namespace nbr {
@@ -504,8 +505,11 @@ struct BatchDev {
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-batch_mark_kernel(const T *__restrict__ xyz, int64_t n, const __grid_constant__ BatchDev B, uint32_t *__restrict__ dir)
+batch_mark_kernel(const T *__restrict__ xyz, int64_t n_bound, const unsigned long long *__restrict__ n_dev,
+                  const __grid_constant__ BatchDev B, uint32_t *__restrict__ dir)
 {
+    // n_dev (optional): the number of points is only known on the device (halo mailbox); n_bound sizes the grid
+    const int64_t n = n_dev ? min(n_bound, (int64_t)*n_dev) : n_bound;
     const int64_t base = ((int64_t)blockIdx.x * PTS) * blockDim.x + threadIdx.x;
     for (int l = 0; l < B.n; ++l) {
         int64_t b[PTS];
@@ -530,9 +534,11 @@ batch_mark_kernel(const T *__restrict__ xyz, int64_t n, const __grid_constant__ 
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-batch_fill_kernel(const T *__restrict__ xyz, int64_t n, const __grid_constant__ BatchDev B, const uint32_t *__restrict__ dir,
+batch_fill_kernel(const T *__restrict__ xyz, int64_t n_bound, const unsigned long long *__restrict__ n_dev,
+                  const __grid_constant__ BatchDev B, const uint32_t *__restrict__ dir,
                   uint32_t *__restrict__ pool, unsigned char *__restrict__ counters)
 {
+    const int64_t n = n_dev ? min(n_bound, (int64_t)*n_dev) : n_bound;
     const int64_t base = ((int64_t)blockIdx.x * PTS) * blockDim.x + threadIdx.x;
     uint32_t pend_old[PTS], pend_bit[PTS];
 #pragma unroll
@@ -604,9 +610,20 @@ batch_fill_kernel(const T *__restrict__ xyz, int64_t n, const __grid_constant__ 
     }
 }
 
+int halo_wait(Mailbox *M, cudaStream_t stream);
+
 int lattices_create_batch(Lattice **out, int n_lat, const nbr_grid *grids, const void *xyz, int dtype, int64_t n,
-                          cudaStream_t stream, const double *local_lohi, const void *xyz2, int64_t n2)
+                          cudaStream_t stream, const double *local_lohi, const void *xyz2, int64_t n2, Mailbox *mailbox)
 {
+    // mailbox: the second part of the search cloud is what the peers pushed into this rank's halo mailbox; its
+    // size stays on the device, the grids are sized for the mailbox's capacity
+    const unsigned long long *n2_dev = nullptr;
+    if (mailbox) {
+        if (mailbox->dtype != dtype) return fail(NBR_ERR_INVALID, "lattices_create_batch: the mailbox holds another dtype");
+        xyz2 = mailbox->rows();
+        n2 = mailbox->capacity;
+        n2_dev = mailbox->count_dev();
+    }
     if (!out || !xyz || !grids || n_lat < 1 || n_lat > LATTICE_BATCH) return fail(NBR_ERR_INVALID, "lattices_create_batch: bad argument");
     if (dtype != NBR_F32 && dtype != NBR_F64) return fail(NBR_ERR_INVALID, "lattices_create_batch: bad dtype");
     if (n < 1) return fail(NBR_ERR_TOO_FEW_POINTS, "lattices_create_batch: empty search cloud");
@@ -655,11 +672,14 @@ int lattices_create_batch(Lattice **out, int n_lat, const nbr_grid *grids, const
 
     const void *parts[2] = {xyz, xyz2};
     const int64_t part_n[2] = {n, n2};
+    const unsigned long long *part_dev[2] = {nullptr, n2_dev};
     for (int p = 0; p < 2; ++p) {
+        // the tile's own bricks are marked while the peers' pushes are still in flight
+        if (p == 1 && mailbox) NBR_TRY(halo_wait(mailbox, stream));
         if (part_n[p] <= 0) continue;
         const unsigned pt_blocks = (unsigned)ceil_div(part_n[p], 256 * PTS);
-        if (dtype == NBR_F32) batch_mark_kernel<float><<<pt_blocks, 256, 0, stream>>>((const float *)parts[p], part_n[p], B, dir);
-        else                  batch_mark_kernel<double><<<pt_blocks, 256, 0, stream>>>((const double *)parts[p], part_n[p], B, dir);
+        if (dtype == NBR_F32) batch_mark_kernel<float><<<pt_blocks, 256, 0, stream>>>((const float *)parts[p], part_n[p], part_dev[p], B, dir);
+        else                  batch_mark_kernel<double><<<pt_blocks, 256, 0, stream>>>((const double *)parts[p], part_n[p], part_dev[p], B, dir);
         NBR_LAUNCHED();
     }
     NBR_TRY(flags_to_slots(dir, dir_total, n_bricks_total, stream));
@@ -668,8 +688,8 @@ int lattices_create_batch(Lattice **out, int n_lat, const nbr_grid *grids, const
     for (int p = 0; p < 2; ++p) {
         if (part_n[p] <= 0) continue;
         const unsigned pt_blocks = (unsigned)ceil_div(part_n[p], 256 * PTS);
-        if (dtype == NBR_F32) batch_fill_kernel<float><<<pt_blocks, 256, 0, stream>>>((const float *)parts[p], part_n[p], B, dir, pool, counters);
-        else                  batch_fill_kernel<double><<<pt_blocks, 256, 0, stream>>>((const double *)parts[p], part_n[p], B, dir, pool, counters);
+        if (dtype == NBR_F32) batch_fill_kernel<float><<<pt_blocks, 256, 0, stream>>>((const float *)parts[p], part_n[p], part_dev[p], B, dir, pool, counters);
+        else                  batch_fill_kernel<double><<<pt_blocks, 256, 0, stream>>>((const double *)parts[p], part_n[p], part_dev[p], B, dir, pool, counters);
         NBR_LAUNCHED();
     }
     for (int l = 0; l < n_lat; ++l) {

@@ -40,9 +40,10 @@ int lattice_create(Lattice **out, const void *xyz, int dtype, int64_t n, const n
 constexpr int LATTICE_BATCH = 8;
 // all lattices of `grids` over the same search cloud in one pass over the points (not INDEXED)
 // xyz2 / n2: optional second part of the search cloud (multi-GPU: the halo points next to the ordered tile)
+struct Mailbox;
 int lattices_create_batch(Lattice **out, int n_lat, const nbr_grid *grids, const void *xyz, int dtype, int64_t n,
                           cudaStream_t stream, const double *local_lohi = nullptr, const void *xyz2 = nullptr,
-                          int64_t n2 = 0);
+                          int64_t n2 = 0, Mailbox *mailbox = nullptr);
 int lattice_counts(const Lattice *L, int64_t *n_voxels, int64_t *n_bricks);
 int bbox(const void *xyz, int dtype, int64_t n, int ndim, double *lohi_dev, cudaStream_t stream);
 int grid_from_bbox(const double lo[3], const double hi[3], double edge, int ndim, nbr_grid *out);

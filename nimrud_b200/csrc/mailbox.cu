@@ -1,0 +1,445 @@
+// mailbox.cu -- multi-GPU halo exchange over peer-mapped memory (NVLink / NVSwitch), no NCCL call and no
+// count hand-shake on the path.
+//
+// every rank owns one device allocation, its MAILBOX: a header (cursor, per-peer flags, the table of tile
+// boxes) followed by rows of 3 coordinates.  the other ranks map it (CUDA IPC between processes; plain
+// pointers when several tiles live in one process, which is how the single-GPU tests drive this code).
+// per step (epoch):
+//   1. box publish : the rank's tile box (bounding box kernel, index.cu) is stored into slot [rank] of every
+//                    peer's box table, then the slot's epoch flag (system-scope release).
+//   2. box wait    : one warp spins until every slot carries this epoch, copies the table to pinned host
+//                    memory; the host synchronises HERE -- the only host synchronisation of the exchange (the
+//                    single-GPU path has the same one: the grid parameters are derived on the host from the
+//                    bounding box).
+//   3. halo push   : ONE pass over the tile: every point is tested against the box of every other tile grown
+//                    by the halo width (inclusive, the precedent is nested_regions, nimrud/utils/geometry.py:203-253);
+//                    a warp reserves rows in the destination's mailbox with one remote atomicAdd on its cursor
+//                    and stores the points straight into the peer's memory.  the last block of the grid raises
+//                    this rank's "done" flag in every peer's header.
+//   4. halo wait   : one warp spins until every peer's done flag carries this epoch; the cursor then is the
+//                    number of rows received (kept on the device: the lattice build reads it there).
+// a peer can only push epoch e+1 after it has seen this rank's box of epoch e+1, which this rank publishes
+// stream-ordered after every kernel of epoch e that reads the mailbox: one buffer is enough.
+// waits are bounded (NBR_MAILBOX_TIMEOUT_MS, default 20 s): a rank that never arrives raises a sticky flag
+// instead of hanging the GPU.
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "mailbox.cuh"
+
+namespace nbr {
+
+int bbox(const void *xyz, int dtype, int64_t n, int ndim, double *lohi_dev, cudaStream_t stream);
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+struct PeerHeaders {
+    MailboxHeader *h[MB_MAX_WORLD];
+};
+
+// lane d stores this rank's box into slot [rank] of peer d's table, then the slot's epoch
+__global__ void box_publish_kernel(const double *__restrict__ lohi, double n_points, PeerHeaders P, int rank, int world,
+                                   unsigned long long epoch)
+{
+    const int d = threadIdx.x;
+    if (d >= world) return;
+    MailboxHeader *H = P.h[d];
+    volatile double *slot = H->boxes[rank];
+    if (n_points > 0) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) slot[k] = lohi[k];
+    } else {
+        // an empty tile contributes the neutral box of min / max
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { slot[k] = INFINITY; slot[3 + k] = -INFINITY; }
+    }
+    slot[6] = n_points;
+    slot[7] = 0.0;
+    __threadfence_system();
+    st_release_sys(&H->box_epoch[rank], epoch);
+}
+
+// lane d waits for slot d; the table goes to pinned host memory [world][8] and status[0] = 1 on a timeout
+__global__ void box_wait_kernel(MailboxHeader *H, int world, unsigned long long epoch, double *host_boxes,
+                                unsigned long long *host_status, unsigned long long timeout_ns)
+{
+    const int d = threadIdx.x;
+    bool ok = true;
+    if (d < world) {
+        const unsigned long long t0 = global_ns();
+        while (ld_acquire_sys(&H->box_epoch[d]) < epoch) {
+            if (global_ns() - t0 > timeout_ns) { ok = false; break; }
+            __nanosleep(200);
+        }
+        if (ok) {
+            const volatile double *slot = H->boxes[d];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) host_boxes[d * 8 + k] = slot[k];
+        }
+    }
+    const bool all_ok = __all_sync(0xffffffffu, ok);
+    if (threadIdx.x == 0) {
+        if (!all_ok) H->timeout = 1;
+        host_status[0] = all_ok ? 0ull : 1ull;
+        __threadfence_system();
+    }
+}
+
+struct PushDev {
+    double lo[MB_MAX_WORLD][3], hi[MB_MAX_WORLD][3];   // grown boxes of the destinations (inverted: no point matches)
+    MailboxHeader *hdr[MB_MAX_WORLD];                  // destination headers (peer-mapped)
+    long long cap[MB_MAX_WORLD];                       // rows a destination's mailbox holds
+    int n_dst;
+    int rank;
+    unsigned long long epoch;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+halo_push_kernel(const T *__restrict__ xyz, int64_t n, const __grid_constant__ PushDev P, MailboxHeader *own)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt = lanemask_lt();
+    bool wrote = false;
+    // grid-stride over the tile, whole warps at a time (the votes below need every lane of the warp)
+    for (int64_t first = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) - lane; first < n; first += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = first + lane;
+        uint32_t m = 0;
+        T px = 0, py = 0, pz = 0;
+        if (i < n) {
+            px = xyz[i * 3 + 0]; py = xyz[i * 3 + 1]; pz = xyz[i * 3 + 2];
+            const double x = (double)px, y = (double)py, z = (double)pz;
+            for (int d = 0; d < P.n_dst; ++d)
+                if (x >= P.lo[d][0] && x <= P.hi[d][0] && y >= P.lo[d][1] && y <= P.hi[d][1] && z >= P.lo[d][2] && z <= P.hi[d][2])
+                    m |= 1u << d;
+        }
+        uint32_t any = __reduce_or_sync(0xffffffffu, m);
+        while (any) {
+            const int d = __ffs(any) - 1;
+            any &= any - 1;
+            const bool mine = (m >> d) & 1u;
+            const uint32_t votes = __ballot_sync(0xffffffffu, mine);
+            const int leader = __ffs(votes) - 1;
+            unsigned long long base = 0;
+            // one remote atomic per warp and destination reserves the rows
+            if (lane == leader) base = atomicAdd_system(&P.hdr[d]->cursor, (unsigned long long)__popc(votes));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (mine) {
+                const long long row = (long long)base + __popc(votes & lt);
+                if (row < P.cap[d]) {
+                    T *dst = reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(P.hdr[d]) + MB_HEADER_BYTES) + row * 3;
+                    dst[0] = px; dst[1] = py; dst[2] = pz;
+                    wrote = true;
+                }
+            }
+        }
+    }
+    // the last block to finish raises this rank's done flag at every destination: every writer fences its remote
+    // stores at system scope before its block takes a ticket, the last block fences again before the flags
+    if (wrote) __threadfence_system();
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long ticket = atomicAdd(&own->blocks_done, 1ull);
+        last = ticket == (unsigned long long)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last) {
+        __threadfence_system();
+        if (threadIdx.x == 0) own->blocks_done = 0;
+        if ((int)threadIdx.x < P.n_dst) st_release_sys(&P.hdr[threadIdx.x]->halo_done[P.rank], P.epoch);
+    }
+}
+
+// lane d waits for peer d's done flag; then the cursor is the number of rows received
+__global__ void halo_wait_kernel(MailboxHeader *H, int rank, int world, unsigned long long epoch, long long cap,
+                                 unsigned long long *host_status, unsigned long long timeout_ns)
+{
+    const int d = threadIdx.x;
+    bool ok = true;
+    if (d < world && d != rank) {
+        const unsigned long long t0 = global_ns();
+        while (ld_acquire_sys(&H->halo_done[d]) < epoch) {
+            if (global_ns() - t0 > timeout_ns) { ok = false; break; }
+            __nanosleep(200);
+        }
+    }
+    const bool all_ok = __all_sync(0xffffffffu, ok);
+    if (threadIdx.x == 0) {
+        const unsigned long long c = all_ok ? ld_acquire_sys(&H->cursor) : 0ull;
+        H->count = c < (unsigned long long)cap ? c : (unsigned long long)cap;
+        if (c > (unsigned long long)cap) { H->overflow += c - (unsigned long long)cap; host_status[1] = H->overflow; }
+        if (!all_ok) { H->timeout = 1; host_status[0] = 1ull; }
+        host_status[2] = c;
+        H->cursor = 0;                       // nobody pushes again before this rank's next box is out
+        __threadfence_system();
+    }
+}
+
+static unsigned long long timeout_ns()
+{
+    static const unsigned long long ns = [] {
+        const char *e = getenv("NBR_MAILBOX_TIMEOUT_MS");
+        const double ms = e ? atof(e) : 20000.0;
+        return (unsigned long long)((ms > 0 ? ms : 20000.0) * 1e6);
+    }();
+    return ns;
+}
+
+Mailbox::~Mailbox()
+{
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(device);
+    for (int d = 0; d < MB_MAX_WORLD; ++d)
+        if (opened[d] && peer[d]) cudaIpcCloseMemHandle(peer[d]);
+    if (base) cudaFree(base);
+    if (host_boxes) cudaFreeHost(host_boxes);
+    if (box_dev) cudaFree(box_dev);
+    cudaSetDevice(cur);
+}
+
+static size_t elem_bytes(int dtype) { return dtype == NBR_F32 ? 4 : 8; }
+
+int halo_wait(Mailbox *M, cudaStream_t stream)
+{
+    unsigned long long *status = reinterpret_cast<unsigned long long *>(M->host_boxes + 8 * MB_MAX_WORLD);
+    halo_wait_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<MailboxHeader *>(M->base), M->rank, M->world, M->epoch,
+                                           (long long)M->capacity, status, timeout_ns());
+    NBR_LAUNCHED();
+    return NBR_OK;
+}
+
+}  // namespace nbr
+
+using namespace nbr;
+
+extern "C" int nbr_mailbox_create(nbr_mailbox **out, int32_t rank, int32_t world, int dtype, int64_t capacity_rows)
+{
+    if (!out || world < 1 || world > MB_MAX_WORLD || rank < 0 || rank >= world || capacity_rows < 0)
+        return fail(NBR_ERR_INVALID, "nbr_mailbox_create: bad argument (world <= 16)");
+    if (dtype != NBR_F32 && dtype != NBR_F64) return fail(NBR_ERR_INVALID, "nbr_mailbox_create: bad dtype");
+    Mailbox *M = new Mailbox();
+    M->rank = rank; M->world = world; M->dtype = dtype; M->capacity = capacity_rows;
+    cudaError_t e = cudaGetDevice(&M->device);
+    const size_t bytes = MB_HEADER_BYTES + (size_t)std::max<int64_t>(capacity_rows, 1) * 3 * elem_bytes(dtype);
+    // cudaMalloc, not the stream-ordered pool: pool memory cannot be exported through cudaIpcGetMemHandle
+    if (e == cudaSuccess) e = cudaMalloc(&M->base, bytes);
+    if (e == cudaSuccess) e = cudaMemset(M->base, 0, MB_HEADER_BYTES);
+    if (e == cudaSuccess) e = cudaMalloc(&M->box_dev, sizeof(double) * 8);
+    if (e == cudaSuccess) e = cudaHostAlloc(&M->host_boxes, sizeof(double) * 8 * MB_MAX_WORLD + 64, cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        delete M;
+        return fail(NBR_ERR_CUDA, std::string("nbr_mailbox_create: ") + cudaGetErrorString(e));
+    }
+    memset(M->host_boxes, 0, sizeof(double) * 8 * MB_MAX_WORLD + 64);
+    M->peer[rank] = M->base;
+    *out = reinterpret_cast<nbr_mailbox *>(M);
+    return NBR_OK;
+}
+
+extern "C" void nbr_mailbox_destroy(nbr_mailbox *mb) { delete reinterpret_cast<Mailbox *>(mb); }
+
+extern "C" int nbr_mailbox_ipc_handle(const nbr_mailbox *mb, void *handle_out_64)
+{
+    const Mailbox *M = reinterpret_cast<const Mailbox *>(mb);
+    if (!M || !handle_out_64) return fail(NBR_ERR_INVALID, "nbr_mailbox_ipc_handle: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaIpcMemHandle_t h;
+    NBR_CUDA(cudaIpcGetMemHandle(&h, M->base));
+    memcpy(handle_out_64, &h, 64);
+    return NBR_OK;
+}
+
+extern "C" int nbr_mailbox_connect_ipc(nbr_mailbox *mb, int32_t peer, const void *handle_64)
+{
+    Mailbox *M = reinterpret_cast<Mailbox *>(mb);
+    if (!M || !handle_64 || peer < 0 || peer >= M->world || peer == M->rank)
+        return fail(NBR_ERR_INVALID, "nbr_mailbox_connect_ipc: bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle_64, 64);
+    void *p = nullptr;
+    NBR_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    M->peer[peer] = reinterpret_cast<unsigned char *>(p);
+    M->opened[peer] = true;
+    return NBR_OK;
+}
+
+// tiles of one process (tests, or several tiles per GPU): the peer's allocation is used directly
+extern "C" int nbr_mailbox_connect_local(nbr_mailbox *mb, int32_t peer, const nbr_mailbox *peer_mb)
+{
+    Mailbox *M = reinterpret_cast<Mailbox *>(mb);
+    const Mailbox *Q = reinterpret_cast<const Mailbox *>(peer_mb);
+    if (!M || !Q || peer < 0 || peer >= M->world || peer == M->rank || Q->rank != peer || Q->world != M->world ||
+        Q->dtype != M->dtype)
+        return fail(NBR_ERR_INVALID, "nbr_mailbox_connect_local: bad argument");
+    if (Q->device != M->device) {
+        int can = 0;
+        NBR_CUDA(cudaDeviceCanAccessPeer(&can, M->device, Q->device));
+        if (!can) return fail(NBR_ERR_UNSUPPORTED, "nbr_mailbox_connect_local: no peer access between the devices");
+        cudaError_t e = cudaDeviceEnablePeerAccess(Q->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+            return fail(NBR_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+        cudaGetLastError();
+    }
+    M->peer[peer] = Q->base;
+    M->opened[peer] = false;
+    M->capacity_of[peer] = Q->capacity;
+    return NBR_OK;
+}
+
+extern "C" int nbr_mailbox_set_peer_capacity(nbr_mailbox *mb, int32_t peer, int64_t capacity_rows)
+{
+    Mailbox *M = reinterpret_cast<Mailbox *>(mb);
+    if (!M || peer < 0 || peer >= M->world || capacity_rows < 0) return fail(NBR_ERR_INVALID, "nbr_mailbox_set_peer_capacity: bad argument");
+    M->capacity_of[peer] = capacity_rows;
+    return NBR_OK;
+}
+
+static int check_connected(const Mailbox *M, const char *who)
+{
+    for (int d = 0; d < M->world; ++d)
+        if (!M->peer[d]) return fail(NBR_ERR_INVALID, std::string(who) + ": mailbox is not connected to every peer");
+    return NBR_OK;
+}
+
+// step 1: this rank's tile box (n may be 0: the neutral box) goes to every peer.  starts a new epoch.
+extern "C" int nbr_tile_box_publish(nbr_mailbox *mb, const void *xyz, int dtype, int64_t n, void *stream)
+{
+    Mailbox *M = reinterpret_cast<Mailbox *>(mb);
+    if (!M || (n > 0 && !xyz) || n < 0) return fail(NBR_ERR_INVALID, "nbr_tile_box_publish: bad argument");
+    if (dtype != M->dtype) return fail(NBR_ERR_INVALID, "nbr_tile_box_publish: dtype differs from the mailbox's");
+    NBR_TRY(check_connected(M, "nbr_tile_box_publish"));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n > 0) {
+        PhaseTimer t(PHASE_BBOX, s);
+        NBR_TRY(bbox(xyz, dtype, n, 3, M->box_dev, s));
+    }
+    M->epoch += 1;
+    PeerHeaders P;
+    for (int d = 0; d < MB_MAX_WORLD; ++d) P.h[d] = reinterpret_cast<MailboxHeader *>(M->peer[d]);
+    box_publish_kernel<<<1, 32, 0, s>>>(M->box_dev, (double)n, P, M->rank, M->world, M->epoch);
+    NBR_LAUNCHED();
+    return NBR_OK;
+}
+
+// step 2: every rank's box of this epoch -> boxes_host[world][8] = lo[3], hi[3], n_points, 0.  SYNCHRONISES the stream.
+extern "C" int nbr_tile_boxes_wait(nbr_mailbox *mb, double *boxes_host, void *stream)
+{
+    Mailbox *M = reinterpret_cast<Mailbox *>(mb);
+    if (!M || !boxes_host) return fail(NBR_ERR_INVALID, "nbr_tile_boxes_wait: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long *status = reinterpret_cast<unsigned long long *>(M->host_boxes + 8 * MB_MAX_WORLD);
+    box_wait_kernel<<<1, 32, 0, s>>>(reinterpret_cast<MailboxHeader *>(M->base), M->world, M->epoch, M->host_boxes, status,
+                                     timeout_ns());
+    NBR_LAUNCHED();
+    NBR_CUDA(cudaStreamSynchronize(s));
+    if (status[0]) return fail(NBR_ERR_CUDA, "nbr_tile_boxes_wait: a peer did not publish its tile box in time");
+    if (status[1]) return fail(NBR_ERR_UNSUPPORTED, "halo mailbox overflow in an earlier step: " + std::to_string(status[1]) +
+                                                        " rows were dropped; create the mailbox with a larger capacity");
+    memcpy(boxes_host, M->host_boxes, sizeof(double) * 8 * M->world);
+    return NBR_OK;
+}
+
+// step 3: one pass over the tile, points inside peer d's box grown by h go straight into d's mailbox
+extern "C" int nbr_halo_push(nbr_mailbox *mb, const void *xyz, int dtype, int64_t n, const double *boxes_host, double h,
+                             void *stream)
+{
+    Mailbox *M = reinterpret_cast<Mailbox *>(mb);
+    if (!M || !boxes_host || (n > 0 && !xyz) || n < 0 || !(h >= 0)) return fail(NBR_ERR_INVALID, "nbr_halo_push: bad argument");
+    if (dtype != M->dtype) return fail(NBR_ERR_INVALID, "nbr_halo_push: dtype differs from the mailbox's");
+    NBR_TRY(check_connected(M, "nbr_halo_push"));
+    PushDev P;
+    memset(&P, 0, sizeof(P));
+    P.rank = M->rank;
+    P.epoch = M->epoch;
+    const double *mine = boxes_host + 8 * M->rank;
+    for (int d = 0; d < M->world; ++d) {
+        if (d == M->rank) continue;
+        const int k = P.n_dst++;
+        const double *b = boxes_host + 8 * d;
+        bool overlap = n > 0 && b[6] > 0;
+        for (int a = 0; a < 3; ++a) {
+            P.lo[k][a] = b[a] - h;
+            P.hi[k][a] = b[3 + a] + h;
+            overlap = overlap && !(P.lo[k][a] > mine[3 + a]) && !(P.hi[k][a] < mine[a]);
+        }
+        if (!overlap)
+            for (int a = 0; a < 3; ++a) { P.lo[k][a] = 1.0; P.hi[k][a] = -1.0; }     // matches nothing
+        P.hdr[k] = reinterpret_cast<MailboxHeader *>(M->peer[d]);
+        P.cap[k] = M->capacity_of[d] > 0 ? M->capacity_of[d] : M->capacity;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 256), (int64_t)device_sm_count() * 8));
+    MailboxHeader *own = reinterpret_cast<MailboxHeader *>(M->base);
+    if (dtype == NBR_F32) halo_push_kernel<float><<<blocks, 256, 0, s>>>((const float *)xyz, n, P, own);
+    else                  halo_push_kernel<double><<<blocks, 256, 0, s>>>((const double *)xyz, n, P, own);
+    NBR_LAUNCHED();
+    return NBR_OK;
+}
+
+// step 4 (stream-ordered, no host synchronisation): afterwards nbr_mailbox_rows / nbr_mailbox_count_dev are valid
+extern "C" int nbr_halo_wait(nbr_mailbox *mb, void *stream)
+{
+    Mailbox *M = reinterpret_cast<Mailbox *>(mb);
+    if (!M) return fail(NBR_ERR_INVALID, "nbr_halo_wait: null argument");
+    return halo_wait(M, (cudaStream_t)stream);
+}
+
+extern "C" const void *nbr_mailbox_rows(const nbr_mailbox *mb)
+{
+    const Mailbox *M = reinterpret_cast<const Mailbox *>(mb);
+    return M ? M->base + MB_HEADER_BYTES : nullptr;
+}
+
+extern "C" const uint64_t *nbr_mailbox_count_dev(const nbr_mailbox *mb)
+{
+    const Mailbox *M = reinterpret_cast<const Mailbox *>(mb);
+    return M ? reinterpret_cast<const uint64_t *>(&reinterpret_cast<const MailboxHeader *>(M->base)->count) : nullptr;
+}
+
+// debugging / tests: the rows of the last completed step -> dst_dev (device, room for max_rows rows); SYNCHRONISES
+extern "C" int nbr_mailbox_read(const nbr_mailbox *mb, void *dst_dev, int64_t max_rows, int64_t *n_rows_host, void *stream)
+{
+    const Mailbox *M = reinterpret_cast<const Mailbox *>(mb);
+    if (!M || !dst_dev || !n_rows_host || max_rows < 0) return fail(NBR_ERR_INVALID, "nbr_mailbox_read: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long count = 0;
+    NBR_CUDA(cudaMemcpyAsync(&count, M->count_dev(), sizeof(count), cudaMemcpyDeviceToHost, s));
+    NBR_CUDA(cudaStreamSynchronize(s));
+    const int64_t rows = std::min<int64_t>((int64_t)count, max_rows);
+    if (rows > 0)
+        NBR_CUDA(cudaMemcpyAsync(dst_dev, M->rows(), (size_t)rows * 3 * elem_bytes(M->dtype), cudaMemcpyDeviceToDevice, s));
+    NBR_CUDA(cudaStreamSynchronize(s));
+    *n_rows_host = (int64_t)count;
+    return NBR_OK;
+}
+
+// host view of the status words written by the wait kernels: [0] timeout, [1] rows dropped so far (overflow),
+// [2] rows pushed to this rank in the last completed epoch.  valid after the stream was synchronised.
+extern "C" int nbr_mailbox_status(const nbr_mailbox *mb, uint64_t *status3_host)
+{
+    const Mailbox *M = reinterpret_cast<const Mailbox *>(mb);
+    if (!M || !status3_host) return fail(NBR_ERR_INVALID, "nbr_mailbox_status: null argument");
+    const volatile unsigned long long *status = reinterpret_cast<const unsigned long long *>(M->host_boxes + 8 * MB_MAX_WORLD);
+    for (int k = 0; k < 3; ++k) status3_host[k] = status[k];
+    return NBR_OK;
+}

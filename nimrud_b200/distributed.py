@@ -13,10 +13,21 @@ spatial tile of the cloud (query == search inside the tile).
     3. the single-GPU path on (queries = tile, search = tile + halo, lattice anchored globally).
     4. optional all-gather-v of the feature rows.
 
-There is no data-path collective besides 2 and 4.  The host logic (box reduction, halo selection,
-exchange) is backend-agnostic torch.distributed, so it is tested on CPU with gloo; the compute
-function is the CUDA path unless a test injects another one.
+There is no data-path collective besides 2 and 4.
+
+Two transports for step 1 + 2:
+  * CUDA tensors (the product path): HALO MAILBOXES over peer-mapped memory (csrc/mailbox.cu).  every rank's tile
+    box goes into every peer's box table, the halo points are stored straight into the destination's
+    mailbox by one pass over the tile (remote atomic cursor + remote stores over NVLink), flags signal
+    completion.  no NCCL call, no count hand-shake, ONE host synchronisation per step (the boxes -- the
+    single-GPU path has the same one for its bounding box).  the same code drives several tiles inside
+    one process (`process_tiles_local`), which is how the single-GPU tests prove tile + halo == unpartitioned.
+  * any other tensors (gloo tests on CPU, NBR_HALO=nccl): backend-agnostic torch.distributed collectives
+    (all-gather of the boxes, all-to-all-v of counts and points).
 """
+import ctypes
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -29,6 +40,9 @@ def halo_width(edge_lengths, radii):
 
 def tile_box(cloud):
     """(lo, hi) float64 tensors (3,) on the cloud's device (min / max are exact in the cloud's own dtype)."""
+    if cloud.shape[0] == 0:
+        inf = torch.full((3,), float("inf"), dtype=torch.float64, device=cloud.device)
+        return inf, -inf                                           # the neutral box of min / max
     if cloud.is_cuda and cloud.dtype in (torch.float32, torch.float64) and cloud.is_contiguous() and cloud.shape[0] > 0:
         from . import _lib
         from ._util import ptr, stream_ptr
@@ -190,69 +204,286 @@ def _side_stream(device):
     return _side_streams[key]
 
 
-def _process_tile_cuda(cloud, edge_lengths, radii, out, out_dtype, group):
-    """the CUDA tile path: the tile is ordered on a side stream while the halo exchange is in flight; the
-    lattices are then built from the ordered tile + the received halo points, the tile's points are the queries."""
-    import ctypes
+# --------------------------------------------------------------------------------------------------
+# halo mailboxes (csrc/mailbox.cu)
+# --------------------------------------------------------------------------------------------------
+def default_capacity(n_local):
+    """rows a rank's mailbox can receive per step: NBR_HALO_CAPACITY, or max(4M, the tile's own size)."""
+    env = os.environ.get("NBR_HALO_CAPACITY")
+    return int(env) if env else max(4 << 20, int(n_local))
+
+
+class HaloMailbox(object):
+    """this rank's mailbox and its view of the peers' (one per (group, device, dtype); reused by every step)."""
+
+    def __init__(self, rank, world, device, dtype, capacity_rows):
+        from . import _lib
+        self.rank, self.world, self.device, self.dtype = int(rank), int(world), torch.device(device), dtype
+        self.capacity = int(capacity_rows)
+        self.code = _lib.F32 if dtype == torch.float32 else _lib.F64
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().nbr_mailbox_create(ctypes.byref(handle), self.rank, self.world, self.code, self.capacity))
+        self.handle = handle
+        self.boxes = np.zeros((self.world, 8), dtype=np.float64)
+
+    def ipc_handle(self):
+        from . import _lib
+        buf = ctypes.create_string_buffer(64)
+        _lib.check(_lib.lib().nbr_mailbox_ipc_handle(self.handle, buf))
+        return bytes(buf.raw)
+
+    @classmethod
+    def connect_group(cls, device, dtype, capacity_rows, group=None):
+        """collective: every rank creates its mailbox and maps every peer's through CUDA IPC."""
+        from . import _lib
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        mb = cls(rank, world, device, dtype, capacity_rows)
+        infos = [None] * world
+        dist.all_gather_object(infos, (mb.ipc_handle(), mb.capacity), group=group)
+        with torch.cuda.device(mb.device):
+            for peer, (h, cap) in enumerate(infos):
+                if peer == rank:
+                    continue
+                _lib.check(_lib.lib().nbr_mailbox_connect_ipc(mb.handle, peer, ctypes.c_char_p(h)))
+                _lib.check(_lib.lib().nbr_mailbox_set_peer_capacity(mb.handle, peer, int(cap)))
+        return mb
+
+    @classmethod
+    def local_set(cls, world, device, dtype, capacity_rows):
+        """`world` mailboxes in this process (several tiles on one device, or one per visible device)."""
+        from . import _lib
+        devices = device if isinstance(device, (list, tuple)) else [device] * world
+        boxes = [cls(r, world, devices[r], dtype, capacity_rows) for r in range(world)]
+        for a in boxes:
+            with torch.cuda.device(a.device):
+                for b in boxes:
+                    if a is not b:
+                        _lib.check(_lib.lib().nbr_mailbox_connect_local(a.handle, b.rank, b.handle))
+        return boxes
+
+    def status(self):
+        """{timeout, dropped, pushed}: valid after the device was synchronised."""
+        from . import _lib
+        st = (ctypes.c_uint64 * 3)()
+        _lib.check(_lib.lib().nbr_mailbox_status(self.handle, st))
+        return {"timeout": int(st[0]), "dropped": int(st[1]), "pushed": int(st[2])}
+
+    def received(self):
+        """(m, 3) tensor: the halo points of the last completed step (synchronises; for tests and debugging)."""
+        from . import _lib
+        from ._util import ptr, stream_ptr
+        out = torch.empty((self.capacity, 3), dtype=self.dtype, device=self.device)
+        n = ctypes.c_int64(0)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().nbr_mailbox_read(self.handle, ptr(out), self.capacity, ctypes.byref(n), stream_ptr(self.device)))
+        return out[:n.value]
+
+    def close(self):
+        from . import _lib
+        if getattr(self, "handle", None):
+            with torch.cuda.device(self.device):
+                torch.cuda.synchronize(self.device)
+                _lib.lib().nbr_mailbox_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- the four steps
+    def publish(self, cloud):
+        from . import _lib
+        from ._util import ptr, stream_ptr
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().nbr_tile_box_publish(self.handle, ptr(cloud) if cloud.shape[0] else None, self.code,
+                                                       int(cloud.shape[0]), stream_ptr(self.device)))
+
+    def wait_boxes(self):
+        """(world, 8) float64: lo, hi, n_points, 0 of every tile.  the step's one host synchronisation."""
+        from . import _lib
+        from ._util import stream_ptr
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().nbr_tile_boxes_wait(self.handle, self.boxes.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                                      stream_ptr(self.device)))
+        return self.boxes
+
+    def push(self, cloud, h):
+        from . import _lib
+        from ._util import ptr, stream_ptr
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().nbr_halo_push(self.handle, ptr(cloud) if cloud.shape[0] else None, self.code,
+                                                int(cloud.shape[0]), self.boxes.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                                float(h), stream_ptr(self.device)))
+
+
+_mailboxes = {}
+
+
+def _group_mailbox(cloud, group):
+    key = (id(group) if group is not None else 0, cloud.device.index, cloud.dtype)
+    mb = _mailboxes.get(key)
+    if mb is None:
+        mb = HaloMailbox.connect_group(cloud.device, cloud.dtype, default_capacity(cloud.shape[0]), group)
+        _mailboxes[key] = mb
+    return mb
+
+
+def release_mailboxes():
+    """collective: free the cached mailboxes (call before destroy_process_group)."""
+    for mb in list(_mailboxes.values()):
+        mb.close()
+    _mailboxes.clear()
+
+
+def _tile_geometry(boxes, rank, edge_lengths, radii):
+    """host side of a step: global box, this tile's box grown by the halo width, the brick origin of the order."""
+    from . import _lib
+    h = halo_width(edge_lengths, radii)
+    filled = boxes[:, 6] > 0
+    if not filled.any():
+        raise ValueError("need at least 2 points to define a voxel grid")
+    g_lo = boxes[filled, 0:3].min(0)
+    g_hi = boxes[filled, 3:6].max(0)
+    glob = np.ascontiguousarray(np.concatenate([g_lo, g_hi]), dtype=np.float64)
+    mine = np.ascontiguousarray(boxes[rank, :6], dtype=np.float64)
+    local = np.ascontiguousarray(np.concatenate([np.maximum(mine[:3] - h, g_lo), np.minimum(mine[3:] + h, g_hi)]))
+    origin = np.zeros(3, dtype=np.float64)
+    if boxes[rank, 6] > 0:
+        f64p = ctypes.POINTER(ctypes.c_double)
+        _lib.check(_lib.lib().nbr_brick_origin(glob.ctypes.data_as(f64p), local.ctypes.data_as(f64p),
+                                               float(min(edge_lengths)), origin.ctypes.data_as(f64p)))
+    return h, glob, mine, local, origin
+
+
+def _check_out(out, n, n_scales, np_out, device):
+    from .multiscale import _TORCH_OUT
+    if out is None:
+        return torch.zeros((n, 4 * n_scales), dtype=_TORCH_OUT[np_out], device=device)
+    if (tuple(out.shape) != (n, 4 * n_scales) or out.dtype != _TORCH_OUT[np_out] or not out.is_cuda
+            or out.device != device or not out.is_contiguous()):
+        raise ValueError("out has the wrong shape, dtype or device")
+    return out
+
+
+def _order_tile(cloud, mine, origin, finest, stream):
+    """perm, ordered copy of the tile in the feature kernels' query order, on `stream`."""
+    from . import _lib
+    from ._util import ptr
+    f64p = ctypes.POINTER(ctypes.c_double)
+    n = int(cloud.shape[0])
+    perm = torch.empty(n, dtype=torch.int32, device=cloud.device)
+    ordered = torch.empty_like(cloud)
+    code = _lib.F32 if cloud.dtype == torch.float32 else _lib.F64
+    if n:
+        _lib.check(_lib.lib().nbr_order_cloud(ptr(cloud), code, n, mine.ctypes.data_as(f64p), origin.ctypes.data_as(f64p),
+                                              finest, ptr(perm), ptr(ordered), ctypes.c_void_p(stream.cuda_stream)))
+    return perm, ordered
+
+
+def _tile_features_mb(mb, ordered, perm, local, glob, edge_lengths, radii, out, out_code):
     from . import _lib
     from ._util import ptr, stream_ptr
-    from .multiscale import _out_code, _TORCH_OUT
-    lib = _lib.lib()
-    code = _lib.F32 if cloud.dtype == torch.float32 else _lib.F64
-    n = int(cloud.shape[0])
-    rank = dist.get_rank(group)
-    gathered = gather_boxes(cloud, group)
-    all_boxes = gathered[0]
-    h = halo_width(edge_lengths, radii)
-    g_lo, g_hi = all_boxes[:, :3].min(0).values, all_boxes[:, 3:].max(0).values
-    # every halo point this rank can receive lies inside its own box grown by h
-    local_lo = torch.maximum(all_boxes[rank, :3] - h, g_lo)
-    local_hi = torch.minimum(all_boxes[rank, 3:] + h, g_hi)
     f64p = ctypes.POINTER(ctypes.c_double)
-    glob = np.ascontiguousarray(torch.cat([g_lo, g_hi]).numpy(), dtype=np.float64)
-    local = np.ascontiguousarray(torch.cat([local_lo, local_hi]).numpy(), dtype=np.float64)
-    mine = np.ascontiguousarray(all_boxes[rank].numpy(), dtype=np.float64)
-    finest = float(min(edge_lengths))
-    origin = np.zeros(3, dtype=np.float64)
-    _lib.check(lib.nbr_brick_origin(glob.ctypes.data_as(f64p), local.ctypes.data_as(f64p), finest,
-                                    origin.ctypes.data_as(f64p)))
-    np_out, out_code = _out_code(out_dtype)
-    n_scales = len(radii)
     edges_arr, edges_p = _lib.f64_array(list(edge_lengths))
     radii_arr, radii_p = _lib.f64_array(list(radii))
+    n = int(ordered.shape[0])
+    _lib.check(_lib.lib().nbr_multiscale_features_tile_mb(
+        ptr(ordered) if n else None, ptr(perm) if n else None, mb.code, n, mb.handle, local.ctypes.data_as(f64p),
+        glob.ctypes.data_as(f64p), edges_p, radii_p, len(radii), ptr(out) if n else None, out_code, 0, None,
+        stream_ptr(ordered.device)))
+
+
+def _process_tile_cuda(cloud, edge_lengths, radii, out, out_dtype, group):
+    """the CUDA tile path over halo mailboxes: box table -> (host) -> push || order -> lattices + features.
+    returns (features, boxes)."""
+    from .multiscale import _out_code
+    np_out, out_code = _out_code(out_dtype)
+    n = int(cloud.shape[0])
+    out = _check_out(out, n, len(radii), np_out, cloud.device)
+    mb = _group_mailbox(cloud, group)
+    mb.publish(cloud)
+    boxes = mb.wait_boxes()
+    h, glob, mine, local, origin = _tile_geometry(boxes, mb.rank, edge_lengths, radii)
     with torch.cuda.device(cloud.device):
         main = torch.cuda.current_stream(cloud.device)
         side = _side_stream(cloud.device)
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            perm = torch.empty(n, dtype=torch.int32, device=cloud.device)
-            ordered = torch.empty_like(cloud)
-            _lib.check(lib.nbr_order_cloud(ptr(cloud), code, n, mine.ctypes.data_as(f64p), origin.ctypes.data_as(f64p),
-                                           finest, ptr(perm), ptr(ordered), ctypes.c_void_p(side.cuda_stream)))
-        halo, _, _ = exchange_halo(cloud, edge_lengths, radii, group, gathered=gathered)
+            perm, ordered = _order_tile(cloud, mine, origin, float(min(edge_lengths)), side)
+        mb.push(cloud, h)                                   # main stream, concurrent with the ordering
         main.wait_stream(side)
         perm.record_stream(main)
         ordered.record_stream(main)
-        if out is None:
-            out = torch.zeros((n, 4 * n_scales), dtype=_TORCH_OUT[np_out], device=cloud.device)
-        _lib.check(lib.nbr_multiscale_features_tile(
-            ptr(ordered), ptr(perm), code, n, ptr(halo) if halo.numel() else None, int(halo.shape[0]),
-            local.ctypes.data_as(f64p), glob.ctypes.data_as(f64p), edges_p, radii_p, n_scales, ptr(out), out_code, 0,
-            None, stream_ptr(cloud.device)))
-    return out
+        _tile_features_mb(mb, ordered, perm, local, glob, edge_lengths, radii, out, out_code)
+    return out, boxes
+
+
+def process_tiles_local(clouds, edge_lengths, radii, out_dtype=np.float32, mailboxes=None, capacity_rows=None):
+    """
+    several tiles in ONE process (one device, or one tile per visible device): the same mailbox path as the
+    multi-process run, every step issued for all tiles before the next one.  returns the list of per-tile
+    feature tensors (rows in each tile's own order).  with one device this is also a way to process a cloud
+    tile by tile; the single-GPU tests use it to prove tile + halo == unpartitioned.
+    """
+    from .multiscale import _out_code
+    assert len(edge_lengths) == len(radii), "edge_lengths and radii should be equal-length sequences."
+    np_out, out_code = _out_code(out_dtype)
+    world = len(clouds)
+    own = mailboxes is None
+    if own:
+        cap = capacity_rows if capacity_rows is not None else default_capacity(max(int(c.shape[0]) for c in clouds))
+        mailboxes = HaloMailbox.local_set(world, [c.device for c in clouds], clouds[0].dtype, cap)
+    try:
+        for mb, c in zip(mailboxes, clouds):
+            mb.publish(c)
+        geo = []
+        for mb, c in zip(mailboxes, clouds):
+            boxes = mb.wait_boxes()
+            geo.append(_tile_geometry(boxes, mb.rank, edge_lengths, radii))
+        for mb, c, g in zip(mailboxes, clouds, geo):
+            mb.push(c, g[0])
+        outs = []
+        for mb, c, (h, glob, mine, local, origin) in zip(mailboxes, clouds, geo):
+            with torch.cuda.device(c.device):
+                stream = torch.cuda.current_stream(c.device)
+                perm, ordered = _order_tile(c, mine, origin, float(min(edge_lengths)), stream)
+                out = _check_out(None, int(c.shape[0]), len(radii), np_out, c.device)
+                _tile_features_mb(mb, ordered, perm, local, glob, edge_lengths, radii, out, out_code)
+            outs.append(out)
+        for mb in mailboxes:
+            torch.cuda.synchronize(mb.device)
+            st = mb.status()
+            if st["timeout"] or st["dropped"]:
+                raise RuntimeError("halo mailbox of tile %d: %s" % (mb.rank, st))
+        return outs
+    finally:
+        if own:
+            for mb in mailboxes:
+                mb.close()
+
+
+def _use_mailboxes(cloud):
+    return (cloud.is_cuda and cloud.dtype in (torch.float32, torch.float64) and cloud.is_contiguous()
+            and os.environ.get("NBR_HALO", "mailbox") != "nccl")
 
 
 def process_tile(cloud, edge_lengths, radii, out=None, out_dtype=np.float32, gather=False, group=None,
                  compute=None):
     """
-    features of this rank's tile (n_local, 4*S).  `cloud`: (n_local, 3) tensor on this rank's device.
+    features of this rank's tile (n_local, 4*S).  `cloud`: (n_local, 3) tensor on this rank's device; a rank may
+    hold an empty tile (it still takes part in every collective step).
     gather=True: returns the rows of every rank, concatenated in rank order, on every rank.
     compute(query, search, edges, radii, (lo, hi) numpy, out_dtype, out) -> features; default = CUDA path.
     """
     assert len(edge_lengths) == len(radii), "edge_lengths and radii should be equal-length sequences."
-    if (compute is None and cloud.is_cuda and cloud.dtype in (torch.float32, torch.float64) and cloud.is_contiguous()
-            and cloud.shape[0] >= 2):
-        feats = _process_tile_cuda(cloud, edge_lengths, radii, out, out_dtype, group)
+    world = dist.get_world_size(group)
+    sizes = None
+    if compute is None and _use_mailboxes(cloud) and world <= 16:
+        feats, boxes = _process_tile_cuda(cloud, edge_lengths, radii, out, out_dtype, group)
+        sizes = [int(v) for v in boxes[:, 6]]
     else:
         halo, (g_lo, g_hi), _ = exchange_halo(cloud, edge_lengths, radii, group)
         search = torch.cat([cloud, halo], 0) if halo.numel() else cloud
@@ -260,19 +491,40 @@ def process_tile(cloud, edge_lengths, radii, out=None, out_dtype=np.float32, gat
         # the queries are handed over as the first rows of the search buffer: the CUDA path then orders tile + halo
         # once, builds the lattices from the ordered copy and keeps only the tile's points as queries
         query = search[:cloud.shape[0]]
-        feats = (compute or _gpu_compute)(query, search, edge_lengths, radii, bbox, out_dtype, out)
+        if cloud.shape[0] == 0:
+            from .multiscale import _TORCH_OUT
+            feats = torch.zeros((0, 4 * len(radii)), dtype=_TORCH_OUT[np.dtype(out_dtype).type], device=cloud.device)
+        else:
+            feats = (compute or _gpu_compute)(query, search, edge_lengths, radii, bbox, out_dtype, out)
     if not gather:
         return feats
+    return gather_rows(feats, sizes, group)
+
+
+def gather_rows(feats, sizes=None, group=None):
+    """all-gather-v of the feature rows into ONE preallocated (sum n, C) tensor, rank order.  sizes: every
+    rank's row count if the caller already has it (the mailbox path carries it in the box table)."""
     world = dist.get_world_size(group)
-    n_local = torch.tensor([feats.shape[0]], dtype=torch.int64, device=feats.device)
-    sizes = [torch.empty_like(n_local) for _ in range(world)]
-    dist.all_gather(sizes, n_local, group=group)
-    sizes = [int(s.item()) for s in sizes]
-    # all-gather-v: pad every contribution to the largest tile, gather, drop the padding
-    cap = max(sizes)
-    padded = feats.contiguous()
-    if padded.shape[0] < cap:
-        padded = torch.cat([padded, padded.new_zeros((cap - padded.shape[0], feats.shape[1]))], 0)
-    parts = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(parts, padded, group=group)
-    return torch.cat([p[:s] for p, s in zip(parts, sizes)], 0)
+    feats = feats.contiguous()
+    if sizes is None:
+        n_local = torch.tensor([feats.shape[0]], dtype=torch.int64, device=feats.device)
+        got = [torch.empty_like(n_local) for _ in range(world)]
+        dist.all_gather(got, n_local, group=group)
+        sizes = [int(v.item()) for v in got]
+    total = torch.empty((sum(sizes), feats.shape[1]), dtype=feats.dtype, device=feats.device)
+    if len(set(sizes)) == 1 and feats.is_cuda:
+        dist.all_gather_into_tensor(total, feats, group=group)        # equal tiles: straight into the result
+    elif not feats.is_cuda:
+        # gloo has no uneven all-gather: pad every contribution to the largest tile
+        cap = max(sizes)
+        padded = feats if feats.shape[0] == cap else torch.cat([feats, feats.new_zeros((cap - feats.shape[0], feats.shape[1]))], 0)
+        parts = [torch.empty((cap, feats.shape[1]), dtype=feats.dtype) for _ in range(world)]
+        dist.all_gather(parts, padded.contiguous(), group=group)
+        offs = np.concatenate([[0], np.cumsum(sizes)])
+        for r in range(world):
+            total[int(offs[r]):int(offs[r + 1])] = parts[r][:sizes[r]]
+    else:
+        offs = np.concatenate([[0], np.cumsum(sizes)])
+        views = [total[int(offs[r]):int(offs[r + 1])] for r in range(world)]
+        dist.all_gather(views, feats, group=group)                     # uneven: one broadcast per rank into its rows
+    return total

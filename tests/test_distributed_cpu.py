@@ -79,3 +79,24 @@ def test_tile_plus_halo_equals_unpartitioned(tmp_path):
 def test_halo_width_rule():
     from nimrud_b200 import distributed as nd
     assert nd.halo_width((0.1, 1.6), (0.3, 4.8)) >= 4.8 + 0.8
+
+
+def test_select_halo_matches_nested_regions_golden():
+    """the host selection rule against golden vectors from the reference's nested_regions
+    (nimrud/utils/geometry.py:203-253): inclusive box +- buffer radius; a region without points selects nothing."""
+    import importlib.util
+    from conftest import GOLDEN, load_golden
+    from nimrud_b200 import distributed as nd
+    spec = importlib.util.spec_from_file_location("make_golden_regions", os.path.join(GOLDEN, "make_golden_regions.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    query, search = mod.clouds()
+    g = load_golden("regions")
+    lo, hi = torch.from_numpy(g["lo"]), torch.from_numpy(g["hi"])
+    for dtype in (torch.float64, torch.float32):      # the float32 path rounds the bounds outward: same set here
+        idx = nd.select_halo(torch.from_numpy(search).to(dtype), lo, hi, float(g["buffer"]))
+        assert np.array_equal(idx.numpy(), g["search_idx"])
+    idx = nd.select_halo(torch.from_numpy(query), lo, hi, 0.0)
+    assert np.array_equal(idx.numpy(), g["query_idx"])
+    far = torch.full((3,), 100.0, dtype=torch.float64)
+    assert nd.select_halo(torch.from_numpy(search), far, far + 10, float(g["buffer"])).numel() == 0
