@@ -167,6 +167,94 @@ def hbm_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def seam_check(nd, multiscale, dist, cloud, out, edges, radii, rank, world):
+    """rank 0 recomputes, on ONE GPU and against the union of all tiles, the rows of its queries that lie within the
+    halo width of its tile's border, and compares them bit for bit with what the tile path produced."""
+    import torch
+    n = cloud.shape[0]
+    union = torch.empty((world * n, 3), dtype=cloud.dtype, device=cloud.device)
+    dist.all_gather_into_tensor(union, cloud)
+    result = None
+    if rank == 0:
+        h = nd.halo_width(edges, radii)
+        # the queries that can need foreign points: those inside another tile's box grown by h
+        near_mask = torch.zeros(n, dtype=torch.bool, device=cloud.device)
+        for r in range(1, world):
+            other = union[r * n:(r + 1) * n]
+            lo, hi = other.min(0).values - h, other.max(0).values + h
+            near_mask |= ((cloud >= lo) & (cloud <= hi)).all(1)
+        near = near_mask.nonzero()[:, 0]
+        if near.numel() > 2_000_000:
+            near = near[:2_000_000]
+        ref = multiscale.process_single_core(cloud[near].contiguous(), union, edges, radii, out_dtype=np.float32)
+        identical = bool(torch.equal(ref, out[near]))
+        result = {"rows": int(near.numel()), "identical": identical,
+                  "how": "rank 0's queries inside another tile's box grown by h = %.2f, recomputed on one GPU against "
+                         "the union of all %d tiles" % (h, world)}
+    del union
+    return result
+
+
+C4_EDGES = (0.5, 1.0, 2.0, 4.0, 8.0)
+C4_RADII = (1.5, 3.0, 6.0, 12.0, 24.0)
+
+
+def run_config4(args, nd, multiscale, dist, synth, lib, rank, world, dev):
+    """BASELINE configs[3]: a 100M-point aerial tile, 5 scales (edge 0.5..8 m, r = 3e), split into `world` spatial
+    tiles with halo exchange: STRONG scaling (the total is fixed).  N = 1 runs the whole tile on one GPU."""
+    import ctypes
+    import torch
+    from nimrud_b200 import _lib
+    total = args.config4_points
+    n = total // world
+    extent = math.sqrt(n / 8.0)
+    cols = 2 if world >= 2 else 1
+    cloud = synth.aerial_tile(n, seed=22 + rank, device=dev, origin=((rank % cols) * extent, (rank // cols) * extent))
+    out = torch.empty((n, 4 * len(C4_RADII)), dtype=torch.float32, device=dev)
+    edges_arr, edges_p = _lib.f64_array(C4_EDGES)
+    radii_arr, radii_p = _lib.f64_array(C4_RADII)
+
+    def step():
+        if world > 1:
+            nd.process_tile(cloud, C4_EDGES, C4_RADII, out=out, gather=False)
+        else:
+            _lib.check(lib.nbr_multiscale_features(
+                ctypes.c_void_p(cloud.data_ptr()), _lib.F32, n, ctypes.c_void_p(cloud.data_ptr()), _lib.F32, n,
+                edges_p, radii_p, len(C4_RADII), ctypes.c_void_p(out.data_ptr()), _lib.F32, 0, None, None,
+                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    steps = max(1, min(args.steps, 5))
+    for _ in range(3):
+        step()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms /= steps
+    block = {"workload": "BASELINE configs[3]: %dM-point synthetic aerial-LiDAR tile, 5 scales (edge 0.5..8 m, r = 3e), "
+                         "%d spatial tile(s) with halo exchange" % (total // 1_000_000, world),
+             "scaling": "strong", "points_total": n * world, "n_gpus": world, "ms_per_step": ms, "steps": steps,
+             "value": n * world * len(C4_RADII) / (ms * 1e-3), "unit": UNIT}
+    if world > 1:
+        block["multi_gpu_check"] = seam_check(nd, multiscale, dist, cloud, out, C4_EDGES, C4_RADII, rank, world)
+    del cloud, out
+    torch.cuda.empty_cache()
+    return block
+
+
 def gpu_arm(args, rank, world, local_rank):
     import ctypes
     import torch
@@ -198,7 +286,7 @@ def gpu_arm(args, rank, world, local_rank):
 
     def step(want_counts=False):
         if world > 1:
-            return nd.process_tile(cloud, EDGES, RADII, out=out, gather=False)
+            return nd.process_tile(cloud, EDGES, RADII, out=out, gather=False, voxel_counts=counts if want_counts else None)
         cp = counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)) if want_counts else None
         _lib.check(lib.nbr_multiscale_features(
             ctypes.c_void_p(cloud.data_ptr()), _lib.F32, n, ctypes.c_void_p(cloud.data_ptr()), _lib.F32, n,
@@ -213,7 +301,7 @@ def gpu_arm(args, rank, world, local_rank):
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
-    step(want_counts=(world == 1))                       # voxel counts for the roofline's rho_s
+    step(want_counts=True)                               # voxel counts for the roofline's rho_s
     torch.cuda.synchronize()
 
     # ---- timed region: device-resident inputs
@@ -221,7 +309,7 @@ def gpu_arm(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     lib.nbr_timing_enable(1)
-    phases = (ctypes.c_double * 4)()
+    phases = (ctypes.c_double * 8)()
     lib.nbr_timing_read(phases)                          # clear
     launches0 = lib.nbr_kernel_launches()
     barrier()
@@ -287,21 +375,54 @@ def gpu_arm(args, rank, world, local_rank):
                "value_float32_out": results["f32"][0], "d2h_bytes_per_step_float32_out": int(results["f32"][1]),
                "steps": e2e_steps, "timer": "host wall clock around the synchronous host-buffer call"}
 
+    # ---- N > 1: the step with the final feature all-gather, and the seam check
+    with_gather, seam = None, None
+    if world > 1:
+        g_steps = max(1, min(args.steps, 5))
+        gathered = nd.process_tile(cloud, EDGES, RADII, out=out, gather=True)
+        barrier()
+        ev0.record()
+        for _ in range(g_steps):
+            gathered = nd.process_tile(cloud, EDGES, RADII, out=out, gather=True)
+        ev1.record()
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        g_ms = float(t.item()) / g_steps
+        with_gather = {"ms_per_step": g_ms, "value": world * n * ns / (g_ms * 1e-3), "unit": UNIT, "steps": g_steps,
+                       "gathered_bytes_per_rank": int(gathered.numel() * gathered.element_size()),
+                       "how": "all_gather_into_tensor of the (n, 20) float32 rows into one preallocated (N*n, 20) result on every rank"}
+        same = bool(torch.equal(gathered[rank * n:(rank + 1) * n], out))
+        del gathered
+        seam = seam_check(nd, multiscale, dist, cloud, out, EDGES, RADII, rank, world)
+        if seam is not None:
+            seam["gathered_rows_match_local"] = same
+
+    # ---- BASELINE configs[3]: 100M-point aerial tile split over the ranks (strong scaling)
+    config4 = None
+    if not args.no_config4:
+        config4 = run_config4(args, nd if world > 1 else None, multiscale, dist, synth, lib, rank, world, dev)
+
     # the sampler covers the device-resident timed region and the e2e region (both under load)
     clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        vox = torch.from_numpy(counts.astype(np.int64)).to(dev)
+        dist.all_reduce(vox)
+        counts_all = vox.cpu().numpy()
+    else:
+        counts_all = counts
     if rank != 0:
         if dist is not None:
+            nd.release_mailboxes()
             dist.destroy_process_group()
         return
 
     # ---- roofline of the dominant kernel (fused feature kernels, all scales of one step)
     peak, peak_src = hbm_peak()
     feat_ms = phases[3] / args.steps
-    if world == 1:
-        rho = counts / float(n)
-    else:
-        rho = np.zeros(ns)
-    algo_bytes = float(sum(n * (28.0 + 12.0 * r) for r in rho)) if world == 1 else float(n * ns * 28.0)
+    # rho_s = voxels a rank's lattices hold (tile + halo at N > 1, summed over the ranks) / queries; bytes per rank
+    rho = counts_all / float(n * world)
+    algo_bytes = float(sum(n * (28.0 + 12.0 * r) for r in rho))
     achieved = algo_bytes / (feat_ms * 1e-3) / 1e9 if feat_ms > 0 else 0.0
     traffic, traffic_src = None, None
     try:
@@ -320,7 +441,9 @@ def gpu_arm(args, rank, world, local_rank):
                 "bytes_per_point_scale": "28 + 12*rho_s (SURVEY.md 8d); rho_s = unique voxels / queries = %s"
                                          % [round(float(r), 4) for r in rho],
                 "phase_ms_per_step": {"bbox": phases[0] / args.steps, "index": phases[1] / args.steps,
-                                      "order": phases[2] / args.steps, "features": feat_ms}}
+                                      "order": phases[2] / args.steps, "features": feat_ms,
+                                      "tile_boxes": phases[4] / args.steps, "halo_push": phases[5] / args.steps,
+                                      "halo_wait_inside_index": phases[6] / args.steps}}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu:
@@ -335,10 +458,19 @@ def gpu_arm(args, rank, world, local_rank):
         "vs_baseline": None, "dtype": "int32 moments + f64 membership/eigen, f32 out", "data": "synthetic",
         "config": workload_config(n, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu_baseline,
-        "voxels_per_scale": [int(c) for c in counts] if world == 1 else None,
+        "voxels_per_scale": [int(c) for c in counts_all],
     }
+    if world > 1:
+        line["with_gather"] = with_gather
+        line["multi_gpu_check"] = seam
+        line["halo_transport"] = os.environ.get("NBR_HALO", "mailbox") + \
+            (": peer-mapped mailboxes over NVLink (csrc/mailbox.cu), one host synchronisation per step"
+             if os.environ.get("NBR_HALO", "mailbox") != "nccl" else ": NCCL all-gather + all-to-all-v")
+    if config4 is not None:
+        line["config4"] = config4
     print(json.dumps(line), flush=True)
     if dist is not None:
+        nd.release_mailboxes()
         dist.destroy_process_group()
 
 
@@ -351,6 +483,8 @@ def main():
     ap.add_argument("--points", type=int, default=10_000_000)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-config4", action="store_true")
+    ap.add_argument("--config4-points", type=int, default=100_000_000)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

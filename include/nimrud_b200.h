@@ -257,14 +257,22 @@ int nbr_multiscale_features_tile_mb(const void *sorted_xyz, const uint32_t *perm
                                     const double *radii_host, int32_t n_scales, void *out, int out_dtype,
                                     int32_t descriptor_mask, int64_t *n_voxels_host, void *stream);
 
+/* one whole step of a rank in one call: publish + wait (host synchronisation) -> push -> query order of the tile ->
+ * lattices from tile + mailbox -> features of the tile's points, rows in the tile's own order.
+ * boxes_host_out: optional [world][8] (lo, hi, n_points, 0 of every tile). */
+int nbr_tile_step(nbr_mailbox *mailbox, const void *xyz, int dtype, int64_t n, const double *edges_host,
+                  const double *radii_host, int32_t n_scales, void *out, int out_dtype, int32_t descriptor_mask,
+                  double *boxes_host_out, int64_t *n_voxels_host, void *stream);
+
 /* counters for tests and benches: number of kernels this library has launched in this process. */
 int64_t nbr_kernel_launches(void);
 
 /* optional device timing of the whole-path drivers, CUDA events on the launching stream.
  * nbr_timing_read synchronises on the recorded events, writes the accumulated milliseconds of the
- * NBR_TIMING_PHASES phases [bounding box, index build, query ordering, feature kernels] since the
+ * NBR_TIMING_PHASES phases [bounding box, index build, query ordering, feature kernels, tile box exchange, halo
+ * push, wait for the peers' halo (also inside the index build's span), reserved] since the
  * previous read, and clears them. */
-#define NBR_TIMING_PHASES 4
+#define NBR_TIMING_PHASES 8
 void nbr_timing_enable(int on);
 int nbr_timing_read(double *ms_out);
 

@@ -81,6 +81,8 @@ SIGNATURES = {
     "nbr_multiscale_features_tile_mb": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_i64, c_vp, ctypes.POINTER(c_f64),
                                                        ctypes.POINTER(c_f64), ctypes.POINTER(c_f64), ctypes.POINTER(c_f64),
                                                        c_i32, c_vp, ctypes.c_int, c_i32, ctypes.POINTER(c_i64), c_vp]),
+    "nbr_tile_step": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_i64, ctypes.POINTER(c_f64), ctypes.POINTER(c_f64), c_i32, c_vp,
+                                     ctypes.c_int, c_i32, ctypes.POINTER(c_f64), ctypes.POINTER(c_i64), c_vp]),
     "nbr_multiscale_features": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_vp, ctypes.c_int, c_i64,
                                                ctypes.POINTER(c_f64), ctypes.POINTER(c_f64), c_i32, c_vp,
                                                ctypes.c_int, c_i32, ctypes.POINTER(c_f64), ctypes.POINTER(c_i64),

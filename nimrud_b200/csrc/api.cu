@@ -543,6 +543,58 @@ extern "C" int nbr_multiscale_features_tile_mb(const void *sorted_xyz, const uin
     return rc;
 }
 
+// one whole step of a rank in ONE call: box table (the step's only host synchronisation) -> halo push -> query
+// order of the tile -> lattices from tile + mailbox -> features.  nothing but C++ runs between the synchronisation
+// and the next launches, so the GPU idles for microseconds there, not for an interpreter's worth of time.
+// h = max_s(r_s + e_s / 2) (+ slack): every voxel centre within r_s of a query of the tile holds a point within h
+// per axis of the tile's box.  boxes_host_out (optional): [world][8] = lo, hi, n_points, 0 of every tile.
+extern "C" int nbr_tile_step(nbr_mailbox *mailbox, const void *xyz, int dtype, int64_t n, const double *edges_host,
+                             const double *radii_host, int32_t n_scales, void *out, int out_dtype,
+                             int32_t descriptor_mask, double *boxes_host_out, int64_t *n_voxels_host, void *stream)
+{
+    if (!mailbox || n < 0 || n_scales < 0 || (n_scales > 0 && (!edges_host || !radii_host)) || (n > 0 && (!xyz || !out)))
+        return fail(NBR_ERR_INVALID, "nbr_tile_step: bad argument");
+    NBR_TRY(check_cloud_dtype(dtype, "nbr_tile_step"));
+    if (out_dtype != NBR_F32 && out_dtype != NBR_F64) return fail(NBR_ERR_INVALID, "nbr_tile_step: bad out_dtype");
+    Mailbox *M = reinterpret_cast<Mailbox *>(mailbox);
+    cudaStream_t s = (cudaStream_t)stream;
+    double boxes[MB_MAX_WORLD][8];
+    NBR_TRY(nbr_tile_box_publish(mailbox, xyz, dtype, n, stream));
+    NBR_TRY(nbr_tile_boxes_wait(mailbox, &boxes[0][0], stream));
+    if (boxes_host_out) memcpy(boxes_host_out, boxes, sizeof(double) * 8 * M->world);
+    double h = 0.0, finest = 0.0;
+    for (int k = 0; k < n_scales; ++k) {
+        if (!(edges_host[k] > 0) || !(radii_host[k] >= 0)) return fail(NBR_ERR_INVALID, "nbr_tile_step: edge lengths must be > 0, radii >= 0");
+        h = std::max(h, radii_host[k] + edges_host[k] / 2);
+        finest = k == 0 ? edges_host[k] : std::min(finest, edges_host[k]);
+    }
+    h *= 1.0 + 1e-6;
+    NBR_TRY(nbr_halo_push(mailbox, xyz, dtype, n, &boxes[0][0], h, stream));
+    if (n == 0 || n_scales == 0) return halo_wait(M, s);                    // an empty tile still drains its mailbox
+    double glob[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    for (int r = 0; r < M->world; ++r)
+        if (boxes[r][6] > 0)
+            for (int a = 0; a < 3; ++a) {
+                glob[a] = std::min(glob[a], boxes[r][a]);
+                glob[3 + a] = std::max(glob[3 + a], boxes[r][3 + a]);
+            }
+    double local[6], origin[3];
+    const double *mine = boxes[M->rank];
+    for (int a = 0; a < 3; ++a) {
+        local[a] = std::max(mine[a] - h, glob[a]);
+        local[3 + a] = std::min(mine[3 + a] + h, glob[3 + a]);
+    }
+    NBR_TRY(brick_origin(glob, local, finest, origin));
+    Scratch perm, sorted;
+    NBR_TRY(order_queries(xyz, dtype, n, mine, finest, origin, perm, sorted, s));
+    Plan *P = nullptr;
+    NBR_TRY(plan_create(&P, sorted.ptr, dtype, n, edges_host, radii_host, n_scales, descriptor_mask, glob, local, s, nullptr, 0, M));
+    int rc = plan_run_sorted(P, sorted.ptr, dtype, perm.as<uint32_t>(), n, out, out_dtype, s);
+    if (rc == NBR_OK && n_voxels_host) rc = plan_voxel_counts(P, n_voxels_host);
+    delete P;
+    return rc;
+}
+
 static size_t elem_size(int dtype) { return dtype == NBR_F32 ? 4 : 8; }
 
 // HOST buffers.  the search cloud goes up once, the lattices are built once, then the queries are

@@ -61,7 +61,7 @@ int device_sm_count();
 bool first_use_on_device(std::atomic<uint64_t> &seen);
 
 // optional per-phase device timing (CUDA events on the launching stream); see nbr_timing_*
-enum Phase { PHASE_BBOX = 0, PHASE_INDEX = 1, PHASE_ORDER = 2, PHASE_FEATURES = 3, PHASE_COUNT = 4 };
+enum Phase { PHASE_BBOX = 0, PHASE_INDEX = 1, PHASE_ORDER = 2, PHASE_FEATURES = 3, PHASE_BOXES = 4, PHASE_PUSH = 5, PHASE_HALO_WAIT = 6, PHASE_COUNT = 8 };
 struct PhaseTimer {
     int phase;
     cudaStream_t stream;

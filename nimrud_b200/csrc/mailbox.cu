@@ -220,6 +220,7 @@ static size_t elem_bytes(int dtype) { return dtype == NBR_F32 ? 4 : 8; }
 
 int halo_wait(Mailbox *M, cudaStream_t stream)
 {
+    PhaseTimer tw(PHASE_HALO_WAIT, stream);
     unsigned long long *status = reinterpret_cast<unsigned long long *>(M->host_boxes + 8 * MB_MAX_WORLD);
     halo_wait_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<MailboxHeader *>(M->base), M->rank, M->world, M->epoch,
                                            (long long)M->capacity, status, timeout_ns());
@@ -334,6 +335,7 @@ extern "C" int nbr_tile_box_publish(nbr_mailbox *mb, const void *xyz, int dtype,
         NBR_TRY(bbox(xyz, dtype, n, 3, M->box_dev, s));
     }
     M->epoch += 1;
+    PhaseTimer tb(PHASE_BOXES, s);
     PeerHeaders P;
     for (int d = 0; d < MB_MAX_WORLD; ++d) P.h[d] = reinterpret_cast<MailboxHeader *>(M->peer[d]);
     box_publish_kernel<<<1, 32, 0, s>>>(M->box_dev, (double)n, P, M->rank, M->world, M->epoch);
@@ -348,9 +350,12 @@ extern "C" int nbr_tile_boxes_wait(nbr_mailbox *mb, double *boxes_host, void *st
     if (!M || !boxes_host) return fail(NBR_ERR_INVALID, "nbr_tile_boxes_wait: null argument");
     cudaStream_t s = (cudaStream_t)stream;
     unsigned long long *status = reinterpret_cast<unsigned long long *>(M->host_boxes + 8 * MB_MAX_WORLD);
-    box_wait_kernel<<<1, 32, 0, s>>>(reinterpret_cast<MailboxHeader *>(M->base), M->world, M->epoch, M->host_boxes, status,
-                                     timeout_ns());
-    NBR_LAUNCHED();
+    {
+        PhaseTimer tb(PHASE_BOXES, s);
+        box_wait_kernel<<<1, 32, 0, s>>>(reinterpret_cast<MailboxHeader *>(M->base), M->world, M->epoch, M->host_boxes, status,
+                                         timeout_ns());
+        NBR_LAUNCHED();
+    }
     NBR_CUDA(cudaStreamSynchronize(s));
     if (status[0]) return fail(NBR_ERR_CUDA, "nbr_tile_boxes_wait: a peer did not publish its tile box in time");
     if (status[1]) return fail(NBR_ERR_UNSUPPORTED, "halo mailbox overflow in an earlier step: " + std::to_string(status[1]) +
@@ -390,6 +395,7 @@ extern "C" int nbr_halo_push(nbr_mailbox *mb, const void *xyz, int dtype, int64_
     cudaStream_t s = (cudaStream_t)stream;
     const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 256), (int64_t)device_sm_count() * 8));
     MailboxHeader *own = reinterpret_cast<MailboxHeader *>(M->base);
+    PhaseTimer tp(PHASE_PUSH, s);
     if (dtype == NBR_F32) halo_push_kernel<float><<<blocks, 256, 0, s>>>((const float *)xyz, n, P, own);
     else                  halo_push_kernel<double><<<blocks, 256, 0, s>>>((const double *)xyz, n, P, own);
     NBR_LAUNCHED();

@@ -383,7 +383,7 @@ def _order_tile(cloud, mine, origin, finest, stream):
     return perm, ordered
 
 
-def _tile_features_mb(mb, ordered, perm, local, glob, edge_lengths, radii, out, out_code):
+def _tile_features_mb(mb, ordered, perm, local, glob, edge_lengths, radii, out, out_code, voxel_counts=None):
     from . import _lib
     from ._util import ptr, stream_ptr
     f64p = ctypes.POINTER(ctypes.c_double)
@@ -392,33 +392,30 @@ def _tile_features_mb(mb, ordered, perm, local, glob, edge_lengths, radii, out, 
     n = int(ordered.shape[0])
     _lib.check(_lib.lib().nbr_multiscale_features_tile_mb(
         ptr(ordered) if n else None, ptr(perm) if n else None, mb.code, n, mb.handle, local.ctypes.data_as(f64p),
-        glob.ctypes.data_as(f64p), edges_p, radii_p, len(radii), ptr(out) if n else None, out_code, 0, None,
+        glob.ctypes.data_as(f64p), edges_p, radii_p, len(radii), ptr(out) if n else None, out_code, 0,
+        voxel_counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)) if voxel_counts is not None and n else None,
         stream_ptr(ordered.device)))
 
 
-def _process_tile_cuda(cloud, edge_lengths, radii, out, out_dtype, group):
-    """the CUDA tile path over halo mailboxes: box table -> (host) -> push || order -> lattices + features.
-    returns (features, boxes)."""
+def _process_tile_cuda(cloud, edge_lengths, radii, out, out_dtype, group, voxel_counts=None):
+    """the CUDA tile path over halo mailboxes, one C call per step (nbr_tile_step): box table -> (host) -> push ->
+    order -> lattices + features.  returns (features, boxes)."""
+    from . import _lib
+    from ._util import ptr, stream_ptr
     from .multiscale import _out_code
     np_out, out_code = _out_code(out_dtype)
     n = int(cloud.shape[0])
     out = _check_out(out, n, len(radii), np_out, cloud.device)
     mb = _group_mailbox(cloud, group)
-    mb.publish(cloud)
-    boxes = mb.wait_boxes()
-    h, glob, mine, local, origin = _tile_geometry(boxes, mb.rank, edge_lengths, radii)
+    edges_arr, edges_p = _lib.f64_array(list(edge_lengths))
+    radii_arr, radii_p = _lib.f64_array(list(radii))
     with torch.cuda.device(cloud.device):
-        main = torch.cuda.current_stream(cloud.device)
-        side = _side_stream(cloud.device)
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            perm, ordered = _order_tile(cloud, mine, origin, float(min(edge_lengths)), side)
-        mb.push(cloud, h)                                   # main stream, concurrent with the ordering
-        main.wait_stream(side)
-        perm.record_stream(main)
-        ordered.record_stream(main)
-        _tile_features_mb(mb, ordered, perm, local, glob, edge_lengths, radii, out, out_code)
-    return out, boxes
+        _lib.check(_lib.lib().nbr_tile_step(
+            mb.handle, ptr(cloud) if n else None, mb.code, n, edges_p, radii_p, len(radii), ptr(out) if n else None,
+            out_code, 0, mb.boxes.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+            voxel_counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)) if voxel_counts is not None and n else None,
+            stream_ptr(cloud.device)))
+    return out, mb.boxes
 
 
 def process_tiles_local(clouds, edge_lengths, radii, out_dtype=np.float32, mailboxes=None, capacity_rows=None):
@@ -471,18 +468,20 @@ def _use_mailboxes(cloud):
 
 
 def process_tile(cloud, edge_lengths, radii, out=None, out_dtype=np.float32, gather=False, group=None,
-                 compute=None):
+                 compute=None, voxel_counts=None):
     """
     features of this rank's tile (n_local, 4*S).  `cloud`: (n_local, 3) tensor on this rank's device; a rank may
     hold an empty tile (it still takes part in every collective step).
     gather=True: returns the rows of every rank, concatenated in rank order, on every rank.
     compute(query, search, edges, radii, (lo, hi) numpy, out_dtype, out) -> features; default = CUDA path.
+    voxel_counts: optional int64 numpy array (S,) receiving the unique voxels per scale of this rank's lattices
+    (tile + halo; mailbox path only, forces a synchronisation).
     """
     assert len(edge_lengths) == len(radii), "edge_lengths and radii should be equal-length sequences."
     world = dist.get_world_size(group)
     sizes = None
     if compute is None and _use_mailboxes(cloud) and world <= 16:
-        feats, boxes = _process_tile_cuda(cloud, edge_lengths, radii, out, out_dtype, group)
+        feats, boxes = _process_tile_cuda(cloud, edge_lengths, radii, out, out_dtype, group, voxel_counts)
         sizes = [int(v) for v in boxes[:, 6]]
     else:
         halo, (g_lo, g_hi), _ = exchange_halo(cloud, edge_lengths, radii, group)

@@ -8,7 +8,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
 cloud = synth.urban_scene(n, seed=20, device="cuda")
 lib = _lib.lib()
 lib.nbr_timing_enable(1)
-ph = (ctypes.c_double * 4)()
+ph = (ctypes.c_double * 8)()
 for e, r in ((0.1, 0.3), (0.2, 0.6), (0.4, 1.2), (0.8, 2.4), (1.6, 4.8)):
     for _ in range(2):
         out = multiscale.process_single_core(cloud, cloud, [e], [r], out_dtype=np.float32)

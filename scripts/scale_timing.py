@@ -3,7 +3,7 @@ import sys, os, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from nimrud_b200 import _lib, multiscale, synth
-lib = _lib.lib(); lib.nbr_timing_enable(1); ph = (ctypes.c_double * 4)()
+lib = _lib.lib(); lib.nbr_timing_enable(1); ph = (ctypes.c_double * 8)()
 cloud = synth.urban_scene(int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000, seed=20, device="cuda")
 for e, r in ((0.2, 0.6), (0.2, 0.8), (0.2, 1.0), (0.2, 1.2), (0.4, 2.0), (1.6, 8.0)):
     for _ in range(2):

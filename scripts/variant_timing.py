@@ -3,7 +3,7 @@ import sys, os, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from nimrud_b200 import _lib, multiscale, synth
-lib = _lib.lib(); lib.nbr_timing_enable(1); ph = (ctypes.c_double * 4)()
+lib = _lib.lib(); lib.nbr_timing_enable(1); ph = (ctypes.c_double * 8)()
 def run(name, cloud, edges, radii, reps=3):
     for _ in range(2):
         out = multiscale.process_single_core(cloud, cloud, edges, radii, out_dtype=np.float32)

@@ -28,9 +28,15 @@ def worker(rank, world, port, tmp):
     split = cloud[:, 0].median()
     mine = cloud[cloud[:, 0] < split] if rank == 0 else cloud[cloud[:, 0] >= split]
     feats = nd.process_tile(mine.cuda().contiguous(), EDGES, RADII, gather=True, out_dtype=np.float32)
+    # the same through the NCCL transport (all-gather of the boxes, all-to-all-v of counts and points)
+    os.environ["NBR_HALO"] = "nccl"
+    feats_nccl = nd.process_tile(mine.cuda().contiguous(), EDGES, RADII, gather=True, out_dtype=np.float32)
+    os.environ.pop("NBR_HALO")
+    assert torch.equal(feats, feats_nccl)
     if rank == 0:
         np.save(os.path.join(tmp, "gathered.npy"), feats.cpu().numpy())
     dist.barrier()
+    nd.release_mailboxes()
     dist.destroy_process_group()
 
 
