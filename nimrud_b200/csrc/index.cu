@@ -511,6 +511,7 @@ batch_mark_kernel(const T *__restrict__ xyz, int64_t n_bound, const unsigned lon
     // n_dev (optional): the number of points is only known on the device (halo mailbox); n_bound sizes the grid
     const int64_t n = n_dev ? min(n_bound, (int64_t)*n_dev) : n_bound;
     const int64_t base = ((int64_t)blockIdx.x * PTS) * blockDim.x + threadIdx.x;
+    if (base - (threadIdx.x & 31) >= n) return;             // the whole warp is past the end (grids sized for a mailbox's capacity)
     for (int l = 0; l < B.n; ++l) {
         int64_t b[PTS];
 #pragma unroll
@@ -540,6 +541,7 @@ batch_fill_kernel(const T *__restrict__ xyz, int64_t n_bound, const unsigned lon
 {
     const int64_t n = n_dev ? min(n_bound, (int64_t)*n_dev) : n_bound;
     const int64_t base = ((int64_t)blockIdx.x * PTS) * blockDim.x + threadIdx.x;
+    if (base - (threadIdx.x & 31) >= n) return;             // whole warp past the end: nothing to vote on
     uint32_t pend_old[PTS], pend_bit[PTS];
 #pragma unroll
     for (int k = 0; k < PTS; ++k) { pend_old[k] = ~0u; pend_bit[k] = 0; }

@@ -43,6 +43,15 @@ namespace nbr {
 #ifndef R3_BLOCKS_N
 #define R3_BLOCKS_N 4
 #endif
+#ifndef R3_PIPELINE
+#define R3_PIPELINE 0               // stage entry li + 1 before the eigen-solve of entry li
+#endif
+#ifndef R3_UNC2
+#define R3_UNC2 0                   // two uncertain cells per trip of the shell loop
+#endif
+#ifndef R3_TAB_PREFETCH
+#define R3_TAB_PREFETCH 0           // the next slab's table masks are loaded one slab ahead
+#endif
 constexpr int R3_WARPS = R3_WARPS_N;
 constexpr int R3_UNROLL = R3_UNROLL_N;   // slabs per trip of the slab loop
 constexpr int R3_CAP = R3_CAP_N;          // staged bricks per warp (128 bytes each)
@@ -133,7 +142,10 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
         int lo0 = 0, lo1 = 0, lo2 = 0, nb0 = 1, nb1 = 1;
         bool staged = false;
 
-        for (int li = 0; li < P.n; ++li) {
+        // stage entry li: anchor cell, table bin, the warp's brick window and every lane's table line (asynchronous
+        // copies; the caller waits for them).  called for entry li + 1 BEFORE entry li's eigen-solve, so that the
+        // directory look-ups and the copies are in flight while the warp does arithmetic
+        auto stage_entry = [&](int li) {
             const R3Entry &E = P.e[li];
             if (!E.reuse) {
                 // ---- anchor cell, fractional position, table bin
@@ -208,7 +220,14 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
 #pragma unroll
                 for (int j = 0; j < N7; ++j) cp_async16(tab_addr + 16u * j, line + 16 * j);
             }
-
+        };
+        // trip li = -1 only stages entry 0; trip li computes entry li, stages entry li + 1, then solves entry li
+        // (one copy of every phase in the instruction stream: the kernel is sensitive to its code size)
+        for (int li = R3_PIPELINE ? -1 : 0; li < P.n; ++li) {
+            int An = 0, Asx = 0, Asy = 0, Asz = 0, Asxx = 0, Asxy = 0, Asxz = 0, Asyy = 0, Asyz = 0, Aszz = 0;
+            const R3Entry &E = P.e[li < 0 ? 0 : li];
+            if (!R3_PIPELINE) stage_entry(li);
+            if (li >= 0) {
             // ---- per lane: 7 slabs of 7 rows of 7 bits
             const int xa = c0 - W3, ya = c1 - W3, za = c2 - W3;
             const int sh = xa & 31;
@@ -232,12 +251,19 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
             }
             asm volatile("cp.async.wait_all;" ::: "memory");
             __syncwarp();
-            int An = 0, Asx = 0, Asy = 0, Asz = 0, Asxx = 0, Asxy = 0, Asxz = 0, Asyy = 0, Asyz = 0, Aszz = 0;
             uint2 *ulist = reinterpret_cast<uint2 *>(const_cast<uint4 *>(tab));
             int n_u = 0;
+#if R3_TAB_PREFETCH
+            uint4 tnext = tab[0];
+#endif
 #pragma unroll R3_UNROLL
             for (int jz = 0; jz < N7; ++jz) {
+#if R3_TAB_PREFETCH
+                const uint4 tcur = tnext;
+                tnext = tab[min(jz + 1, N7 - 1)];
+#else
                 const uint4 tcur = tab[jz];
+#endif
                 // every skip of this loop is warp-uniform (the body synchronises the warp): no lane's cells of this slab
                 // can be in the ball
                 if (!__any_sync(0xffffffffu, (tcur.x | tcur.y | tcur.z | tcur.w) != 0)) continue;
@@ -333,6 +359,42 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
             }
             // ---- occupied cells of the uncertain shell: float32 first, |d^2 - rho^2| > band decides; inside the band
             // the reference's float64 expression does.  accepted cells are added to the moments one by one
+#if R3_UNC2 && R3_ROW_BITS == 8
+            {
+                // two cells of the same word per trip: their distance arithmetic overlaps, and the trip count (the
+                // maximum over the lanes) halves.  a rejected cell is added with weight 0
+                uint32_t cur = 0;
+                int k = 0, jzc = 0, half = 0;
+                float dz2f = 0.0f;
+                for (;;) {
+                    if (cur == 0) {
+                        if (k >= n_u) break;
+                        const uint2 e = ulist[k++];
+                        cur = e.x;
+                        jzc = (int)(e.y & 255u);
+                        half = (int)(e.y >> 8) * 4;
+                        const float dzf = fzm - (float)jzc;
+                        dz2f = dzf * dzf;
+                    }
+                    const int i1 = __ffs(cur) - 1;
+                    cur &= cur - 1;
+                    const bool has2 = cur != 0;
+                    const int i2 = has2 ? __ffs(cur) - 1 : i1;
+                    cur &= cur - 1;                                        // 0 stays 0
+                    const int jy1 = (i1 >> 3) + half, t1 = i1 & 7, jy2 = (i2 >> 3) + half, t2 = i2 & 7;
+                    const float dx1 = fxm - (float)t1, dy1 = fym - (float)jy1, dx2 = fxm - (float)t2, dy2 = fym - (float)jy2;
+                    const float d21 = fmaf(dx1, dx1, fmaf(dy1, dy1, dz2f)), d22 = fmaf(dx2, dx2, fmaf(dy2, dy2, dz2f));
+                    bool in1 = d21 < E.rho2, in2 = has2 && d22 < E.rho2;
+                    if (fabsf(d21 - E.rho2) < 4.0e-5f) in1 = r3_exact_in(E, q[0], q[1], q[2], xa + t1, ya + jy1, za + jzc);
+                    if (has2 && fabsf(d22 - E.rho2) < 4.0e-5f) in2 = r3_exact_in(E, q[0], q[1], q[2], xa + t2, ya + jy2, za + jzc);
+                    const int w1 = in1 ? 1 : 0, w2 = in2 ? 1 : 0;
+                    const int x1 = w1 * t1, x2 = w2 * t2, y1 = w1 * jy1, y2 = w2 * jy2, nz = w1 + w2;
+                    An += nz; Asx += x1 + x2; Asy += y1 + y2; Asz += nz * jzc;
+                    Asxx += x1 * t1 + x2 * t2; Asxy += x1 * jy1 + x2 * jy2; Asxz += (x1 + x2) * jzc;
+                    Asyy += y1 * jy1 + y2 * jy2; Asyz += (y1 + y2) * jzc; Aszz += nz * jzc * jzc;
+                }
+            }
+#else
             {
                 uint32_t cur = 0;
                 int k = 0, jzc = 0, half = 0;                               // half: first row (8-bit rows) / first bit (7-bit rows) of the word
@@ -367,8 +429,14 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
                     }
                 }
             }
-            if (active)
-                emit_features_window<OutT>(An, Asx, Asy, Asz, Asxx, Asxy, Asxz, Asyy, Asyz, Aszz, fxm, fym, fzm, true,
+#endif
+            }
+            const float exm = fxm, eym = fym, ezm = fzm;
+#if R3_PIPELINE
+            if (li + 1 < P.n) stage_entry(li + 1);              // window and table lines of entry li are consumed
+#endif
+            if (active && li >= 0)
+                emit_features_window<OutT>(An, Asx, Asy, Asz, Asxx, Asxy, Asxz, Asyy, Asyz, Aszz, exm, eym, ezm, true,
                                            E.edge, dst_row + E.col, EXT ? NBR_DESC_EXTENDED : 0);
         }
         if (stage_rows) {
