@@ -330,25 +330,23 @@ def gpu_arm(args, rank, world, local_rank):
     ms_per_step = elapsed_ms / args.steps
     value = world * n * ns / (ms_per_step * 1e-3)
 
-    # ---- e2e: host buffers (pinned), reference-facing host entry point, float64 output (drop-in)
+    # ---- e2e: host buffers in, host rows out, copies inside the timed region.  headline = the reference-facing host
+    # entry point (C ABI) with pinned buffers and float64 rows (the reference's output dtype); beside it the same call
+    # with float32 rows and the documented drop-in `process_single_core(numpy, numpy)` with plain (pageable) arrays
     e2e = None
     if not args.no_e2e:
         host_in = cloud.cpu().pin_memory()
         e2e_steps = max(1, min(args.steps, 3))
         results = {}
-        for label, tdt, code in (("f64", torch.float64, _lib.F64), ("f32", torch.float32, _lib.F32)):
+        legs = [("f64", torch.float64, _lib.F64), ("f32", torch.float32, _lib.F32)]
+        for label, tdt, code in legs:
             host_out = torch.empty((n, 4 * ns), dtype=tdt).pin_memory()
             if world > 1:
-                dev_in = torch.empty_like(cloud)
-                dev_out = torch.empty((n, 4 * ns), dtype=tdt, device=dev)
                 np_dt = np.float64 if tdt == torch.float64 else np.float32
 
                 def host_step():
-                    # host tile -> device, halo exchange + compute, features -> host
-                    dev_in.copy_(host_in, non_blocking=True)
-                    nd.process_tile(dev_in, EDGES, RADII, out=dev_out, out_dtype=np_dt, gather=False)
-                    host_out.copy_(dev_out, non_blocking=True)
-                    torch.cuda.synchronize()
+                    # host tile -> device, box table + halo push + lattices, rows -> host in batches (nbr_tile_step_host)
+                    nd.process_tile_host(host_in, EDGES, RADII, out=host_out, out_dtype=np_dt, device=dev)
             else:
                 def host_step():
                     _lib.check(lib.nbr_multiscale_features_host(
@@ -371,9 +369,23 @@ def gpu_arm(args, rank, world, local_rank):
                 assert torch.equal(check[:, 0::4], out[:4096, 0::4].cpu()), "e2e and device-resident results differ"
             del host_out
         e2e = {"value": results["f64"][0], "unit": UNIT, "h2d_bytes_per_step": int(host_in.numel() * 4),
-               "d2h_bytes_per_step": int(results["f64"][1]), "out_dtype": "float64 (drop-in default)",
+               "d2h_bytes_per_step": int(results["f32"][1]), "out_dtype": "float64 (drop-in default)",
+               "wire": "float32 rows over PCIe, widened to float64 by host threads inside the call",
                "value_float32_out": results["f32"][0], "d2h_bytes_per_step_float32_out": int(results["f32"][1]),
                "steps": e2e_steps, "timer": "host wall clock around the synchronous host-buffer call"}
+        if world == 1:
+            # the documented drop-in: numpy in, fresh numpy float64 out (pageable on both sides)
+            np_in = host_in.numpy().copy()
+            multiscale.process_single_core(np_in, np_in, EDGES, RADII)
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                res = multiscale.process_single_core(np_in, np_in, EDGES, RADII)
+            dt = time.perf_counter() - t0
+            assert res.dtype == np.float64 and np.array_equal(res[:4096, 0::4].astype(np.float32), out[:4096, 0::4].cpu().numpy())
+            e2e["value_numpy_shim"] = n * ns * e2e_steps / dt
+            e2e["numpy_shim"] = "nimrud_b200.multiscale.process_single_core(ndarray, ndarray): pageable input staged through " \
+                                "pinned rings, fresh pageable float64 result"
+            del res, np_in
 
     # ---- N > 1: the step with the final feature all-gather, and the seam check
     with_gather, seam = None, None

@@ -14,8 +14,8 @@
  *     stream-ordered and return without synchronising unless stated.
  *   - every function returns NBR_OK (0) or an error code; nbr_last_error() gives the message of the
  *     last failure on the calling thread.
- *   - scratch memory comes from the stream-ordered CUDA pool (cudaMallocAsync); the caller owns
- *     every input and output buffer.
+ *   - scratch memory comes from the library's own stream-ordered CUDA memory pool (see nbr_trim_memory);
+ *     the caller owns every input and output buffer.
  *   - the device that holds the buffers (and owns `stream`) must be the CURRENT device of the calling
  *     thread (cudaSetDevice) for every call, including nbr_lattice_destroy / nbr_lattice_info: kernels,
  *     scratch and cached tables are created on the current device.  one process may drive several
@@ -58,6 +58,10 @@ extern "C" {
 
 const char *nbr_last_error(void);
 int nbr_version(void);
+/* scratch comes from a PRIVATE stream-ordered memory pool per device (the application's default pool is never
+ * touched); it keeps up to NBR_POOL_KEEP_MB (default 5 % of the device memory, at least 2 GB) of freed scratch for
+ * the next call.  nbr_trim_memory releases what is cached on the current device (synchronises the device). */
+int nbr_trim_memory(void);
 
 /* ------------------------------------------------------------------------------------------------
  * voxel grid (replaces VoxelFilter.__init__ / _calculate_shift, utils/geometry.py:23-62)
@@ -166,12 +170,20 @@ int nbr_multiscale_features(const void *query_xyz, int q_dtype, int64_t n_query,
                             int64_t *n_voxels_host, void *stream);
 
 /* same with HOST buffers: copies the clouds in, runs, copies the features out; synchronous.
- * this is the call the reference-facing Python shim makes for numpy arguments. */
+ * this is the call the reference-facing Python shim makes for numpy arguments.  the rows cross PCIe as float32 and,
+ * for out_dtype NBR_F64, are widened into out_host by host threads (NBR_HOST_WIRE=f64: float64 on the wire);
+ * pageable buffers are staged through pinned rings, pinned ones are used in place; the queries run in batches whose
+ * copies overlap the kernels.  NBR_HOST_THREADS bounds the host threads (default: all cores, at most 64). */
 int nbr_multiscale_features_host(const void *query_host, int q_dtype, int64_t n_query,
                                  const void *search_host, int s_dtype, int64_t n_search,
                                  const double *edges_host, const double *radii_host, int32_t n_scales,
                                  void *out_host, int out_dtype, int32_t descriptor_mask,
                                  int64_t *n_voxels_host);
+
+/* page-locked host buffers (cudaHostAlloc) for callers that want their clouds / result rows used in place by
+ * nbr_multiscale_features_host; the Python shim recycles its result arrays through these. */
+int nbr_host_alloc(size_t bytes, void **out);
+int nbr_host_free(void *ptr);
 
 /* vector-field multiscale operator (extension; legacy precedent V_MSO, nimrud/prototypes/mso.py:12-257).
  * nbr_voxel_vector_means: vectors (n_search, n_components) float32 carried by the search points are averaged
@@ -263,6 +275,12 @@ int nbr_multiscale_features_tile_mb(const void *sorted_xyz, const uint32_t *perm
 int nbr_tile_step(nbr_mailbox *mailbox, const void *xyz, int dtype, int64_t n, const double *edges_host,
                   const double *radii_host, int32_t n_scales, void *out, int out_dtype, int32_t descriptor_mask,
                   double *boxes_host_out, int64_t *n_voxels_host, void *stream);
+
+/* nbr_tile_step with HOST buffers (the tile goes up, the rows come down in batches whose copies overlap the kernels;
+ * float32 on the wire, widened by host threads for out_dtype NBR_F64, like nbr_multiscale_features_host). */
+int nbr_tile_step_host(nbr_mailbox *mailbox, const void *xyz_host, int dtype, int64_t n, const double *edges_host,
+                       const double *radii_host, int32_t n_scales, void *out_host, int out_dtype,
+                       int32_t descriptor_mask, double *boxes_host_out);
 
 /* counters for tests and benches: number of kernels this library has launched in this process. */
 int64_t nbr_kernel_launches(void);

@@ -11,4 +11,14 @@ from . import geometry        # noqa: F401
 from . import multiscale      # noqa: F401
 from .multiscale import process_single_core, one_scale_single_core   # noqa: F401
 
-__all__ = ["geometry", "multiscale", "process_single_core", "one_scale_single_core"]
+
+
+def trim_memory():
+    """release the scratch memory the library keeps cached on the current CUDA device (its private stream-ordered
+    pool is invisible to torch's caching allocator); synchronises the device."""
+    _lib.check(_lib.lib().nbr_trim_memory())
+    from . import _results
+    _results.trim()
+
+
+__all__ = ["geometry", "multiscale", "process_single_core", "one_scale_single_core", "trim_memory"]

@@ -29,6 +29,9 @@ class Grid(ctypes.Structure):
 SIGNATURES = {
     "nbr_last_error": (ctypes.c_char_p, []),
     "nbr_version": (ctypes.c_int, []),
+    "nbr_trim_memory": (ctypes.c_int, []),
+    "nbr_host_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(c_vp)]),
+    "nbr_host_free": (ctypes.c_int, [c_vp]),
     "nbr_kernel_launches": (c_i64, []),
     "nbr_timing_enable": (None, [ctypes.c_int]),
     "nbr_timing_read": (ctypes.c_int, [ctypes.POINTER(c_f64)]),
@@ -83,6 +86,8 @@ SIGNATURES = {
                                                        c_i32, c_vp, ctypes.c_int, c_i32, ctypes.POINTER(c_i64), c_vp]),
     "nbr_tile_step": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_i64, ctypes.POINTER(c_f64), ctypes.POINTER(c_f64), c_i32, c_vp,
                                      ctypes.c_int, c_i32, ctypes.POINTER(c_f64), ctypes.POINTER(c_i64), c_vp]),
+    "nbr_tile_step_host": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_i64, ctypes.POINTER(c_f64), ctypes.POINTER(c_f64), c_i32, c_vp,
+                                          ctypes.c_int, c_i32, ctypes.POINTER(c_f64)]),
     "nbr_multiscale_features": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_vp, ctypes.c_int, c_i64,
                                                ctypes.POINTER(c_f64), ctypes.POINTER(c_f64), c_i32, c_vp,
                                                ctypes.c_int, c_i32, ctypes.POINTER(c_f64), ctypes.POINTER(c_i64),

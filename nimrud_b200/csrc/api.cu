@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "lattice.cuh"
 #include "mailbox.cuh"
+#include "plan.cuh"
 #include "radius_rows.cuh"
 
 namespace nbr {
@@ -28,7 +29,7 @@ int Scratch::alloc(size_t bytes, cudaStream_t s)
     release();
     stream = s;
     if (bytes == 0) bytes = 16;
-    cudaError_t e = cudaMallocAsync(&ptr, bytes, s);
+    cudaError_t e = pool_alloc(&ptr, bytes, s);
     if (e != cudaSuccess) {
         ptr = nullptr;
         return fail(NBR_ERR_CUDA, std::string("cudaMallocAsync(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
@@ -50,15 +51,48 @@ int device_sm_count()
     int sms = sms_of[dev].load(std::memory_order_relaxed);
     if (!sms) {
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-        // keep freed scratch in the pool: the path allocates the same sizes on every call
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            uint64_t keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
         sms_of[dev].store(sms, std::memory_order_relaxed);
     }
     return sms;
+}
+
+static std::mutex g_pool_mutex;
+static cudaMemPool_t g_pools[64] = {nullptr};
+
+static cudaMemPool_t private_pool(int dev)
+{
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (g_pools[dev]) return g_pools[dev];
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t pool = nullptr;
+    if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    // keep a bounded amount of freed scratch: the path allocates the same sizes on every call
+    uint64_t keep = 0;
+    const char *env = getenv("NBR_POOL_KEEP_MB");
+    if (env) keep = (uint64_t)atof(env) * (1ull << 20);
+    else {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) total_b = 0;
+        keep = std::max<uint64_t>(2ull << 30, total_b / 20);
+    }
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    g_pools[dev] = pool;
+    return pool;
+}
+
+cudaError_t pool_alloc(void **ptr, size_t bytes, cudaStream_t stream)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    cudaMemPool_t pool = dev >= 0 && dev < 64 ? private_pool(dev) : nullptr;
+    if (!pool) return cudaMallocAsync(ptr, bytes, stream);          // no private pool on this driver: the default one, untouched
+    return cudaMallocFromPoolAsync(ptr, bytes, pool, stream);
 }
 
 bool first_use_on_device(std::atomic<uint64_t> &seen)
@@ -192,20 +226,9 @@ static int host_bbox(const void *xyz, int dtype, int64_t n, double *lohi_host, c
 
 static int brick_origin(const double *lohi, const double *local_box, double finest, double origin[3]);
 
-struct Plan {
-    struct Group { double edge; Lattice *lat; std::vector<int> scales; };
-    std::vector<Group> groups;
-    std::vector<double> edges, radii;
-    int n_scales = 0, ncol = 4, descriptor_mask = 0;
-    double finest = 0.0;
-    double local_box[6];
-    double order_origin[3];   // brick corner of the finest lattice: the query order is aligned with it
-    ~Plan() { for (auto &g : groups) delete g.lat; }
-};
-
 int plan_create(Plan **out, const void *search, int s_dtype, int64_t ns, const double *edges, const double *radii,
                 int n_scales, int descriptor_mask, const double *global_lohi, const double *known_local_box,
-                cudaStream_t stream, const void *search2 = nullptr, int64_t ns2 = 0, Mailbox *mailbox = nullptr)
+                cudaStream_t stream, const void *search2, int64_t ns2, Mailbox *mailbox)
 {
     NBR_TRY(check_cloud_dtype(s_dtype, "multiscale_features"));
     if (n_scales < 0) return fail(NBR_ERR_INVALID, "multiscale_features: negative number of scales");
@@ -427,7 +450,22 @@ int multiscale_features(const void *query, int q_dtype, int64_t nq, const void *
 using namespace nbr;
 
 extern "C" const char *nbr_last_error(void) { return g_error.c_str(); }
-extern "C" int nbr_version(void) { return 100; }
+extern "C" int nbr_version(void) { return 200; }
+
+// releases the scratch the library's private pool keeps cached on the current device (synchronises the device)
+extern "C" int nbr_trim_memory(void)
+{
+    int dev = 0;
+    NBR_CUDA(cudaGetDevice(&dev));
+    NBR_CUDA(cudaDeviceSynchronize());
+    cudaMemPool_t pool = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        pool = dev >= 0 && dev < 64 ? g_pools[dev] : nullptr;
+    }
+    if (pool) NBR_CUDA(cudaMemPoolTrimTo(pool, 0));
+    return NBR_OK;
+}
 extern "C" int64_t nbr_kernel_launches(void) { return g_launches.load(); }
 
 extern "C" void nbr_timing_enable(int on) { g_timing.store(on ? 1 : 0); }
@@ -548,23 +586,25 @@ extern "C" int nbr_multiscale_features_tile_mb(const void *sorted_xyz, const uin
 // and the next launches, so the GPU idles for microseconds there, not for an interpreter's worth of time.
 // h = max_s(r_s + e_s / 2) (+ slack): every voxel centre within r_s of a query of the tile holds a point within h
 // per axis of the tile's box.  boxes_host_out (optional): [world][8] = lo, hi, n_points, 0 of every tile.
-extern "C" int nbr_tile_step(nbr_mailbox *mailbox, const void *xyz, int dtype, int64_t n, const double *edges_host,
-                             const double *radii_host, int32_t n_scales, void *out, int out_dtype,
-                             int32_t descriptor_mask, double *boxes_host_out, int64_t *n_voxels_host, void *stream)
+//
+// tile_step_plan: everything up to the lattices.  *P_out stays NULL for an empty tile (its mailbox is drained).
+namespace nbr {
+int tile_step_plan(Mailbox *M, const void *xyz, int dtype, int64_t n, const double *edges_host, const double *radii_host,
+                   int32_t n_scales, int32_t descriptor_mask, double *boxes_host_out, Scratch &perm, Scratch &sorted, Plan **P_out,
+                   cudaStream_t s)
 {
-    if (!mailbox || n < 0 || n_scales < 0 || (n_scales > 0 && (!edges_host || !radii_host)) || (n > 0 && (!xyz || !out)))
-        return fail(NBR_ERR_INVALID, "nbr_tile_step: bad argument");
-    NBR_TRY(check_cloud_dtype(dtype, "nbr_tile_step"));
-    if (out_dtype != NBR_F32 && out_dtype != NBR_F64) return fail(NBR_ERR_INVALID, "nbr_tile_step: bad out_dtype");
-    Mailbox *M = reinterpret_cast<Mailbox *>(mailbox);
-    cudaStream_t s = (cudaStream_t)stream;
+    *P_out = nullptr;
+    for (int k = 0; k < n_scales; ++k)                     // before the first collective step: a bad argument must not strand the peers
+        if (!edges_host || !radii_host || !(edges_host[k] > 0) || !(radii_host[k] >= 0))
+            return fail(NBR_ERR_INVALID, "nbr_tile_step: edge lengths must be > 0, radii >= 0");
+    nbr_mailbox *mailbox = reinterpret_cast<nbr_mailbox *>(M);
+    void *stream = (void *)s;
     double boxes[MB_MAX_WORLD][8];
     NBR_TRY(nbr_tile_box_publish(mailbox, xyz, dtype, n, stream));
     NBR_TRY(nbr_tile_boxes_wait(mailbox, &boxes[0][0], stream));
     if (boxes_host_out) memcpy(boxes_host_out, boxes, sizeof(double) * 8 * M->world);
     double h = 0.0, finest = 0.0;
     for (int k = 0; k < n_scales; ++k) {
-        if (!(edges_host[k] > 0) || !(radii_host[k] >= 0)) return fail(NBR_ERR_INVALID, "nbr_tile_step: edge lengths must be > 0, radii >= 0");
         h = std::max(h, radii_host[k] + edges_host[k] / 2);
         finest = k == 0 ? edges_host[k] : std::min(finest, edges_host[k]);
     }
@@ -585,86 +625,28 @@ extern "C" int nbr_tile_step(nbr_mailbox *mailbox, const void *xyz, int dtype, i
         local[3 + a] = std::min(mine[3 + a] + h, glob[3 + a]);
     }
     NBR_TRY(brick_origin(glob, local, finest, origin));
-    Scratch perm, sorted;
     NBR_TRY(order_queries(xyz, dtype, n, mine, finest, origin, perm, sorted, s));
+    return plan_create(P_out, sorted.ptr, dtype, n, edges_host, radii_host, n_scales, descriptor_mask, glob, local, s, nullptr, 0, M);
+}
+}  // namespace nbr
+
+extern "C" int nbr_tile_step(nbr_mailbox *mailbox, const void *xyz, int dtype, int64_t n, const double *edges_host,
+                             const double *radii_host, int32_t n_scales, void *out, int out_dtype,
+                             int32_t descriptor_mask, double *boxes_host_out, int64_t *n_voxels_host, void *stream)
+{
+    if (!mailbox || n < 0 || n_scales < 0 || (n_scales > 0 && (!edges_host || !radii_host)) || (n > 0 && (!xyz || !out)))
+        return fail(NBR_ERR_INVALID, "nbr_tile_step: bad argument");
+    NBR_TRY(check_cloud_dtype(dtype, "nbr_tile_step"));
+    if (out_dtype != NBR_F32 && out_dtype != NBR_F64) return fail(NBR_ERR_INVALID, "nbr_tile_step: bad out_dtype");
+    cudaStream_t s = (cudaStream_t)stream;
+    Scratch perm, sorted;
     Plan *P = nullptr;
-    NBR_TRY(plan_create(&P, sorted.ptr, dtype, n, edges_host, radii_host, n_scales, descriptor_mask, glob, local, s, nullptr, 0, M));
+    NBR_TRY(tile_step_plan(reinterpret_cast<Mailbox *>(mailbox), xyz, dtype, n, edges_host, radii_host, n_scales, descriptor_mask,
+                           boxes_host_out, perm, sorted, &P, s));
+    if (!P) return NBR_OK;
     int rc = plan_run_sorted(P, sorted.ptr, dtype, perm.as<uint32_t>(), n, out, out_dtype, s);
     if (rc == NBR_OK && n_voxels_host) rc = plan_voxel_counts(P, n_voxels_host);
     delete P;
     return rc;
 }
 
-static size_t elem_size(int dtype) { return dtype == NBR_F32 ? 4 : 8; }
-
-// HOST buffers.  the search cloud goes up once, the lattices are built once, then the queries are
-// processed in batches: the device->host copy of batch k (on a second stream) overlaps the kernels of
-// batch k+1.  pinned host buffers make the copies asynchronous; pageable ones still work.
-extern "C" int nbr_multiscale_features_host(const void *query_host, int q_dtype, int64_t n_query,
-                                            const void *search_host, int s_dtype, int64_t n_search,
-                                            const double *edges_host, const double *radii_host, int32_t n_scales,
-                                            void *out_host, int out_dtype, int32_t descriptor_mask,
-                                            int64_t *n_voxels_host)
-{
-    NBR_TRY(check_cloud_dtype(q_dtype, "nbr_multiscale_features_host"));
-    NBR_TRY(check_cloud_dtype(s_dtype, "nbr_multiscale_features_host"));
-    if (out_dtype != NBR_F32 && out_dtype != NBR_F64) return fail(NBR_ERR_INVALID, "nbr_multiscale_features_host: bad out_dtype");
-    if (n_search < 2) return fail(NBR_ERR_TOO_FEW_POINTS, "need at least 2 points to define a voxel grid");
-    if (n_query <= 0 || n_scales <= 0) return NBR_OK;
-    if (!query_host || !search_host || !out_host) return fail(NBR_ERR_INVALID, "nbr_multiscale_features_host: null argument");
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
-    NBR_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    if (cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
-        cudaStreamDestroy(stream);
-        return fail(NBR_ERR_CUDA, "nbr_multiscale_features_host: cannot create the copy stream");
-    }
-    const int ncol = (descriptor_mask & NBR_DESC_EXTENDED) ? NBR_COLS_EXTENDED : NBR_COLS_REFERENCE;
-    const size_t qrow = 3 * elem_size(q_dtype), orow = (size_t)ncol * n_scales * elem_size(out_dtype);
-    const size_t sbytes = (size_t)n_search * 3 * elem_size(s_dtype);
-    const bool same = query_host == search_host && q_dtype == s_dtype && n_query == n_search;
-    const int64_t batch = std::max<int64_t>(262144, (n_query + 7) / 8);
-    std::vector<cudaEvent_t> events;
-    int rc = NBR_OK;
-    Plan *P = nullptr;
-    {
-        Scratch q, s, o;
-        rc = s.alloc(sbytes, stream);
-        if (!rc && !same) rc = q.alloc((size_t)n_query * qrow, stream);
-        if (!rc) rc = o.alloc((size_t)n_query * orow, stream);
-        cudaError_t e = cudaSuccess;
-        if (!rc) e = cudaMemcpyAsync(s.ptr, search_host, sbytes, cudaMemcpyHostToDevice, stream);
-        if (!rc && e == cudaSuccess)
-            rc = plan_create(&P, s.ptr, s_dtype, n_search, edges_host, radii_host, n_scales, descriptor_mask, nullptr, nullptr, stream);
-        for (int64_t first = 0; !rc && e == cudaSuccess && first < n_query; first += batch) {
-            const int64_t n = std::min(batch, n_query - first);
-            char *qdev = (same ? (char *)s.ptr : (char *)q.ptr) + (size_t)first * qrow;
-            if (!same) e = cudaMemcpyAsync(qdev, (const char *)query_host + (size_t)first * qrow, (size_t)n * qrow,
-                                           cudaMemcpyHostToDevice, stream);
-            if (e != cudaSuccess) break;
-            char *odev = (char *)o.ptr + (size_t)first * orow;
-            rc = plan_run(P, qdev, q_dtype, n, same ? P->local_box : nullptr, odev, out_dtype, stream);
-            if (rc) break;
-            cudaEvent_t done;
-            e = cudaEventCreateWithFlags(&done, cudaEventDisableTiming);
-            if (e != cudaSuccess) break;
-            events.push_back(done);
-            e = cudaEventRecord(done, stream);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(copy_stream, done, 0);
-            if (e == cudaSuccess)
-                e = cudaMemcpyAsync((char *)out_host + (size_t)first * orow, odev, (size_t)n * orow, cudaMemcpyDeviceToHost,
-                                    copy_stream);
-        }
-        if (!rc && e == cudaSuccess) e = cudaStreamSynchronize(stream);
-        if (!rc && e == cudaSuccess) e = cudaStreamSynchronize(copy_stream);
-        if (!rc && e == cudaSuccess && n_voxels_host) rc = plan_voxel_counts(P, n_voxels_host);
-        if (!rc && e != cudaSuccess) rc = fail(NBR_ERR_CUDA, std::string("host path: ") + cudaGetErrorString(e));
-        cudaStreamSynchronize(copy_stream);
-        cudaStreamSynchronize(stream);
-        delete P;
-    }
-    for (cudaEvent_t ev : events) cudaEventDestroy(ev);
-    cudaStreamSynchronize(stream);
-    cudaStreamDestroy(copy_stream);
-    cudaStreamDestroy(stream);
-    return rc;
-}

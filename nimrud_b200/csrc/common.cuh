@@ -56,6 +56,10 @@ struct Scratch {
 };
 
 int device_sm_count();
+// stream-ordered allocation from the library's PRIVATE memory pool of the current device (the default pool and its
+// attributes belong to the application).  freed with cudaFreeAsync.  the pool keeps up to NBR_POOL_KEEP_MB
+// (default: 5 % of the device's memory, at least 2 GB) of freed scratch for the next call; nbr_trim_memory() drops it.
+cudaError_t pool_alloc(void **ptr, size_t bytes, cudaStream_t stream);
 // true the first time it is called with this flag word on the current device (kernel attributes such as the
 // dynamic shared memory limit are per device: a process that drives several GPUs has to set them on each)
 bool first_use_on_device(std::atomic<uint64_t> &seen);

@@ -437,9 +437,9 @@ int lattice_create(Lattice **out, const void *xyz, int dtype, int64_t n, const n
 #define L_LAUNCHED() do { g_launches.fetch_add(1, std::memory_order_relaxed); cudaError_t _e = cudaGetLastError(); \
         if (_e != cudaSuccess) { delete L; return fail(NBR_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(_e)); } } while (0)
 
-    L_CUDA(cudaMallocAsync(&L->dir, sizeof(uint32_t) * L->n_dir, stream));
-    L_CUDA(cudaMallocAsync(&L->pool, sizeof(uint32_t) * BRICK_WORDS * L->pool_slots, stream));
-    L_CUDA(cudaMallocAsync(&L->counters, 64, stream));
+    L_CUDA(pool_alloc((void **)&L->dir, sizeof(uint32_t) * L->n_dir, stream));
+    L_CUDA(pool_alloc((void **)&L->pool, sizeof(uint32_t) * BRICK_WORDS * L->pool_slots, stream));
+    L_CUDA(pool_alloc((void **)&L->counters, 64, stream));
     L_CUDA(cudaMemsetAsync(L->dir, 0, sizeof(uint32_t) * L->n_dir, stream));
     L_CUDA(cudaMemsetAsync(L->counters, 0, 64, stream));
     uint32_t *n_bricks_dev = reinterpret_cast<uint32_t *>(L->counters);
@@ -470,8 +470,8 @@ int lattice_create(Lattice **out, const void *xyz, int dtype, int64_t n, const n
         Scratch addr, tmp;
         L_TRY(addr.alloc(sizeof(uint64_t) * n, stream));
         L_TRY(tmp.alloc(sizeof(uint64_t) * n, stream));
-        L_CUDA(cudaMallocAsync(&L->ukeys, sizeof(uint64_t) * n, stream));
-        L_CUDA(cudaMallocAsync(&L->rowbase, sizeof(uint32_t) * BRICK_WORDS * L->pool_slots, stream));
+        L_CUDA(pool_alloc((void **)&L->ukeys, sizeof(uint64_t) * n, stream));
+        L_CUDA(pool_alloc((void **)&L->rowbase, sizeof(uint32_t) * BRICK_WORDS * L->pool_slots, stream));
         address_kernel<<<blocks, 256, 0, stream>>>(xyz, dtype, n, L->gdev, grid->max_corner[0], grid->max_corner[1],
                                                    grid->max_corner[2], addr.as<int64_t>(), nullptr);
         L_LAUNCHED();
@@ -510,8 +510,9 @@ batch_mark_kernel(const T *__restrict__ xyz, int64_t n_bound, const unsigned lon
 {
     // n_dev (optional): the number of points is only known on the device (halo mailbox); n_bound sizes the grid
     const int64_t n = n_dev ? min(n_bound, (int64_t)*n_dev) : n_bound;
-    const int64_t base = ((int64_t)blockIdx.x * PTS) * blockDim.x + threadIdx.x;
-    if (base - (threadIdx.x & 31) >= n) return;             // the whole warp is past the end (grids sized for a mailbox's capacity)
+    for (int64_t chunk = blockIdx.x; chunk * PTS * blockDim.x < n; chunk += gridDim.x) {      // one trip unless the grid was capped
+    const int64_t base = (chunk * PTS) * blockDim.x + threadIdx.x;
+    if (base - (threadIdx.x & 31) >= n) return;             // the whole warp is past the end
     for (int l = 0; l < B.n; ++l) {
         int64_t b[PTS];
 #pragma unroll
@@ -531,6 +532,7 @@ batch_mark_kernel(const T *__restrict__ xyz, int64_t n_bound, const unsigned lon
         for (int k = 0; k < PTS; ++k)
             if (seen[k] == 0) dir[b[k]] = 1;   // benign race: every writer stores 1
     }
+    }
 }
 
 template <typename T>
@@ -540,7 +542,8 @@ batch_fill_kernel(const T *__restrict__ xyz, int64_t n_bound, const unsigned lon
                   uint32_t *__restrict__ pool, unsigned char *__restrict__ counters)
 {
     const int64_t n = n_dev ? min(n_bound, (int64_t)*n_dev) : n_bound;
-    const int64_t base = ((int64_t)blockIdx.x * PTS) * blockDim.x + threadIdx.x;
+    for (int64_t chunk = blockIdx.x; chunk * PTS * blockDim.x < n; chunk += gridDim.x) {      // one trip unless the grid was capped
+    const int64_t base = (chunk * PTS) * blockDim.x + threadIdx.x;
     if (base - (threadIdx.x & 31) >= n) return;             // whole warp past the end: nothing to vote on
     uint32_t pend_old[PTS], pend_bit[PTS];
 #pragma unroll
@@ -610,6 +613,7 @@ batch_fill_kernel(const T *__restrict__ xyz, int64_t n_bound, const unsigned lon
         if ((threadIdx.x & 31) == 0 && fresh && B.n > 0)
             atomicAdd(reinterpret_cast<unsigned long long *>(counters + 64 * (B.n - 1) + 8), (unsigned long long)fresh);
     }
+    }
 }
 
 int halo_wait(Mailbox *M, cudaStream_t stream);
@@ -662,9 +666,9 @@ int lattices_create_batch(Lattice **out, int n_lat, const nbr_grid *grids, const
         return fail(NBR_ERR_UNSUPPORTED, "lattices_create_batch: the batch needs more than 2^32 bricks");
     auto shared = std::make_shared<Lattice::SharedBuffers>();
     shared->stream = stream;
-    NBR_CUDA(cudaMallocAsync(&shared->dir, sizeof(uint32_t) * dir_total, stream));
-    NBR_CUDA(cudaMallocAsync(&shared->pool, sizeof(uint32_t) * BRICK_WORDS * slot_bound, stream));
-    NBR_CUDA(cudaMallocAsync(&shared->counters, 64 * (n_lat + 1), stream));
+    NBR_CUDA(pool_alloc((void **)&shared->dir, sizeof(uint32_t) * dir_total, stream));
+    NBR_CUDA(pool_alloc((void **)&shared->pool, sizeof(uint32_t) * BRICK_WORDS * slot_bound, stream));
+    NBR_CUDA(pool_alloc((void **)&shared->counters, 64 * (n_lat + 1), stream));
     NBR_CUDA(cudaMemsetAsync(shared->dir, 0, sizeof(uint32_t) * dir_total, stream));
     NBR_CUDA(cudaMemsetAsync(shared->counters, 0, 64 * (n_lat + 1), stream));
     uint32_t *dir = reinterpret_cast<uint32_t *>(shared->dir);
@@ -679,7 +683,8 @@ int lattices_create_batch(Lattice **out, int n_lat, const nbr_grid *grids, const
         // the tile's own bricks are marked while the peers' pushes are still in flight
         if (p == 1 && mailbox) NBR_TRY(halo_wait(mailbox, stream));
         if (part_n[p] <= 0) continue;
-        const unsigned pt_blocks = (unsigned)ceil_div(part_n[p], 256 * PTS);
+        // a part whose size is only known on the device gets a capped grid that strides over its chunks
+        const unsigned pt_blocks = (unsigned)std::min<int64_t>(ceil_div(part_n[p], 256 * PTS), part_dev[p] ? device_sm_count() * 8 : INT64_MAX);
         if (dtype == NBR_F32) batch_mark_kernel<float><<<pt_blocks, 256, 0, stream>>>((const float *)parts[p], part_n[p], part_dev[p], B, dir);
         else                  batch_mark_kernel<double><<<pt_blocks, 256, 0, stream>>>((const double *)parts[p], part_n[p], part_dev[p], B, dir);
         NBR_LAUNCHED();
@@ -689,7 +694,7 @@ int lattices_create_batch(Lattice **out, int n_lat, const nbr_grid *grids, const
     NBR_LAUNCHED();
     for (int p = 0; p < 2; ++p) {
         if (part_n[p] <= 0) continue;
-        const unsigned pt_blocks = (unsigned)ceil_div(part_n[p], 256 * PTS);
+        const unsigned pt_blocks = (unsigned)std::min<int64_t>(ceil_div(part_n[p], 256 * PTS), part_dev[p] ? device_sm_count() * 8 : INT64_MAX);
         if (dtype == NBR_F32) batch_fill_kernel<float><<<pt_blocks, 256, 0, stream>>>((const float *)parts[p], part_n[p], part_dev[p], B, dir, pool, counters);
         else                  batch_fill_kernel<double><<<pt_blocks, 256, 0, stream>>>((const double *)parts[p], part_n[p], part_dev[p], B, dir, pool, counters);
         NBR_LAUNCHED();

@@ -102,6 +102,8 @@ __global__ void box_wait_kernel(MailboxHeader *H, int world, unsigned long long 
 }
 
 struct PushDev {
+    float in_lo[3], in_hi[3];                          // a box that meets no destination's grown box: points strictly
+                                                       // inside it (most of the tile) skip the per-destination tests
     double lo[MB_MAX_WORLD][3], hi[MB_MAX_WORLD][3];   // grown boxes of the destinations (inverted: no point matches)
     MailboxHeader *hdr[MB_MAX_WORLD];                  // destination headers (peer-mapped)
     long long cap[MB_MAX_WORLD];                       // rows a destination's mailbox holds
@@ -116,6 +118,8 @@ __device__ __forceinline__ uint32_t push_mask(const T *__restrict__ xyz, int64_t
     uint32_t m = 0;
     if (i < n) {
         px = xyz[i * 3 + 0]; py = xyz[i * 3 + 1]; pz = xyz[i * 3 + 2];
+        const float fx = (float)px, fy = (float)py, fz = (float)pz;          // rounding is monotone: strictly inside stays inside or on the face
+        if (fx > P.in_lo[0] && fx < P.in_hi[0] && fy > P.in_lo[1] && fy < P.in_hi[1] && fz > P.in_lo[2] && fz < P.in_hi[2]) return 0u;
         const double x = (double)px, y = (double)py, z = (double)pz;
         for (int d = 0; d < P.n_dst; ++d)
             if (x >= P.lo[d][0] && x <= P.hi[d][0] && y >= P.lo[d][1] && y <= P.hi[d][1] && z >= P.lo[d][2] && z <= P.hi[d][2])
@@ -421,6 +425,37 @@ extern "C" int nbr_halo_push(nbr_mailbox *mb, const void *xyz, int dtype, int64_
             for (int a = 0; a < 3; ++a) { P.lo[k][a] = 1.0; P.hi[k][a] = -1.0; }     // matches nothing
         P.hdr[k] = reinterpret_cast<MailboxHeader *>(M->peer[d]);
         P.cap[k] = M->capacity_of[d] > 0 ? M->capacity_of[d] : M->capacity;
+    }
+    // interior box: start from this tile's box and, for every destination that can receive something, move the
+    // face that loses the least volume until the destination's grown box is outside.  float bounds, rounded inward
+    {
+        double ilo[3], ihi[3];
+        for (int a = 0; a < 3; ++a) { ilo[a] = mine[a]; ihi[a] = mine[3 + a]; }
+        for (int k = 0; k < P.n_dst; ++k) {
+            if (P.lo[k][0] > P.hi[k][0]) continue;                       // matches nothing
+            int best = -1; bool low_side = false; double best_loss = INFINITY;
+            for (int a = 0; a < 3; ++a) {
+                const double span = std::max(ihi[a] - ilo[a], 1e-300);
+                // cut below the destination (keep [ilo, lo_k)) or above it (keep (hi_k, ihi])
+                const double loss_hi = (ihi[a] - std::min(ihi[a], P.lo[k][a])) / span;     // keep the low part
+                const double loss_lo = (std::max(ilo[a], P.hi[k][a]) - ilo[a]) / span;     // keep the high part
+                if (loss_hi < best_loss) { best_loss = loss_hi; best = a; low_side = false; }
+                if (loss_lo < best_loss) { best_loss = loss_lo; best = a; low_side = true; }
+            }
+            if (best < 0) continue;
+            if (low_side) ilo[best] = std::max(ilo[best], P.hi[k][best]);
+            else          ihi[best] = std::min(ihi[best], P.lo[k][best]);
+        }
+        for (int a = 0; a < 3; ++a) {
+            // strict tests against bounds moved one float inward: a point that passes is outside every grown box
+            P.in_lo[a] = nextafterf((float)ilo[a], INFINITY);
+            if ((double)P.in_lo[a] < ilo[a]) P.in_lo[a] = nextafterf(P.in_lo[a], INFINITY);
+            P.in_hi[a] = nextafterf((float)ihi[a], -INFINITY);
+            if ((double)P.in_hi[a] > ihi[a]) P.in_hi[a] = nextafterf(P.in_hi[a], -INFINITY);
+            // the tile's own faces are not constraints: open them up so that border points of the tile count as interior
+            if (ilo[a] == mine[a]) P.in_lo[a] = -INFINITY;
+            if (ihi[a] == mine[3 + a]) P.in_hi[a] = INFINITY;
+        }
     }
     cudaStream_t s = (cudaStream_t)stream;
     const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 256), (int64_t)device_sm_count() * 8));

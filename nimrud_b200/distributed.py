@@ -418,6 +418,44 @@ def _process_tile_cuda(cloud, edge_lengths, radii, out, out_dtype, group, voxel_
     return out, mb.boxes
 
 
+def process_tile_host(cloud, edge_lengths, radii, out=None, out_dtype=np.float64, device=None, group=None, mailbox=None):
+    """
+    this rank's tile with HOST buffers: `cloud` (n_local, 3) numpy array or CPU tensor (float32 / float64; pinned
+    memory is used in place), returns / fills a host array of (n_local, 4*S) rows (nbr_tile_step_host: the tile
+    goes up, the rows come down in batches that overlap the kernels).  collective over the ranks.
+    """
+    from . import _lib, _results
+    from .multiscale import _out_code
+    assert len(edge_lengths) == len(radii), "edge_lengths and radii should be equal-length sequences."
+    np_out, out_code = _out_code(out_dtype)
+    arr = cloud.numpy() if isinstance(cloud, torch.Tensor) else np.asarray(cloud)
+    if arr.dtype not in (np.float32, np.float64):
+        arr = arr.astype(np.float64)
+    arr = np.ascontiguousarray(arr)
+    if arr.ndim != 2 or arr.shape[1] != 3:
+        raise ValueError("wrong point cloud array shape")
+    device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    tdt = torch.float32 if arr.dtype == np.float32 else torch.float64
+    n = int(arr.shape[0])
+    mb = mailbox if mailbox is not None else _mailboxes.get((id(group) if group is not None else 0, device.index, tdt))
+    if mb is None:
+        mb = HaloMailbox.connect_group(device, tdt, default_capacity(n), group)
+        _mailboxes[(id(group) if group is not None else 0, device.index, tdt)] = mb
+    if out is None:
+        out = _results.empty((n, 4 * len(radii)), np_out)
+    out_arr = out.numpy() if isinstance(out, torch.Tensor) else out
+    if out_arr.shape != (n, 4 * len(radii)) or out_arr.dtype != np_out or not out_arr.flags["C_CONTIGUOUS"]:
+        raise ValueError("out has the wrong shape, dtype or layout")
+    edges_arr, edges_p = _lib.f64_array(list(edge_lengths))
+    radii_arr, radii_p = _lib.f64_array(list(radii))
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().nbr_tile_step_host(
+            mb.handle, ctypes.c_void_p(arr.ctypes.data) if n else None, mb.code, n, edges_p, radii_p, len(radii),
+            ctypes.c_void_p(out_arr.ctypes.data) if n else None, out_code, 0,
+            mb.boxes.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
+    return out
+
+
 def process_tiles_local(clouds, edge_lengths, radii, out_dtype=np.float32, mailboxes=None, capacity_rows=None):
     """
     several tiles in ONE process (one device, or one tile per visible device): the same mailbox path as the

@@ -19,7 +19,7 @@ import time
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, _results
 from ._util import device_cloud, host_cloud, is_torch, ptr, require_cuda, stream_ptr, validate_cloud
 from .geometry import cloud_bbox, grid_from_bbox
 
@@ -121,7 +121,11 @@ def process_single_core(query_cloud, search_cloud, edge_lengths, radii, verbose=
             s, sc = q, qc
         else:
             s, sc = host_cloud(search_cloud.cpu().numpy() if is_torch(search_cloud) else search_cloud)
-        out = np.zeros((nq, ncol * n_scales), dtype=np_out)
+        # every element is written by the call; an untouched allocation lets the host threads that fill it fault
+        # its pages in parallel
+        out = _results.empty((nq, ncol * n_scales), np_out)
+        if n_scales == 0 or nq == 0:
+            out[...] = 0
         _lib.check(_lib.lib().nbr_multiscale_features_host(
             ctypes.c_void_p(q.ctypes.data), qc, nq, ctypes.c_void_p(s.ctypes.data), sc, ns, edges_p, radii_p,
             n_scales, ctypes.c_void_p(out.ctypes.data), out_code, mask, counts_p))

@@ -33,6 +33,10 @@ def worker(rank, world, port, tmp):
     feats_nccl = nd.process_tile(mine.cuda().contiguous(), EDGES, RADII, gather=True, out_dtype=np.float32)
     os.environ.pop("NBR_HALO")
     assert torch.equal(feats, feats_nccl)
+    # host buffers (nbr_tile_step_host): float32 on the wire, widened on the host
+    local = nd.process_tile(mine.cuda().contiguous(), EDGES, RADII, out_dtype=np.float32)
+    host_rows = nd.process_tile_host(mine.numpy(), EDGES, RADII, out_dtype=np.float64)
+    assert host_rows.dtype == np.float64 and np.array_equal(host_rows, local.cpu().numpy().astype(np.float64))
     if rank == 0:
         np.save(os.path.join(tmp, "gathered.npy"), feats.cpu().numpy())
     dist.barrier()

@@ -210,9 +210,22 @@ def test_raw_ctypes_stub_from_integration_md():
     from nimrud_b200 import multiscale, synth
     cloud = synth.urban_scene(700_000, seed=9).numpy()
     a = multiscale.process_single_core(cloud[:300_000].copy(), cloud, (0.2, 0.4), (0.6, 1.2))
-    b = multiscale.process_single_core(torch.from_numpy(cloud[:300_000]).cuda(), torch.from_numpy(cloud).cuda(),
-                                       (0.2, 0.4), (0.6, 1.2)).cpu().numpy()
-    assert np.array_equal(a, b)
+    dev_q, dev_s = torch.from_numpy(cloud[:300_000]).cuda(), torch.from_numpy(cloud).cuda()
+    b32 = multiscale.process_single_core(dev_q, dev_s, (0.2, 0.4), (0.6, 1.2), out_dtype=np.float32).cpu().numpy()
+    # host buffers: the rows cross PCIe as float32 and are widened on the host (include/nimrud_b200.h)
+    assert a.dtype == np.float64 and np.array_equal(a, b32.astype(np.float64))
+    # NBR_HOST_WIRE=f64 keeps float64 on the wire: identical to the device-resident float64 rows
+    import os
+    os.environ["NBR_HOST_WIRE"] = "f64"
+    try:
+        a64 = multiscale.process_single_core(cloud[:300_000].copy(), cloud, (0.2, 0.4), (0.6, 1.2))
+    finally:
+        os.environ.pop("NBR_HOST_WIRE")
+    b = multiscale.process_single_core(dev_q, dev_s, (0.2, 0.4), (0.6, 1.2)).cpu().numpy()
+    assert np.array_equal(a64, b)
+    # float32 rows into a pageable float32 result
+    a32 = multiscale.process_single_core(cloud[:300_000].copy(), cloud, (0.2, 0.4), (0.6, 1.2), out_dtype=np.float32)
+    assert np.array_equal(a32, b32)
 
 
 def test_mixed_window_widths_in_one_call(c_oracle):

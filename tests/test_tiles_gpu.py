@@ -191,3 +191,18 @@ def test_mailbox_overflow_is_reported(scene):
     tiles = [cloud[i].contiguous() for i in idx]
     with pytest.raises(RuntimeError, match="dropped"):
         nd.process_tiles_local(tiles, EDGES, RADII, capacity_rows=100)
+
+
+def test_tile_step_with_host_buffers(scene):
+    """nbr_tile_step_host on a world of one tile: rows == the device-resident call (float32 on the wire)."""
+    from nimrud_b200 import distributed as nd
+    cloud, whole = scene
+    mb = nd.HaloMailbox(0, 1, "cuda", torch.float32, 1024)
+    try:
+        host = cloud.cpu().numpy()
+        rows = nd.process_tile_host(host, EDGES, RADII, out_dtype=np.float64, device="cuda:0", mailbox=mb)
+        assert rows.dtype == np.float64 and np.array_equal(rows, whole.cpu().numpy().astype(np.float64))
+        rows32 = nd.process_tile_host(torch.from_numpy(host).pin_memory(), EDGES, RADII, out_dtype=np.float32, device="cuda:0", mailbox=mb)
+        assert np.array_equal(rows32, whole.cpu().numpy())
+    finally:
+        mb.close()
