@@ -180,9 +180,10 @@ int nbr_multiscale_features_host(const void *query_host, int q_dtype, int64_t n_
                                  void *out_host, int out_dtype, int32_t descriptor_mask,
                                  int64_t *n_voxels_host);
 
-/* page-locked host buffers (cudaHostAlloc) for callers that want their clouds / result rows used in place by
- * nbr_multiscale_features_host; the Python shim recycles its result arrays through these. */
-int nbr_host_alloc(size_t bytes, void **out);
+/* host buffers for clouds / result rows.  pinned = 1: page-locked (cudaHostAlloc), used in place by
+ * nbr_multiscale_features_host; pinned = 0: 2 MB-aligned pageable memory with huge pages requested (the Python shim
+ * recycles its result arrays through these: a recycled buffer costs no page faults). */
+int nbr_host_alloc(size_t bytes, int pinned, void **out);
 int nbr_host_free(void *ptr);
 
 /* vector-field multiscale operator (extension; legacy precedent V_MSO, nimrud/prototypes/mso.py:12-257).

@@ -30,7 +30,7 @@ SIGNATURES = {
     "nbr_last_error": (ctypes.c_char_p, []),
     "nbr_version": (ctypes.c_int, []),
     "nbr_trim_memory": (ctypes.c_int, []),
-    "nbr_host_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(c_vp)]),
+    "nbr_host_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(c_vp)]),
     "nbr_host_free": (ctypes.c_int, [c_vp]),
     "nbr_kernel_launches": (c_i64, []),
     "nbr_timing_enable": (None, [ctypes.c_int]),

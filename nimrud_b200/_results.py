@@ -2,9 +2,9 @@
 result arrays of the host-buffer path.
 
 a fresh pageable (N, 4*S) float64 array costs more in page faults (the kernel zeroes 1.6 GB for 10M points x 5
-scales) than its rows cost on the PCIe link.  results are therefore numpy arrays over PAGE-LOCKED buffers from the
-C library, and a buffer whose array (and every view of it) has been garbage collected is kept for the next call of
-the same size.  NBR_RESULT_POOL_MB bounds what is kept (default 4096; 0 disables the pool: plain np.empty).
+scales) than its rows cost on the PCIe link.  results are therefore numpy arrays over buffers from the C library
+(2 MB-aligned, huge pages requested), and a buffer whose array (and every view of it) has been garbage collected is
+kept for the next call of the same size: a recycled buffer is already mapped.  NBR_RESULT_POOL_MB bounds what is kept (default 4096; 0 disables the pool: plain np.empty).
 """
 import ctypes
 import os
@@ -38,7 +38,7 @@ def _release(ptr, nbytes):
 
 
 def empty(shape, dtype):
-    """uninitialised array of `shape`: page-locked and recycled when the pool is enabled, np.empty otherwise."""
+    """uninitialised array of `shape`: recycled when the pool is enabled, np.empty otherwise."""
     global _kept
     dtype = np.dtype(dtype)
     nbytes = int(np.prod(shape)) * dtype.itemsize
@@ -52,8 +52,8 @@ def empty(shape, dtype):
             _kept -= nbytes
     if ptr is None:
         out = ctypes.c_void_p()
-        if _lib.lib().nbr_host_alloc(nbytes, ctypes.byref(out)) != _lib.OK or not out.value:
-            return np.empty(shape, dtype=dtype)           # no page-locked memory left: a plain array
+        if _lib.lib().nbr_host_alloc(nbytes, 0, ctypes.byref(out)) != _lib.OK or not out.value:
+            return np.empty(shape, dtype=dtype)
         ptr = out.value
     raw = (ctypes.c_char * nbytes).from_address(ptr)
     weakref.finalize(raw, _release, ptr, nbytes)          # runs when the array and all its views are gone

@@ -87,8 +87,10 @@ public:
 private:
     HostPool()
     {
-        const char *env = getenv("NBR_HOST_THREADS");
-        int n = env ? atoi(env) : (int)std::thread::hardware_concurrency();
+        // default: this process' share of the cores (torchrun exports LOCAL_WORLD_SIZE: one process per GPU)
+        const char *env = getenv("NBR_HOST_THREADS"), *lws = getenv("LOCAL_WORLD_SIZE");
+        const int share = lws && atoi(lws) > 0 ? atoi(lws) : 1;
+        int n = env ? atoi(env) : (int)std::thread::hardware_concurrency() / share;
         n = std::max(2, std::min(n, 64));                           // at least one worker besides the caller
         for (int i = 0; i + 1 < n; ++i) workers_.emplace_back([this, i] { loop(i); });
     }
@@ -236,19 +238,44 @@ static int upload(void *dev, const void *host, size_t bytes, cudaStream_t stream
 
 using namespace nbr;
 
-// page-locked host memory for result arrays (the Python shim recycles them: a fresh pageable 1.6 GB result costs
-// more in page faults than its rows cost on the wire)
-extern "C" int nbr_host_alloc(size_t bytes, void **out)
+// host memory for clouds / result arrays.  pinned = 1: page-locked (cudaHostAlloc; used in place by the host path,
+// but locking 1.6 GB takes hundreds of milliseconds); pinned = 0: 2 MB-aligned pageable memory with huge pages
+// requested.  the Python shim recycles its result arrays through the pageable kind: a FRESH 1.6 GB result costs
+// more in page faults than its rows cost on the wire, a recycled one costs nothing.
+static std::mutex g_host_alloc_mutex;
+static std::vector<std::pair<void *, int>> g_host_allocs;
+
+extern "C" int nbr_host_alloc(size_t bytes, int pinned, void **out)
 {
     if (!out) return fail(NBR_ERR_INVALID, "nbr_host_alloc: null argument");
     *out = nullptr;
-    NBR_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    if (bytes == 0) bytes = 1;
+    if (pinned) {
+        NBR_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+    } else {
+        const size_t align = 2u << 20, padded = (bytes + align - 1) & ~(align - 1);
+        void *p = nullptr;
+        if (posix_memalign(&p, align, padded) != 0 || !p) return fail(NBR_ERR_INVALID, "nbr_host_alloc: out of host memory");
+        madvise(p, padded, MADV_HUGEPAGE);
+        *out = p;
+    }
+    std::lock_guard<std::mutex> lock(g_host_alloc_mutex);
+    g_host_allocs.emplace_back(*out, pinned);
     return NBR_OK;
 }
 
 extern "C" int nbr_host_free(void *ptr)
 {
-    if (ptr) NBR_CUDA(cudaFreeHost(ptr));
+    if (!ptr) return NBR_OK;
+    int kind = -1;
+    {
+        std::lock_guard<std::mutex> lock(g_host_alloc_mutex);
+        for (size_t i = 0; i < g_host_allocs.size(); ++i)
+            if (g_host_allocs[i].first == ptr) { kind = g_host_allocs[i].second; g_host_allocs.erase(g_host_allocs.begin() + i); break; }
+    }
+    if (kind < 0) return fail(NBR_ERR_INVALID, "nbr_host_free: not a pointer from nbr_host_alloc");
+    if (kind) NBR_CUDA(cudaFreeHost(ptr));
+    else free(ptr);
     return NBR_OK;
 }
 
