@@ -503,16 +503,17 @@ struct BatchDev {
     int n;
 };
 
-template <typename T>
+// DEV_N: the number of points is only known on the device (halo mailbox): n_bound sizes a capped grid that strides
+// over the chunks.  otherwise one chunk per block (the common path keeps its straight-line code)
+template <typename T, bool DEV_N>
 __global__ void __launch_bounds__(256)
 batch_mark_kernel(const T *__restrict__ xyz, int64_t n_bound, const unsigned long long *__restrict__ n_dev,
                   const __grid_constant__ BatchDev B, uint32_t *__restrict__ dir)
 {
-    // n_dev (optional): the number of points is only known on the device (halo mailbox); n_bound sizes the grid
-    const int64_t n = n_dev ? min(n_bound, (int64_t)*n_dev) : n_bound;
-    for (int64_t chunk = blockIdx.x; chunk * PTS * blockDim.x < n; chunk += gridDim.x) {      // one trip unless the grid was capped
+    const int64_t n = DEV_N ? min(n_bound, (int64_t)*n_dev) : n_bound;
+    for (int64_t chunk = blockIdx.x; DEV_N ? chunk * PTS * blockDim.x < n : chunk == blockIdx.x; chunk += gridDim.x) {
     const int64_t base = (chunk * PTS) * blockDim.x + threadIdx.x;
-    if (base - (threadIdx.x & 31) >= n) return;             // the whole warp is past the end
+    if (DEV_N && base - (threadIdx.x & 31) >= n) return;    // the whole warp is past the end
     for (int l = 0; l < B.n; ++l) {
         int64_t b[PTS];
 #pragma unroll
@@ -535,16 +536,16 @@ batch_mark_kernel(const T *__restrict__ xyz, int64_t n_bound, const unsigned lon
     }
 }
 
-template <typename T>
+template <typename T, bool DEV_N>
 __global__ void __launch_bounds__(256)
 batch_fill_kernel(const T *__restrict__ xyz, int64_t n_bound, const unsigned long long *__restrict__ n_dev,
                   const __grid_constant__ BatchDev B, const uint32_t *__restrict__ dir,
                   uint32_t *__restrict__ pool, unsigned char *__restrict__ counters)
 {
-    const int64_t n = n_dev ? min(n_bound, (int64_t)*n_dev) : n_bound;
-    for (int64_t chunk = blockIdx.x; chunk * PTS * blockDim.x < n; chunk += gridDim.x) {      // one trip unless the grid was capped
+    const int64_t n = DEV_N ? min(n_bound, (int64_t)*n_dev) : n_bound;
+    for (int64_t chunk = blockIdx.x; DEV_N ? chunk * PTS * blockDim.x < n : chunk == blockIdx.x; chunk += gridDim.x) {
     const int64_t base = (chunk * PTS) * blockDim.x + threadIdx.x;
-    if (base - (threadIdx.x & 31) >= n) return;             // whole warp past the end: nothing to vote on
+    if (DEV_N && base - (threadIdx.x & 31) >= n) return;    // whole warp past the end: nothing to vote on
     uint32_t pend_old[PTS], pend_bit[PTS];
 #pragma unroll
     for (int k = 0; k < PTS; ++k) { pend_old[k] = ~0u; pend_bit[k] = 0; }
@@ -685,8 +686,13 @@ int lattices_create_batch(Lattice **out, int n_lat, const nbr_grid *grids, const
         if (part_n[p] <= 0) continue;
         // a part whose size is only known on the device gets a capped grid that strides over its chunks
         const unsigned pt_blocks = (unsigned)std::min<int64_t>(ceil_div(part_n[p], 256 * PTS), part_dev[p] ? device_sm_count() * 8 : INT64_MAX);
-        if (dtype == NBR_F32) batch_mark_kernel<float><<<pt_blocks, 256, 0, stream>>>((const float *)parts[p], part_n[p], part_dev[p], B, dir);
-        else                  batch_mark_kernel<double><<<pt_blocks, 256, 0, stream>>>((const double *)parts[p], part_n[p], part_dev[p], B, dir);
+        if (part_dev[p]) {
+            if (dtype == NBR_F32) batch_mark_kernel<float, true><<<pt_blocks, 256, 0, stream>>>((const float *)parts[p], part_n[p], part_dev[p], B, dir);
+            else                  batch_mark_kernel<double, true><<<pt_blocks, 256, 0, stream>>>((const double *)parts[p], part_n[p], part_dev[p], B, dir);
+        } else {
+            if (dtype == NBR_F32) batch_mark_kernel<float, false><<<pt_blocks, 256, 0, stream>>>((const float *)parts[p], part_n[p], nullptr, B, dir);
+            else                  batch_mark_kernel<double, false><<<pt_blocks, 256, 0, stream>>>((const double *)parts[p], part_n[p], nullptr, B, dir);
+        }
         NBR_LAUNCHED();
     }
     NBR_TRY(flags_to_slots(dir, dir_total, n_bricks_total, stream));
@@ -695,8 +701,13 @@ int lattices_create_batch(Lattice **out, int n_lat, const nbr_grid *grids, const
     for (int p = 0; p < 2; ++p) {
         if (part_n[p] <= 0) continue;
         const unsigned pt_blocks = (unsigned)std::min<int64_t>(ceil_div(part_n[p], 256 * PTS), part_dev[p] ? device_sm_count() * 8 : INT64_MAX);
-        if (dtype == NBR_F32) batch_fill_kernel<float><<<pt_blocks, 256, 0, stream>>>((const float *)parts[p], part_n[p], part_dev[p], B, dir, pool, counters);
-        else                  batch_fill_kernel<double><<<pt_blocks, 256, 0, stream>>>((const double *)parts[p], part_n[p], part_dev[p], B, dir, pool, counters);
+        if (part_dev[p]) {
+            if (dtype == NBR_F32) batch_fill_kernel<float, true><<<pt_blocks, 256, 0, stream>>>((const float *)parts[p], part_n[p], part_dev[p], B, dir, pool, counters);
+            else                  batch_fill_kernel<double, true><<<pt_blocks, 256, 0, stream>>>((const double *)parts[p], part_n[p], part_dev[p], B, dir, pool, counters);
+        } else {
+            if (dtype == NBR_F32) batch_fill_kernel<float, false><<<pt_blocks, 256, 0, stream>>>((const float *)parts[p], part_n[p], nullptr, B, dir, pool, counters);
+            else                  batch_fill_kernel<double, false><<<pt_blocks, 256, 0, stream>>>((const double *)parts[p], part_n[p], nullptr, B, dir, pool, counters);
+        }
         NBR_LAUNCHED();
     }
     for (int l = 0; l < n_lat; ++l) {
