@@ -21,13 +21,20 @@
 namespace nbr {
 
 constexpr int R5_WARPS = 4;
-constexpr int R5_CAP = 48;                 // staged bricks per warp (6 KB)
+#ifndef R5_BLOCKS_N
+#define R5_BLOCKS_N 6
+#endif
+#ifndef R5_CAP_N
+#define R5_CAP_N 64
+#endif
+constexpr int R5_CAP = R5_CAP_N;           // staged bricks per warp (128 bytes each)
 constexpr int N11 = 11, W5 = 5;
 constexpr int R5_SLAB_WORDS = 12;          // 11 row words + 1 padding word = 3 x uint4
 constexpr int R5_BIN_WORDS = N11 * R5_SLAB_WORDS;
-constexpr int R5_ULIST = N11 * N11;        // one 16-bit slot per window row and lane (direct mapped)
 constexpr int R5_WIN_BYTES = R5_CAP * BRICK_WORDS * 4;
-constexpr int R5_ULIST_BYTES = ((32 * R5_ULIST * 2 + 127) / 128) * 128;
+constexpr int R5_ULIST_BYTES = 0;          // rows with occupied uncertain cells are only FLAGGED (121 bits per lane) and
+                                           // gathered again when they are decided: parking their masks took 7.8 KB of
+                                           // shared memory per warp and a store per row
 
 // ---- shell table for the 11-wide window: table[bin][slab][12] uint32 = in | unc << 16 per row
 __global__ void __launch_bounds__(256)
@@ -107,13 +114,18 @@ int ball_tables5_trim()
 }
 
 // 11-bit row -> {count | sum(pos) << 8 | sum(pos^2) << 19,  count | sum(pos) << 12}: the first word adds up a
-// whole slab (121 cells) without overflow, the second its jy-weighted sums
-__device__ __forceinline__ uint2 row11_entry(uint32_t b)
+// whole slab (121 cells) without overflow, the second its jy-weighted sums.  the table is split: entry(row) =
+// lo[row & 63] + hi[row >> 6] (the fields are sums over the set bits, the high part carries its positions 6..10):
+// 96 entries (768 bytes) instead of 2048 (16 KB of shared memory per block, which capped the kernel at 12 warps per SM)
+#ifndef R5_SPLIT_LUT
+#define R5_SPLIT_LUT 1
+#endif
+__device__ __forceinline__ uint2 row11_entry(uint32_t b, int first_pos = 0)
 {
     uint32_t cnt = 0, s1 = 0, s2 = 0;
 #pragma unroll
     for (int i = 0; i < N11; ++i)
-        if (b & (1u << i)) { cnt += 1; s1 += i; s2 += i * i; }
+        if (b & (1u << i)) { cnt += 1; s1 += i + first_pos; s2 += (i + first_pos) * (i + first_pos); }
     return make_uint2(cnt | (s1 << 8) | (s2 << 19), cnt | (s1 << 12));
 }
 
@@ -134,6 +146,12 @@ __device__ __noinline__ bool r5_exact_in(const R3Entry &E, double qx, double qy,
     s = __dadd_rn(s, sqdiff(qy, r5_centre(E, ky, 1)));
     s = __dadd_rn(s, sqdiff(qz, r5_centre(E, kz, 2)));
     return s <= __dmul_rn(E.r, E.r);
+}
+
+__device__ __forceinline__ uint2 r5_lut2(const uint2 *lut, uint32_t M)
+{
+    const uint2 a = lut[M & 63u], b = lut[64u + (M >> 6)];
+    return make_uint2(a.x + b.x, a.y + b.y);
 }
 
 struct Acc10 {
@@ -162,19 +180,26 @@ __device__ __forceinline__ void r5_decide(const R3Entry &E, const double q[3], f
 }
 
 template <typename OutT, bool EXT>
-__global__ void __launch_bounds__(R5_WARPS * 32, 4)
+__global__ void __launch_bounds__(R5_WARPS * 32, R5_BLOCKS_N)
 rows5_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query, int dtype,
              const uint32_t *__restrict__ perm, int64_t nq, OutT *__restrict__ out, int64_t row_stride)
 {
     // dynamic shared memory, per warp: brick window | parked rows
     extern __shared__ __align__(128) unsigned char smem_raw[];
+#if R5_SPLIT_LUT
+    __shared__ uint2 s_lut[64 + 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 96; i += blockDim.x) s_lut[i] = i < 64 ? row11_entry(i) : row11_entry(i - 64, 6);
+#define R5_LUT(M) r5_lut2(s_lut, (M))
+#else
     __shared__ uint2 s_lut[1 << N11];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < (1 << N11); i += blockDim.x) s_lut[i] = row11_entry(i);
+#define R5_LUT(M) s_lut[(M)]
+#endif
     unsigned char *warp_base = smem_raw + (size_t)warp * (R5_WIN_BYTES + R5_ULIST_BYTES);
     const uint32_t *win = reinterpret_cast<const uint32_t *>(warp_base);
     const uint32_t win_addr = (uint32_t)__cvta_generic_to_shared(win);
-    unsigned short *ulist = reinterpret_cast<unsigned short *>(warp_base + R5_WIN_BYTES) + lane;   // [121 rows][32 lanes]
     __syncthreads();
     const int64_t n_groups = (nq + 31) >> 5;
     constexpr uint32_t rowmask = (1u << N11) - 1u;
@@ -292,10 +317,9 @@ rows5_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
                         const uint32_t w1 = two ? win[off + BRICK_WORDS] : 0u;
                         const uint32_t bits = __funnelshift_r(w0, w1, sh) & rowmask;
                         const uint32_t M = bits & T[jy], U = bits & (T[jy] >> 16);
-                        // uncertain occupied cells are parked (direct mapped, no branch) and decided after the rows
-                        ulist[32 * (jz * N11 + jy)] = (unsigned short)U;
+                        // rows with uncertain occupied cells are flagged and decided after the rows
                         uflags |= (U ? 1u : 0u) << jy;
-                        const uint2 e = s_lut[M];
+                        const uint2 e = R5_LUT(M);
                         Pk += e.x;
                         Qk += jy * e.y;
                         R += jy * jy * (int)(e.x & 255u);
@@ -326,9 +350,8 @@ rows5_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
                         const uint32_t w1 = slot_b ? E.pool[(int64_t)slot_b * BRICK_WORDS + word] : 0u;
                         const uint32_t bits = __funnelshift_r(w0, w1, sh) & rowmask;
                         const uint32_t M = bits & tw, U = bits & (tw >> 16);
-                        ulist[32 * (jz * N11 + jy)] = (unsigned short)U;
                         uflags |= (U ? 1u : 0u) << jy;
-                        const uint2 e = s_lut[M];
+                        const uint2 e = R5_LUT(M);
                         Pk += e.x;
                         Qk += jy * e.y;
                         R += jy * jy * (int)(e.x & 255u);
@@ -352,7 +375,26 @@ rows5_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
                     fl &= fl - 1;
                     const int rid = b + part * 4 * N11;
                     const int jz = (rid * 373) >> 12, jy = rid - N11 * jz;          // rid / 11 for rid < 121
-                    r5_decide(E, q, fxm, fym, fzm, xa, ya, za, (uint32_t)ulist[32 * rid], jy, jz, A);
+                    // the row's occupancy again (a flagged row is rare: a handful per query), and its uncertain mask
+                    const int az = za + jz, ay = ya + jy;
+                    const int wz = (az & (BRICK_Z - 1)) << BRICK_YS, gz = az >> BRICK_ZS;
+                    uint32_t w0 = 0, w1 = 0;
+                    if (staged) {
+                        const int off = (gz - lo2) * zstride + wz + ybase + jy + (jy >= ycross ? ystep : 0) + (jy >= ycross + BRICK_Y ? ystep : 0);
+                        w0 = win[off];
+                        w1 = two ? win[off + BRICK_WORDS] : 0u;
+                    } else {
+                        const int gy = ay >> BRICK_YS;
+                        const int64_t rowb = ((int64_t)gz * E.nby + gy) * E.nbx;             // flagged rows are inside the directory
+                        const uint32_t slot_a = (bx0 >= 0 && bx0 < E.nbx) ? E.dir[rowb + bx0] : 0u;
+                        const uint32_t slot_b = (two && bx0 + 1 >= 0 && bx0 + 1 < E.nbx) ? E.dir[rowb + bx0 + 1] : 0u;
+                        const int word = wz | (ay & (BRICK_Y - 1));
+                        w0 = slot_a ? E.pool[(int64_t)slot_a * BRICK_WORDS + word] : 0u;
+                        w1 = slot_b ? E.pool[(int64_t)slot_b * BRICK_WORDS + word] : 0u;
+                    }
+                    const uint32_t tw = reinterpret_cast<const uint32_t *>(tab)[jz * R5_SLAB_WORDS + jy];
+                    const uint32_t U = __funnelshift_r(w0, w1, sh) & rowmask & (tw >> 16);
+                    r5_decide(E, q, fxm, fym, fzm, xa, ya, za, U, jy, jz, A);
                 }
             }
             if (active)
