@@ -255,6 +255,107 @@ def run_config4(args, nd, multiscale, dist, synth, lib, rank, world, dev):
     return block
 
 
+def _timed_ms(fn, reps, torch):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def run_extras(args, lib, multiscale, synth, cloud, dev):
+    """the other BASELINE configs that fit one GPU, device-resident, CUDA events: configs[0] (the reference's own
+    example: r/e = 5, the 11-wide-window kernel), the equal-edge variant of configs[1] (one lattice, five
+    radii: 7-wide, 11-wide and interval kernels), configs[2] (10M kNN, k = 10/20/50, ties) and the radix sort."""
+    import ctypes
+    import torch
+    from nimrud_b200 import _lib
+    from nimrud_b200.geometry import VoxelFilter
+    extras = {}
+    n = int(cloud.shape[0])
+    # ---- configs[0]
+    c0 = torch.from_numpy(synth.uniform_box()).to(dev)
+    e0, r0 = (0.1, 0.2, 0.4), (0.5, 1.0, 2.0)
+    ms = _timed_ms(lambda: multiscale.process_single_core(c0, c0, e0, r0, out_dtype=np.float32), 20, torch)
+    extras["config0"] = {"workload": "BASELINE configs[0]: 100k uniform points in 20 x 20 x 2, edges (0.1, 0.2, 0.4), radii (0.5, 1, 2) "
+                                     "(nimrud/minimal/multiscale.py example, r/e = 5)",
+                         "ms_per_step": ms, "value": c0.shape[0] * 3 / (ms * 1e-3), "unit": UNIT,
+                         "reference_1core": "5 723 points*scales/s measured on the reference itself (SURVEY.md 6)"}
+    # ---- equal-edge variant of configs[1]
+    ee, er = (0.2,) * 5, (0.4, 0.6, 0.8, 1.0, 1.2)
+    out = torch.empty((n, 20), dtype=torch.float32, device=dev)
+    ms = _timed_ms(lambda: multiscale.process_single_core(cloud, cloud, ee, er, out_dtype=np.float32, out=out), max(2, min(args.steps, 5)), torch)
+    extras["equal_edge"] = {"workload": "configs[1] scene, one lattice (edge 0.2) shared by five radii 0.4 .. 1.2 (r/e = 2 .. 6)",
+                            "ms_per_step": ms, "value": n * 5 / (ms * 1e-3), "unit": UNIT,
+                            "mean_population": [round(float(out[:, 4 * s].mean()), 1) for s in range(5)]}
+    del out
+    # ---- radix sort of the voxel addresses of the kNN index (the sort inside np.unique, utils/geometry.py:150)
+    kcloud = synth.urban_scene(n, seed=21, device=dev)
+    vf = VoxelFilter(kcloud, 0.1)
+    bits = int(sum(vf.widths))
+    keys0 = vf.coordinate_to_address(kcloud).to(torch.int64).contiguous()
+    keys, tmp = keys0.clone(), torch.empty_like(keys0)
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def sort_once():
+        keys.copy_(keys0)
+        _lib.check(lib.nbr_sort_u64(ctypes.c_void_p(keys.data_ptr()), ctypes.c_void_p(tmp.data_ptr()), n, 0, bits, stream))
+    ms_copy = _timed_ms(lambda: keys.copy_(keys0), 5, torch)
+    ms = _timed_ms(sort_once, 5, torch) - ms_copy
+    passes = (bits + 7) // 8
+    peak, _ = hbm_peak()
+    extras["sort"] = {"what": "LSD radix sort of %d 64-bit voxel addresses, %d key bits, %d passes of 8 bits" % (n, bits, passes),
+                      "ms": ms, "keys_per_s": n / (ms * 1e-3), "algorithmic_gbs": n * 16 * passes / ms / 1e6,
+                      "frac_of_hbm_peak": n * 16 * passes / ms / 1e6 / peak,
+                      "bytes": "16 B per key and pass (one read + one write); the histogram pass re-reads the keys"}
+    del keys, tmp, keys0
+    # ---- configs[2]: kNN over the voxel centres at e = 0.1, 1 % duplicated + 1 % lattice-aligned queries (ties)
+    q = synth.with_ties(kcloud, 0.1, seed=21, fraction=0.01)
+    index = None
+    ms_build = _timed_ms(lambda: multiscale.LatticeIndex(kcloud, 0.1, indexed=True).close(), 2, torch)
+    index = multiscale.LatticeIndex(kcloud, 0.1, indexed=True)
+    res = {}
+    ms50 = _timed_ms(lambda: res.__setitem__("r", index.knn(q, 50, ks=(10, 20, 50), out_dtype=np.float32)), 2, torch)
+    idx, d2, _ = res["r"]
+    # check a spatial subset against a float64 brute force on the device (total order (d2, index)); the CPU oracle check
+    # of the same path is tests/test_knn_gpu.py and scripts/config3.py
+    addr, cen = index.addresses_and_centres()
+    lo = torch.tensor([120.0, 120.0], device=dev, dtype=torch.float64)
+    sub = ((q[:, :2].double() >= lo) & (q[:, :2].double() < lo + 34.0)).all(1).nonzero()[:, 0][:20000]
+    near = ((cen[:, :2] >= lo - 6.0) & (cen[:, :2] < lo + 40.0)).all(1).nonzero()[:, 0]
+    ok_rows, checked = 0, 0
+    if sub.numel() and near.numel() >= 50:
+        dmax = d2[sub][:, -1].max().item() ** 0.5
+        qs = q[sub].double()
+        cl = cen[near]
+        same_all = True
+        for a in range(0, qs.shape[0], 256):
+            blk = qs[a:a + 256]
+            dd = ((blk[:, None, 0] - cl[None, :, 0]) ** 2 + (blk[:, None, 1] - cl[None, :, 1]) ** 2) + (blk[:, None, 2] - cl[None, :, 2]) ** 2
+            # total order (d2, index): stable sort by index first (already ascending), then by d2
+            order = torch.sort(dd, dim=1, stable=True).indices[:, :50]
+            ref_idx = near[order]
+            got = idx[sub[a:a + 256]].long()
+            good = (got == ref_idx).all(1) & (d2[sub[a:a + 256]] == torch.gather(dd, 1, order)).all(1)
+            ok_rows += int(good.sum())
+            checked += int(blk.shape[0])
+        check = {"queries": checked, "identical": bool(ok_rows == checked), "margin_ok": bool(dmax < 6.0),
+                 "how": "float64 brute force on the device over the voxel centres around a 34 m x 34 m window, "
+                        "stable sort = (d2, index) order"}
+    else:
+        check = None
+    extras["knn"] = {"workload": "BASELINE configs[2]: %d queries (10M points + 1 %% duplicates + 1 %% lattice-aligned) against the %d voxel "
+                                 "centres of the cloud at e = 0.1, k = 50 with features for k = 10 / 20 / 50" % (q.shape[0], index.n_voxels),
+                     "ms": ms50, "queries_per_s": q.shape[0] / (ms50 * 1e-3), "value": q.shape[0] * 3 / (ms50 * 1e-3), "unit": UNIT,
+                     "indexed_lattice_build_ms": ms_build, "check": check}
+    index.close()
+    return extras
+
+
 def gpu_arm(args, rank, world, local_rank):
     import ctypes
     import torch
@@ -410,6 +511,10 @@ def gpu_arm(args, rank, world, local_rank):
         if seam is not None:
             seam["gathered_rows_match_local"] = same
 
+    extras = None
+    if world == 1 and not args.no_extras:
+        extras = run_extras(args, lib, multiscale, synth, cloud, dev)
+
     # ---- BASELINE configs[3]: 100M-point aerial tile split over the ranks (strong scaling)
     config4 = None
     if not args.no_config4:
@@ -480,6 +585,8 @@ def gpu_arm(args, rank, world, local_rank):
              if os.environ.get("NBR_HALO", "mailbox") != "nccl" else ": NCCL all-gather + all-to-all-v")
     if config4 is not None:
         line["config4"] = config4
+    if extras is not None:
+        line["extra"] = extras
     print(json.dumps(line), flush=True)
     if dist is not None:
         nd.release_mailboxes()
@@ -496,6 +603,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-config4", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--config4-points", type=int, default=100_000_000)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -283,6 +283,10 @@ int nbr_tile_step_host(nbr_mailbox *mailbox, const void *xyz_host, int dtype, in
                        const double *radii_host, int32_t n_scales, void *out_host, int out_dtype,
                        int32_t descriptor_mask, double *boxes_host_out);
 
+/* debug builds only (-DNBR_BOUNDS_CHECK=1, scripts/bounds_check.sh): number of out-of-range shared-memory indices the
+ * fused kernel has seen on the current device; always 0 in a normal build. */
+int64_t nbr_debug_bounds_violations(void);
+
 /* counters for tests and benches: number of kernels this library has launched in this process. */
 int64_t nbr_kernel_launches(void);
 

@@ -33,6 +33,7 @@ SIGNATURES = {
     "nbr_host_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(c_vp)]),
     "nbr_host_free": (ctypes.c_int, [c_vp]),
     "nbr_kernel_launches": (c_i64, []),
+    "nbr_debug_bounds_violations": (c_i64, []),
     "nbr_timing_enable": (None, [ctypes.c_int]),
     "nbr_timing_read": (ctypes.c_int, [ctypes.POINTER(c_f64)]),
     "nbr_bbox": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, ctypes.c_int, c_vp, c_vp]),

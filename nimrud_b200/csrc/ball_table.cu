@@ -94,11 +94,20 @@ int ball_table_get(double rho2, double margin, int Q, int row_bits, const uint4 
 // process that keeps asking for new r/e ratios drops every table once no kernel can be reading them
 int ball_tables_trim()
 {
+    // only the CURRENT device's tables, and only after that device has drained: a table of another device may be in
+    // use by a kernel this thread cannot wait for.  (a process that drives one device from several host threads
+    // must not interleave feature calls with more than 128 distinct r/e ratios in flight)
+    int dev = 0;
+    NBR_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lock(g_table_mutex);
-    if (g_tables.size() < 128) return NBR_OK;
+    size_t mine = 0;
+    for (auto &kv : g_tables) mine += std::get<0>(kv.first) == dev;
+    if (mine < 128) return NBR_OK;
     NBR_CUDA(cudaDeviceSynchronize());
-    for (auto &kv : g_tables) cudaFree(const_cast<uint4 *>(kv.second));
-    g_tables.clear();
+    for (auto it = g_tables.begin(); it != g_tables.end();) {
+        if (std::get<0>(it->first) == dev) { cudaFree(const_cast<uint4 *>(it->second)); it = g_tables.erase(it); }
+        else ++it;
+    }
     return NBR_OK;
 }
 

@@ -312,9 +312,17 @@ __device__ __forceinline__ void emit_features_window(int n, int sx, int sy, int 
 {
     double centroid = 0.0;
     if (n > 0) {
-        const float inv = rcp_fast((float)n);
-        const float dx = fxm - (float)sx * inv, dy = fym - (float)sy * inv, dz = fzm - (float)sz * inv;
-        centroid = (double)sqrt_fast(dx * dx + dy * dy + dz * dz) * edge;
+        if (sizeof(OutT) == 8) {
+            // float64 rows: the sums are exact integers, only the query's window position (fxm ..., float32) limits
+            // the column: |error| <= 3e-7 * edge, relative accuracy is kept when the centroid is close to the query
+            const double inv = 1.0 / (double)n;
+            const double dx = (double)fxm - (double)sx * inv, dy = (double)fym - (double)sy * inv, dz = (double)fzm - (double)sz * inv;
+            centroid = sqrt(dx * dx + dy * dy + dz * dz) * edge;
+        } else {
+            const float inv = rcp_fast((float)n);
+            const float dx = fxm - (float)sx * inv, dy = fym - (float)sy * inv, dz = fzm - (float)sz * inv;
+            centroid = (double)sqrt_fast(dx * dx + dy * dy + dz * dz) * edge;
+        }
     }
     double a[6];
     if (SMALL) {

@@ -52,6 +52,18 @@ namespace nbr {
 #ifndef R3_TAB_PREFETCH
 #define R3_TAB_PREFETCH 0           // the next slab's table masks are loaded one slab ahead
 #endif
+// NBR_BOUNDS_CHECK=1 (debug builds; compute-sanitizer is closed on the pool this was developed on): every shared-memory
+// index of the window gather, the parked-cell list and the row buffer is checked against the warp's own buffers and
+// violations are counted (nbr_debug_bounds_violations()).  scripts/bounds_check.sh builds and runs such a variant.
+#ifndef NBR_BOUNDS_CHECK
+#define NBR_BOUNDS_CHECK 0
+#endif
+__device__ unsigned long long g_r3_violations = 0;
+#if NBR_BOUNDS_CHECK
+#define R3_CHECK(cond) do { if (!(cond)) atomicAdd(&g_r3_violations, 1ull); } while (0)
+#else
+#define R3_CHECK(cond) do { } while (0)
+#endif
 constexpr int R3_WARPS = R3_WARPS_N;
 constexpr int R3_UNROLL = R3_UNROLL_N;   // slabs per trip of the slab loop
 constexpr int R3_CAP = R3_CAP_N;          // staged bricks per warp (128 bytes each)
@@ -284,6 +296,9 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
 #pragma unroll
                     for (int jy = 0; jy < N7; ++jy) {
                         const int off = zoff + jy + (jy >= ycross ? ystep : 0);
+                        // w0 inside the staged bricks; w1 (read unconditionally) at most one brick further: inside the
+                        // window + table area of this warp
+                        R3_CHECK(off >= 0 && off < R3_CAP * BRICK_WORDS && off + BRICK_WORDS < (R3_WIN_BYTES + R3_TAB_BYTES) / 4);
                         const uint32_t w0 = win[off];
 #if R3_W1_ALWAYS
                         const uint32_t w1 = win[off + BRICK_WORDS];   // unused bits when !two; stays inside the warp's buffers
@@ -326,6 +341,7 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
                 if (!__any_sync(0xffffffffu, (Mlo | Mhi | Ulo | Uhi) != 0)) continue;
                 // the uncertain cells are parked in the lane's table line (slots <= jz are consumed) and decided after
                 // the slab loop in ONE loop: deciding them slab by slab made every slab wait for its slowest lane
+                R3_CHECK(n_u <= 2 * jz && n_u + 1 < 2 * N7);                             // both stores land in consumed slots of the lane's line
                 ulist[n_u] = make_uint2(Ulo, (uint32_t)jz);                               // slot n_u <= 2 jz + 1: consumed
                 n_u += Ulo != 0;
                 ulist[n_u] = make_uint2(Uhi, (uint32_t)jz | 256u);
@@ -539,3 +555,10 @@ int rows3_launch(const R3Launch *L, const void *query, int dtype, const uint32_t
 }
 
 }  // namespace nbr
+
+extern "C" int64_t nbr_debug_bounds_violations(void)
+{
+    unsigned long long v = 0;
+    if (cudaMemcpyFromSymbol(&v, nbr::g_r3_violations, sizeof(v)) != cudaSuccess) return -1;
+    return (int64_t)v;
+}

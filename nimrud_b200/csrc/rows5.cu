@@ -105,11 +105,18 @@ static int ball_table5_get(double rho2, double margin, int Q, const uint32_t **o
 
 int ball_tables5_trim()
 {
+    // the current device's tables only (see ball_tables_trim)
+    int dev = 0;
+    NBR_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lock(g_table5_mutex);
-    if (g_tables5.size() < 128) return NBR_OK;
+    size_t mine = 0;
+    for (auto &kv : g_tables5) mine += std::get<0>(kv.first) == dev;
+    if (mine < 128) return NBR_OK;
     NBR_CUDA(cudaDeviceSynchronize());
-    for (auto &kv : g_tables5) cudaFree(const_cast<uint32_t *>(kv.second));
-    g_tables5.clear();
+    for (auto it = g_tables5.begin(); it != g_tables5.end();) {
+        if (std::get<0>(it->first) == dev) { cudaFree(const_cast<uint32_t *>(it->second)); it = g_tables5.erase(it); }
+        else ++it;
+    }
     return NBR_OK;
 }
 
