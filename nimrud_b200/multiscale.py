@@ -109,10 +109,15 @@ def process_single_core(query_cloud, search_cloud, edge_lengths, radii, verbose=
         if global_bbox is not None:
             box_arr, box_p = _lib.f64_array(np.concatenate([np.asarray(global_bbox[0], dtype=np.float64),
                                                              np.asarray(global_bbox[1], dtype=np.float64)]))
-        with torch.cuda.device(q.device):
-            _lib.check(_lib.lib().nbr_multiscale_features(
-                ptr(q), qc, nq, ptr(s), sc, ns, edges_p, radii_p, n_scales, ptr(out), out_code, mask, box_p,
-                counts_p, stream_ptr(q.device)))
+        try:
+            with torch.cuda.device(q.device):
+                _lib.check(_lib.lib().nbr_multiscale_features(
+                    ptr(q), qc, nq, ptr(s), sc, ns, edges_p, radii_p, n_scales, ptr(out), out_code, mask, box_p,
+                    counts_p, stream_ptr(q.device)))
+        except NotImplementedError as err:
+            if "directory" not in str(err) or global_bbox is not None or counts_p is not None:
+                raise
+            _process_in_tiles(q, s, edge_lengths, radii, out, out_dtype, descriptors)
     else:
         if global_bbox is not None or out is not None:
             raise ValueError("global_bbox / out are only supported for CUDA tensor inputs")
@@ -126,9 +131,18 @@ def process_single_core(query_cloud, search_cloud, edge_lengths, radii, verbose=
         out = _results.empty((nq, ncol * n_scales), np_out)
         if n_scales == 0 or nq == 0:
             out[...] = 0
-        _lib.check(_lib.lib().nbr_multiscale_features_host(
+        rc = _lib.lib().nbr_multiscale_features_host(
             ctypes.c_void_p(q.ctypes.data), qc, nq, ctypes.c_void_p(s.ctypes.data), sc, ns, edges_p, radii_p,
-            n_scales, ctypes.c_void_p(out.ctypes.data), out_code, mask, counts_p))
+            n_scales, ctypes.c_void_p(out.ctypes.data), out_code, mask, counts_p)
+        if rc == _lib.ERR_UNSUPPORTED and "directory" in _lib.last_error() and counts_p is None:
+            # sparse cloud over a large extent: tile by tile on the device (see _process_in_tiles)
+            dq = torch.from_numpy(q).cuda()
+            ds = dq if search_cloud is query_cloud else torch.from_numpy(s).cuda()
+            dout = torch.zeros((nq, ncol * n_scales), dtype=_TORCH_OUT[np_out], device=dq.device)
+            _process_in_tiles(dq, ds, edge_lengths, radii, dout, out_dtype, descriptors)
+            out[...] = dout.cpu().numpy()
+        else:
+            _lib.check(rc)
         if is_torch(query_cloud):
             out = torch.from_numpy(out)
 
@@ -144,6 +158,77 @@ def process_single_core(query_cloud, search_cloud, edge_lengths, radii, verbose=
         print("final rate of {} points per second".format(np.around(nq / max(elapsed, 1e-12), 3)))
     if return_voxel_counts:
         return out, counts[:n_scales].copy()
+    return out
+
+
+def _process_in_tiles(q, s, edge_lengths, radii, out, out_dtype, descriptors, max_dir_entries=4.0e8):
+    """
+    a cloud whose bounding box is too large for a dense brick directory (the reference only needs the packed voxel
+    address to fit 64 bits, utils/geometry.py:55-60): the x-y plane is cut into square tiles small enough for their
+    directories, every tile's queries run against the search points of the tile grown by h = max(r + e/2), and
+    every lattice stays anchored on the WHOLE search cloud's box -- the same voxels, hence the same rows, as one
+    unpartitioned call (the multi-GPU tile path proves the same decomposition bit for bit, tests/test_tiles_gpu.py).
+    q, s: CUDA tensors; out: preallocated CUDA tensor, rows in the queries' order.
+    """
+    from .distributed import halo_width
+    ncol, mask = _ncol(descriptors)
+    np_out, out_code = _out_code(out_dtype)
+    lo = s.min(0).values.double()
+    hi = s.max(0).values.double()
+    g_lo, g_hi = lo.cpu().numpy(), hi.cpu().numpy()
+    grid_from_bbox(g_lo, g_hi, float(min(edge_lengths)), 3)          # ValueError if the address needs more than 64 bits
+    h = halo_width(edge_lengths, radii)
+    e_min = float(min(edge_lengths))
+    lz = float(g_hi[2] - g_lo[2]) + 2 * h + 8 * e_min
+    # directory entries of a tile of side T: (T + 2h)^2 * lz / (1024 e^3) for the finest lattice (bricks of 32 x 8 x 4)
+    side = (max_dir_entries * 1024.0 * e_min ** 3 / lz) ** 0.5 - 2 * h
+    if not side > 4 * h:
+        raise NotImplementedError("cloud too tall / edge too small for tiled processing (tile side %.3g, halo %.3g)" % (side, h))
+    nx = max(1, int(np.ceil((g_hi[0] - g_lo[0]) / side)))
+    ny = max(1, int(np.ceil((g_hi[1] - g_lo[1]) / side)))
+    if nx * ny > 1 << 20:
+        raise NotImplementedError("cloud extent needs more than 2^20 tiles")
+
+    def tile_ids(c):
+        ix = ((c[:, 0].double() - lo[0]) / side).floor().clamp_(0, nx - 1).long()
+        iy = ((c[:, 1].double() - lo[1]) / side).floor().clamp_(0, ny - 1).long()
+        return iy * nx + ix
+
+    q_tile = tile_ids(q)
+    q_order = torch.argsort(q_tile)
+    q_sorted_tile = q_tile[q_order]
+    tiles, q_counts = torch.unique_consecutive(q_sorted_tile, return_counts=True)
+    q_starts = torch.cumsum(q_counts, 0) - q_counts
+    same = s is q
+    s_tile = q_tile if same else tile_ids(s)
+    s_order = q_order if same else torch.argsort(s_tile)
+    s_sorted_tile = s_tile[s_order]
+    s_starts_all = torch.searchsorted(s_sorted_tile, torch.arange(nx * ny + 1, device=s.device))
+    s_starts_all = s_starts_all.cpu().numpy()
+    out.zero_()
+    for t, q0, qn in zip(tiles.cpu().tolist(), q_starts.cpu().tolist(), q_counts.cpu().tolist()):
+        ty, tx = divmod(t, nx)
+        rows = q_order[q0:q0 + qn]
+        t_lo = torch.tensor([float(g_lo[0]) + tx * side - h, float(g_lo[1]) + ty * side - h], dtype=torch.float64, device=s.device)
+        t_hi = t_lo + side + 2 * h
+        parts = []
+        for yy in range(max(ty - 1, 0), min(ty + 1, ny - 1) + 1):
+            for xx in range(max(tx - 1, 0), min(tx + 1, nx - 1) + 1):
+                a, b = int(s_starts_all[yy * nx + xx]), int(s_starts_all[yy * nx + xx + 1])
+                if b > a:
+                    cand = s[s_order[a:b]]
+                    if (yy, xx) != (ty, tx):
+                        keep = ((cand[:, :2].double() >= t_lo) & (cand[:, :2].double() <= t_hi)).all(1)
+                        cand = cand[keep]
+                    parts.append(cand)
+        if not parts:
+            continue
+        search = torch.cat(parts, 0).contiguous() if len(parts) > 1 else parts[0].contiguous()
+        if search.shape[0] < 2:
+            search = torch.cat([search, search], 0)                    # one point: the same voxel set, and the C entry wants two
+        tile_out = process_single_core(q[rows].contiguous(), search, edge_lengths, radii, out_dtype=out_dtype,
+                                       descriptors=descriptors, global_bbox=(g_lo, g_hi))
+        out[rows] = tile_out
     return out
 
 
@@ -182,6 +267,10 @@ class LatticeIndex(object):
         self.grid = grid_from_bbox(lo, hi, edge_length, 3)
         self.indexed = bool(indexed)
         handle = ctypes.c_void_p()
+        # the lattice is built (and later freed) on the stream that is current now; calls made under another
+        # stream are ordered after the build, and the release after them (_sync_streams)
+        self._stream = torch.cuda.current_stream(self.device)
+        self._used_on = set()
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().nbr_lattice_create(
                 ctypes.byref(handle), ptr(self._search), self._code, self._search.shape[0], ctypes.byref(self.grid),
@@ -189,9 +278,18 @@ class LatticeIndex(object):
         self._handle = handle
         self._counts = None
 
+    def _sync_streams(self):
+        """order the current stream after the lattice's build stream (no-op when they are the same stream)."""
+        cur = torch.cuda.current_stream(self.device)
+        if cur != self._stream:
+            cur.wait_stream(self._stream)
+            self._used_on.add(cur)
+
     def close(self):
         if getattr(self, "_handle", None):
-            with torch.cuda.device(self.device):       # frees are ordered on this device's stream
+            with torch.cuda.device(self.device):       # frees are ordered on the build stream: after every user
+                for st in getattr(self, "_used_on", ()):
+                    self._stream.wait_stream(st)
                 _lib.lib().nbr_lattice_destroy(self._handle)
             self._handle = None
 
@@ -219,6 +317,7 @@ class LatticeIndex(object):
 
     def addresses_and_centres(self):
         """(sorted unique addresses int64 (Nv,), centres float64 (Nv,3)) as CUDA tensors."""
+        self._sync_streams()
         nv = self.n_voxels
         addr = torch.empty(nv, dtype=torch.int64, device=self.device)
         cen = torch.empty((nv, 3), dtype=torch.float64, device=self.device)
@@ -228,6 +327,7 @@ class LatticeIndex(object):
 
     def radius_features(self, query_cloud, radii, out_dtype=np.float64, descriptors="reference", algorithm=0):
         """(Nq, C*len(radii)) features for several radii sharing this lattice's edge; CUDA tensor."""
+        self._sync_streams()
         validate_cloud(query_cloud, "query_cloud")
         np_out, out_code = _out_code(out_dtype)
         ncol, mask = _ncol(descriptors)
@@ -242,6 +342,7 @@ class LatticeIndex(object):
 
     def radius_sets(self, query_cloud, radius):
         """CSR neighbor index sets (offsets int64 (Nq+1,), indices int32) -- what query_ball_tree returns."""
+        self._sync_streams()
         validate_cloud(query_cloud, "query_cloud")
         q, qc = device_cloud(query_cloud, self.device)
         nq = q.shape[0]
@@ -260,6 +361,7 @@ class LatticeIndex(object):
         k nearest voxels per query in (squared distance, index) order.
         returns (indices int32 (Nq,k), d2 float64 (Nq,k)[, features (Nq, C*len(ks))]).
         """
+        self._sync_streams()
         validate_cloud(query_cloud, "query_cloud")
         q, qc = device_cloud(query_cloud, self.device)
         nq = q.shape[0]

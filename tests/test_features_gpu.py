@@ -345,3 +345,31 @@ def test_many_scales_in_one_call(c_oracle):
         out = multiscale.process_single_core(q, cloud, edges, radii, out_dtype=dt)
         assert out.shape == (2500, 72)
         assert_features_close(out, ref, radii)
+
+
+def test_large_extent_sparse_cloud_is_tiled():
+    """a 10 km x 10 km x 200 m cloud at e = 0.1 fits the reference's 64-bit voxel address (17 + 17 + 11 bits,
+    utils/geometry.py:55-60) but not a dense brick directory: the shim processes it tile by tile with the lattices
+    anchored on the whole cloud's box.  checked against the oracle; numpy and CUDA-tensor inputs."""
+    from nimrud_b200 import multiscale
+    from oracle import nimrud_oracle as O
+    rs = np.random.RandomState(4)
+    a = rs.rand(3000, 3) * [25.0, 25.0, 3.0]
+    b = rs.rand(3000, 3) * [25.0, 25.0, 3.0] + [9990.0, 9970.0, 197.0]
+    lone = np.array([[5000.0, 5000.0, 100.0]])
+    cloud = np.concatenate([a, b, lone]).astype(np.float32)
+    edges, radii = (0.1, 0.4), (0.3, 1.2)
+    with pytest.raises(NotImplementedError):
+        multiscale.LatticeIndex(cloud, 0.1)                       # the dense directory itself still refuses
+    got = multiscale.process_single_core(cloud, cloud, edges, radii)
+    ref = O.process(cloud.astype(np.float64), cloud.astype(np.float64), edges, radii)
+    assert_features_close(got, ref, radii)
+    assert got[-1, 0] == 1.0 and got[-1, 4] == 1.0                # the lone point sees its own voxel
+    dev = torch.from_numpy(cloud).cuda()
+    got_dev = multiscale.process_single_core(dev, dev, edges, radii, out_dtype=np.float32)
+    assert np.array_equal(got_dev.cpu().numpy()[:, 0::4], ref[:, 0::4].astype(np.float32))
+    # separate query cloud, some queries outside the search cloud's box
+    q = np.concatenate([cloud[::7], [[-0.2, 3.0, 1.0], [12000.0, 0.0, 0.0]]]).astype(np.float32)
+    got_q = multiscale.process_single_core(q, cloud, edges, radii)
+    ref_q = O.process(q.astype(np.float64), cloud.astype(np.float64), edges, radii)
+    assert_features_close(got_q, ref_q, radii)
