@@ -541,19 +541,30 @@ def gpu_arm(args, rank, world, local_rank):
     rho = counts_all / float(n * world)
     algo_bytes = float(sum(n * (28.0 + 12.0 * r) for r in rho))
     achieved = algo_bytes / (feat_ms * 1e-3) / 1e9 if feat_ms > 0 else 0.0
-    traffic, traffic_src = None, None
+    traffic, traffic_src, secondary = None, None, None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_rows3_traffic.json")))
-        if world == 1 and n == 10_000_000:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_rows3_traffic.json")))
+        if n == 10_000_000:
             traffic = float(tr["dram_bytes_read"] + tr["dram_bytes_write"])
             traffic_src = "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel " \
-                          "on this workload (profiles/r01_rows3_traffic.json)"
+                          "on this workload (profiles/r02_rows3_traffic.json)"
+            # the secondary bounds beside the HBM figure.  the kernel is bound by instruction issue
+            secondary = {"bound": "instruction issue (integer / FP32 pipes)",
+                         "issue_slot_util": tr["issue_slot_util_pct"] / 100.0,
+                         "inst_per_point_scale": tr["warp_instructions"] / float(n * ns),
+                         "inst_unit": "warp instructions per query and scale (x 32 / threads_per_instruction for thread instructions)",
+                         "threads_per_instruction": tr["threads_per_instruction"],
+                         "l2_gbs": tr["lts_sectors"] * 32.0 / (tr["gpu_time_ms_under_ncu"] * 1e-3) / 1e9,
+                         "l2_hit_rate": tr["l2_hit_rate_pct"] / 100.0,
+                         "pipes_pct_of_peak": tr["pipes_pct_of_peak"],
+                         "source": "the same ncu capture (profiles/r02_rows3_ncu_raw.csv)"}
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "nbr::rows3_kernel: fused radius query + covariance + eigen + features "
                                           "(one launch for all scales of a step)",
                 "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "secondary": secondary,
                 "algorithmic_bytes_per_step": algo_bytes, "kernel_ms_per_step": feat_ms,
                 "bytes_per_point_scale": "28 + 12*rho_s (SURVEY.md 8d); rho_s = unique voxels / queries = %s"
                                          % [round(float(r), 4) for r in rho],
