@@ -200,6 +200,66 @@ __device__ __forceinline__ void eig3_unit_trace(const double a[6], double l[3], 
     }
 }
 
+// ---- eigenvalue ratios from SMALL INTEGER matrices (the window kernels' fast path, reference columns only)
+//
+// the window kernels hand over n*S2 - S1*S1^T as exact integers below 2^28.  for those the ratios do not need an
+// eigenvector: with c1 = sum of the principal 2x2 minors / tr^2 (EXACT numerator: int64) and c0 = det / tr^3 the
+// normalised spectrum solves  l^3 - l^2 + c1 l - c0 = 0.
+//   * the isolated root (largest if the depressed cubic's cos(theta) >= 0, smallest otherwise) is well conditioned:
+//     float32 trigonometric estimate, two Newton steps in float64;
+//   * the other two follow from the deflated quadratic  m^2 - s m + P,  s = 1 - l,  P = c1 - l s.  a (near-)double
+//     root of the pair costs sqrt(1e-16) = 1e-8 absolute, i.e. <= 1e-5 relative for any pair a window of integer
+//     offsets can produce (the smallest non-zero normalised eigenvalue of such a matrix is > 1e-4) -- and the one case
+//     where the pair is a double root at ZERO (collinear voxels, rank <= 1) is detected exactly: c1's numerator is 0.
+// about a third of the instructions of the eigenvector-deflation route (eig3_unit_trace), which stays in use for the
+// extended columns, the interval / exact / kNN kernels (larger integers) and near-isotropic matrices.
+#ifndef NBR_FAST_EIG
+#define NBR_FAST_EIG 1
+#endif
+__device__ __forceinline__ bool eig_ratios_small_int(int a0, int a1, int a2, int a3, int a4, int a5, double tr, double it,
+                                                     double &l0, double &l1)
+{
+    const long long m01 = (long long)a0 * a3 - (long long)a1 * a1;
+    const long long m02 = (long long)a0 * a5 - (long long)a2 * a2;
+    const long long m12 = (long long)a3 * a5 - (long long)a4 * a4;
+    const long long C1 = m01 + m02 + m12;                   // exact; > 0 unless the voxels are collinear
+    if (C1 <= 0) { l0 = 1.0; l1 = 0.0; return true; }
+    const double d01 = (double)((long long)a1 * a5 - (long long)a4 * a2), d02 = (double)((long long)a1 * a4 - (long long)a3 * a2);
+    const double D = (double)a0 * (double)m12 - (double)a1 * d01 + (double)a2 * d02;
+    it = it * (2.0 - tr * it);                               // 1 / tr to the last bit: c1 and c0 feed a square root below
+    const double it2 = it * it;
+    const double c1 = (double)C1 * it2;
+    const double c0 = fmax(D * it2 * it, 0.0);
+    // depressed cubic m^3 + a m + b, l = 1/3 + m
+    const float p2 = (float)(1.0 / 3.0 - c1) * (1.0f / 3.0f);          // -a / 3
+    if (!(p2 > 1.0e-7f)) return false;                                  // near-isotropic: the careful route
+    const float bf = (float)(c1 * (1.0 / 3.0) - 2.0 / 27.0 - c0);
+    const float ip = rsqrtf(p2);
+    const float pf = p2 * ip;
+    float r = -0.5f * bf * ip * ip * ip;                                // cos(theta)
+    r = fminf(1.0f, fmaxf(-1.0f, r));
+    const float phi = acosf(r) * (1.0f / 3.0f);
+    const bool top = r >= 0.0f;                                         // the largest root is the isolated one
+    double lam = 1.0 / 3.0 + (double)(2.0f * pf * __cosf(top ? phi : phi + 2.0943951f));
+#pragma unroll
+    for (int itn = 0; itn < 2; ++itn) {
+        const double pl = ((lam - 1.0) * lam + c1) * lam - c0;
+        const double dp = (3.0 * lam - 2.0) * lam + c1;                 // (l - la)(l - lb): away from 0 at the isolated root
+        lam -= pl * (double)rcp_fast((float)dp);
+    }
+    const double s = 1.0 - lam, mid = 0.5 * s;
+    const double P = c1 - lam * s;
+    const double disc = mid * mid - P;
+    double rad = 0.0;
+    if (disc > 1.0e-30) {
+        const double y0 = (double)rsqrtf((float)disc);
+        rad = disc * (y0 * (1.5 - 0.5 * disc * y0 * y0));
+    }
+    if (top) { l0 = lam; l1 = mid + rad; }
+    else     { l0 = mid + rad; l1 = mid - rad; }
+    return true;
+}
+
 // x > 0, else x == 0 and y > 0, else z > 0: the sign convention of the emitted leading eigenvectors
 __device__ __forceinline__ void canonical_sign_xy(double w[3])
 {
@@ -243,7 +303,7 @@ static __device__ __noinline__ void extended_descriptors(const double l[3], doub
 // (exact integers converted to double).  writes 4 (reference) or 26 (extended) columns at out[0..]
 template <typename OutT>
 __device__ __forceinline__ void emit_core(long long n_int, double centroid, double a[6], double edge, OutT *out,
-                                          int descriptor_mask)
+                                          int descriptor_mask, const int *small_ints = nullptr)
 {
     const int ncol = (descriptor_mask & NBR_DESC_EXTENDED) ? NBR_COLS_EXTENDED : NBR_COLS_REFERENCE;
     const double n = (double)n_int;
@@ -258,15 +318,23 @@ __device__ __forceinline__ void emit_core(long long n_int, double centroid, doub
             // 1/tr: float32 seed + one Newton step (relative error ~1e-14)
             const double r0 = (double)rcp_fast((float)tr);
             const double it = r0 * (2.0 - tr * r0);
+            bool done = false;
+#if NBR_FAST_EIG
+            if (small_ints && !(descriptor_mask & NBR_DESC_EXTENDED))
+                done = eig_ratios_small_int(small_ints[0], small_ints[1], small_ints[2], small_ints[3], small_ints[4], small_ints[5],
+                                            tr, it, l0, l1);
+#endif
+            if (!done) {
 #pragma unroll
-            for (int i = 0; i < 6; ++i) a[i] *= it;
-            double l[3], v[3], lead[3];
-            if (descriptor_mask & NBR_DESC_EXTENDED) eig3_unit_trace<true>(a, l, v, lead);
-            else eig3_unit_trace<false>(a, l, v, lead);
-            l0 = l[0];
-            l1 = l[1];
-            if ((descriptor_mask & NBR_DESC_EXTENDED) && n_int >= 3)
-                extended_descriptors(l, v, lead, tr * edge * edge / (n * (n - 1.0)), a, ext);
+                for (int i = 0; i < 6; ++i) a[i] *= it;
+                double l[3], v[3], lead[3];
+                if (descriptor_mask & NBR_DESC_EXTENDED) eig3_unit_trace<true>(a, l, v, lead);
+                else eig3_unit_trace<false>(a, l, v, lead);
+                l0 = l[0];
+                l1 = l[1];
+                if ((descriptor_mask & NBR_DESC_EXTENDED) && n_int >= 3)
+                    extended_descriptors(l, v, lead, tr * edge * edge / (n * (n - 1.0)), a, ext);
+            }
         }
     }
     out[0] = (OutT)n;
@@ -325,15 +393,18 @@ __device__ __forceinline__ void emit_features_window(int n, int sx, int sy, int 
         }
     }
     double a[6];
+    int ai[6] = {0, 0, 0, 0, 0, 0};
     if (SMALL) {
-        a[0] = (double)(n * sxx - sx * sx); a[1] = (double)(n * sxy - sx * sy); a[2] = (double)(n * sxz - sx * sz);
-        a[3] = (double)(n * syy - sy * sy); a[4] = (double)(n * syz - sy * sz); a[5] = (double)(n * szz - sz * sz);
+        ai[0] = n * sxx - sx * sx; ai[1] = n * sxy - sx * sy; ai[2] = n * sxz - sx * sz;
+        ai[3] = n * syy - sy * sy; ai[4] = n * syz - sy * sz; ai[5] = n * szz - sz * sz;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) a[i] = (double)ai[i];
     } else {
         const long long N = n, X = sx, Y = sy, Z = sz;
         a[0] = (double)(N * sxx - X * X); a[1] = (double)(N * sxy - X * Y); a[2] = (double)(N * sxz - X * Z);
         a[3] = (double)(N * syy - Y * Y); a[4] = (double)(N * syz - Y * Z); a[5] = (double)(N * szz - Z * Z);
     }
-    emit_core<OutT>(n, centroid, a, edge, out, descriptor_mask);
+    emit_core<OutT>(n, centroid, a, edge, out, descriptor_mask, SMALL ? ai : nullptr);
 }
 
 // anchor cell and fractional position of a query on one axis.  c is clamped so that far-away

@@ -316,7 +316,9 @@ def test_many_distinct_radius_ratios_recycle_the_table_caches(c_oracle):
 def test_table_kernels_against_the_per_candidate_kernel_at_scale():
     # two independent code paths on 2M queries of the 10M-point scene: the shell-table kernels decide most
     # cells by table lookup, the per-candidate kernel evaluates the reference's float64 expression for every
-    # occupied cell of the window.  populations (neighbor set sizes) must be identical, eigen ratios equal to 1e-9.
+    # occupied cell of the window.  populations (neighbor set sizes) must be identical; the eigen ratios come from two
+    # different solvers (cubic + deflated quadratic on exact integer minors vs eigenvector deflation) and must agree
+    # 100x tighter than the parity bar: a double root of the quadratic costs sqrt(1e-16) = 1e-8 absolute.
     import torch
     from nimrud_b200 import multiscale, synth
     cloud = synth.urban_scene(10_000_000, seed=20, device="cuda")
@@ -330,7 +332,8 @@ def test_table_kernels_against_the_per_candidate_kernel_at_scale():
         d = (fast - slow).abs()
         for k, r in enumerate(radii):
             assert d[:, 4 * k + 1].max().item() <= 1e-5 * r          # centroid: float32 vs float64 finish
-            assert d[:, 4 * k + 2:4 * k + 4].max().item() <= 1e-9    # same integer moments, same eigen-solver
+            lim = 1e-6 * slow[:, 4 * k + 2:4 * k + 4].abs() + 1e-9
+            assert bool((d[:, 4 * k + 2:4 * k + 4] <= lim).all())      # same integer moments, two eigen-solvers
 
 
 def test_many_scales_in_one_call(c_oracle):
