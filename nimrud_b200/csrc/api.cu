@@ -132,7 +132,8 @@ int radius_features_exact(const Lattice *lat, const void *query, int dtype, cons
 int morton_order(const void *xyz, int dtype, int64_t n, const double lohi[6], double cell, uint32_t *perm_out,
                  void *sorted_xyz_out, cudaStream_t stream);
 int cell_order(const void *xyz, int dtype, int64_t n, const double lohi[6], const double origin[3],
-               const double cell_in[3], uint32_t *perm_out, void *sorted_xyz_out, cudaStream_t stream);
+               const double cell_in[3], uint32_t *perm_out, void *sorted_xyz_out, cudaStream_t stream,
+               const GridDev *finest = nullptr, CellOrderInfo *info = nullptr);
 int compact_prefix_queries(const uint32_t *perm, const void *sorted, int dtype, int64_t n, int64_t nq, uint32_t *perm_q,
                            void *sorted_q, cudaStream_t stream);
 int radius_sets(const Lattice *lat, const void *query, int dtype, int64_t nq, double radius, int64_t *offsets,
@@ -224,11 +225,14 @@ static int host_bbox(const void *xyz, int dtype, int64_t n, double *lohi_host, c
     return NBR_OK;
 }
 
-static int brick_origin(const double *lohi, const double *local_box, double finest, double origin[3]);
+static int brick_origin(const double *lohi, const double *local_box, double finest, double origin[3], GridDev *gdev = nullptr);
+int order_queries(const void *query, int q_dtype, int64_t nq, const double *qbox_known, double finest,
+                  const double *origin, Scratch &perm, Scratch &sorted, cudaStream_t stream,
+                  const GridDev *finest_grid = nullptr, CellOrderInfo *info = nullptr);
 
 int plan_create(Plan **out, const void *search, int s_dtype, int64_t ns, const double *edges, const double *radii,
                 int n_scales, int descriptor_mask, const double *global_lohi, const double *known_local_box,
-                cudaStream_t stream, const void *search2, int64_t ns2, Mailbox *mailbox)
+                cudaStream_t stream, const void *search2, int64_t ns2, Mailbox *mailbox, const CellOrderInfo *order)
 {
     NBR_TRY(check_cloud_dtype(s_dtype, "multiscale_features"));
     if (n_scales < 0) return fail(NBR_ERR_INVALID, "multiscale_features: negative number of scales");
@@ -269,7 +273,7 @@ int plan_create(Plan **out, const void *search, int s_dtype, int64_t ns, const d
             nbr_grid grids[LATTICE_BATCH];
             Lattice *made[LATTICE_BATCH] = {nullptr};
             for (int k = 0; !rc && k < nb; ++k) rc = grid_from_bbox(lohi, lohi + 3, P->groups[base + k].edge, 3, &grids[k]);
-            if (!rc) rc = lattices_create_batch(made, nb, grids, search, s_dtype, ns, stream, global_lohi ? P->local_box : nullptr, search2, ns2, mailbox);
+            if (!rc) rc = lattices_create_batch(made, nb, grids, search, s_dtype, ns, stream, global_lohi ? P->local_box : nullptr, search2, ns2, mailbox, order);
             if (!rc) for (int k = 0; k < nb; ++k) P->groups[base + k].lat = made[k];
         }
     }
@@ -345,13 +349,14 @@ int plan_run_sorted(const Plan *P, const void *sorted, int q_dtype, const uint32
 }
 
 // corner of brick (0,0,0) of the lattice with edge `finest` that plan_create would build for this box
-static int brick_origin(const double *lohi, const double *local_box, double finest, double origin[3])
+static int brick_origin(const double *lohi, const double *local_box, double finest, double origin[3], GridDev *gdev)
 {
     nbr_grid grid;
     GridDev d;
     NBR_TRY(grid_from_bbox(lohi, lohi + 3, finest, 3, &grid));
     NBR_TRY(grid_to_dev(&grid, &d, local_box));
     for (int a = 0; a < 3; ++a) origin[a] = d.minc[a] + (double)d.cell_lo[a] * finest;
+    if (gdev) *gdev = d;
     return NBR_OK;
 }
 
@@ -359,7 +364,8 @@ static int brick_origin(const double *lohi, const double *local_box, double fine
 // aligned like the bricks of the finest lattice (origin = its minimum corner); NBR_ORDER=morton: Z-curve of
 // cells of 4 finest voxels, radix sorted
 int order_queries(const void *query, int q_dtype, int64_t nq, const double *qbox_known, double finest,
-                  const double *origin, Scratch &perm, Scratch &sorted, cudaStream_t stream)
+                  const double *origin, Scratch &perm, Scratch &sorted, cudaStream_t stream, const GridDev *finest_grid,
+                  CellOrderInfo *info)
 {
     NBR_TRY(perm.alloc(sizeof(uint32_t) * nq, stream));
     NBR_TRY(sorted.alloc((size_t)nq * 3 * (q_dtype == NBR_F32 ? 4 : 8), stream));
@@ -371,7 +377,7 @@ int order_queries(const void *query, int q_dtype, int64_t nq, const double *qbox
     if (use_morton) return morton_order(query, q_dtype, nq, qbox, 4.0 * finest, perm.as<uint32_t>(), sorted.ptr, stream);
     const double cell[3] = {BRICK_X * finest, BRICK_Y * finest, BRICK_Z * finest};
     const double org[3] = {origin ? origin[0] : qbox[0], origin ? origin[1] : qbox[1], origin ? origin[2] : qbox[2]};
-    return cell_order(query, q_dtype, nq, qbox, org, cell, perm.as<uint32_t>(), sorted.ptr, stream);
+    return cell_order(query, q_dtype, nq, qbox, org, cell, perm.as<uint32_t>(), sorted.ptr, stream, finest_grid, info);
 }
 
 // features of one batch of queries in arbitrary order -> rows [0, nq) of `out`
@@ -420,9 +426,12 @@ int multiscale_features(const void *query, int q_dtype, int64_t nq, const void *
         NBR_TRY(host_bbox(search, s_dtype, ns, box, stream));
         Scratch perm, sorted, perm_q, sorted_q;
         double origin[3];
-        NBR_TRY(brick_origin(global_lohi ? global_lohi : box, global_lohi ? box : nullptr, finest, origin));
-        NBR_TRY(order_queries(search, s_dtype, ns, box, finest, origin, perm, sorted, stream));
-        NBR_TRY(plan_create(&P, sorted.ptr, s_dtype, ns, edges, radii, n_scales, descriptor_mask, global_lohi, box, stream));
+        GridDev fgrid;
+        CellOrderInfo order;
+        NBR_TRY(brick_origin(global_lohi ? global_lohi : box, global_lohi ? box : nullptr, finest, origin, &fgrid));
+        NBR_TRY(order_queries(search, s_dtype, ns, box, finest, origin, perm, sorted, stream, &fgrid, &order));
+        NBR_TRY(plan_create(&P, sorted.ptr, s_dtype, ns, edges, radii, n_scales, descriptor_mask, global_lohi, box, stream, nullptr, 0,
+                            nullptr, &order));
         if (nq < ns) {
             rc = perm_q.alloc(sizeof(uint32_t) * nq, stream);
             if (!rc) rc = sorted_q.alloc((size_t)nq * 3 * (q_dtype == NBR_F32 ? 4 : 8), stream);
@@ -624,9 +633,12 @@ int tile_step_plan(Mailbox *M, const void *xyz, int dtype, int64_t n, const doub
         local[a] = std::max(mine[a] - h, glob[a]);
         local[3 + a] = std::min(mine[3 + a] + h, glob[3 + a]);
     }
-    NBR_TRY(brick_origin(glob, local, finest, origin));
-    NBR_TRY(order_queries(xyz, dtype, n, mine, finest, origin, perm, sorted, s));
-    return plan_create(P_out, sorted.ptr, dtype, n, edges_host, radii_host, n_scales, descriptor_mask, glob, local, s, nullptr, 0, M);
+    GridDev fgrid;
+    CellOrderInfo order;
+    NBR_TRY(brick_origin(glob, local, finest, origin, &fgrid));
+    NBR_TRY(order_queries(xyz, dtype, n, mine, finest, origin, perm, sorted, s, &fgrid, &order));
+    return plan_create(P_out, sorted.ptr, dtype, n, edges_host, radii_host, n_scales, descriptor_mask, glob, local, s, nullptr, 0, M,
+                       &order);
 }
 }  // namespace nbr
 

@@ -7,6 +7,7 @@
 
 #include <atomic>
 #include <string>
+#include <utility>
 
 #include "../../include/nimrud_b200.h"
 
@@ -53,6 +54,7 @@ struct Scratch {
     void release();
     template <typename T>
     T *as() const { return reinterpret_cast<T *>(ptr); }
+    void swap(Scratch &o) { std::swap(ptr, o.ptr); std::swap(stream, o.stream); }
 };
 
 int device_sm_count();
@@ -102,6 +104,20 @@ struct LatticeDev {
     const uint32_t *pool;         // [slots][32] occupancy words; word = (z&3)*8 + (y&7), bit = x&31
     const uint32_t *rowbase;      // [slots][32] index (np.unique order) of the first voxel of the row; or NULL
     const uint64_t *ukeys;        // sorted unique packed addresses (np.unique order); or NULL
+};
+
+// what the query order (order.cu) leaves behind for the lattice build when its cells ARE the bricks of the finest
+// lattice (cell coordinates from the lattice's own exact cell arithmetic): the first ordered point of every cell.
+// cells are numbered in blocks of 8 x 8 x 8, Z-curve inside a block (order.cu); the bricks a cell's points can touch
+// on every lattice follow from the cell alone, so the build marks bricks per occupied CELL instead of per point.
+struct CellOrderInfo {
+    Scratch offsets;            // uint32 [n_cells]: exclusive scan of the cell populations
+    int64_t n_cells = 0;
+    int64_t n_points = 0;
+    int32_t bdims[3] = {0, 0, 0};   // blocks of 8 x 8 x 8 cells per axis
+    int32_t dims[3] = {0, 0, 0};    // cells per axis (== bricks of the finest lattice)
+    double finest = 0.0;            // edge of the lattice whose bricks the cells are
+    bool valid = false;
 };
 
 #ifdef __CUDACC__
@@ -163,6 +179,33 @@ __device__ __forceinline__ uint32_t lanemask_lt()
 }
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// rare path of point_cell: u = (p - minc) * (1/e) sits next to an integer, only the division tells the cell
+static __device__ __noinline__ int cell_by_division(double d, double edge)
+{
+    return (int)fmin(fmax(floor(__ddiv_rn(d, edge)), -2.0e9), 2.0e9);
+}
+
+// LOCAL cell of point i on every axis: floor((p - min_corner) / e) - cell_lo  (utils/geometry.py:107),
+// bit-identical to cell_coord_f but with one multiply, one float64 -> int conversion and a short test in
+// the common case (the quotient is only formed when the product is within a few ulp of an integer)
+template <typename T>
+__device__ __forceinline__ void point_cell(const T *__restrict__ xyz, int64_t i, const GridDev &g, int c[3])
+{
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const double d = __dsub_rn((double)xyz[i * 3 + a], g.minc[a]);
+        const double u = d * g.inv_edge;
+        int k = __double2int_rd(u);
+        const double fr = u - (double)k;                  // in [0, 1] when u is in int range
+        const double tol = 4.0e-15 * fabs(u) + 1e-300;
+        if (!(fr > tol && fr < 1.0 - tol)) k = cell_by_division(d, g.edge);
+        // search points lie inside the covered range by construction; the clamp defends against a
+        // caller-supplied box that does not contain them.
+        c[a] = clampi(k - g.cell_lo[a], 0, g.ncell[a] - 1);
+    }
+}
+
 #endif
 
 }  // namespace nbr

@@ -5,7 +5,10 @@
 // nimrud/minimal/multiscale.py:75-87.
 #include <math.h>
 
+#include <stdlib.h>
+
 #include <memory>
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -240,32 +243,6 @@ int unique_sorted(const uint64_t *sorted, int64_t n, uint64_t *out, int64_t *n_o
 // ------------------------------------------------------------------------------------------------
 // lattice (bit bricks)
 // ------------------------------------------------------------------------------------------------
-// rare path of point_cell: u = (p - minc) * (1/e) sits next to an integer, only the division tells the cell
-static __device__ __noinline__ int cell_by_division(double d, double edge)
-{
-    return (int)fmin(fmax(floor(__ddiv_rn(d, edge)), -2.0e9), 2.0e9);
-}
-
-// LOCAL cell of point i on every axis: floor((p - min_corner) / e) - cell_lo  (utils/geometry.py:107),
-// bit-identical to cell_coord_f but with one multiply, one float64 -> int conversion and a short test in
-// the common case (the quotient is only formed when the product is within a few ulp of an integer)
-template <typename T>
-__device__ __forceinline__ void point_cell(const T *__restrict__ xyz, int64_t i, const GridDev &g, int c[3])
-{
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        const double d = __dsub_rn((double)xyz[i * 3 + a], g.minc[a]);
-        const double u = d * g.inv_edge;
-        int k = __double2int_rd(u);
-        const double fr = u - (double)k;                  // in [0, 1] when u is in int range
-        const double tol = 4.0e-15 * fabs(u) + 1e-300;
-        if (!(fr > tol && fr < 1.0 - tol)) k = cell_by_division(d, g.edge);
-        // search points lie inside the covered range by construction; the clamp defends against a
-        // caller-supplied box that does not contain them.
-        c[a] = clampi(k - g.cell_lo[a], 0, g.ncell[a] - 1);
-    }
-}
-
 // mark / fill handle PTS points per thread with the loads of all of them in flight together: the kernels are
 // bound by the latency of the dependent directory / pool accesses, not by bandwidth
 #ifndef NBR_PTS
@@ -617,10 +594,105 @@ batch_fill_kernel(const T *__restrict__ xyz, int64_t n_bound, const unsigned lon
     }
 }
 
+// bricks of every lattice that the points of an occupied ORDER CELL can touch (order.cu: the cells are the bricks of
+// the finest lattice of the batch, so for that lattice the cell IS the brick; for a coarser lattice the cell's box
+// [P_lo, P_hi) maps to a range of its cells, at most 2 x 2 x 2 bricks).  one thread per cell of the dense cell array
+// instead of one directory read + store per point and lattice.  a marked brick may stay empty (the range is a
+// superset by a 1e-6-cell slack against the rounding of the two cell computations): it costs a zero brick.
+struct CellsDev {
+    int bdims[3];
+    int dims[3];
+    int finest;                          // index of the lattice whose bricks the cells are
+    // cell coordinate c (in bricks of the finest lattice) -> position of the cell's low face on axis a, in cells of
+    // lattice l (global numbering):  alpha[l][a] + beta[l][a] * c ;  the high face is one beta further
+    double alpha[LATTICE_BATCH][3], beta[LATTICE_BATCH][3];
+};
+
+// one WARP per 512 cells of the order (8 x 8 x 8, Z-curve inside; no block-wide barrier: the latency chains of the
+// 64 warps of an SM overlap): the occupied cells of the group are compacted in the warp's shared memory, then a lane
+// per occupied cell (a few dozen per group) takes the lattices in turn
+constexpr int CM_WARPS = 8;
+__global__ void __launch_bounds__(CM_WARPS * 32)
+cells_mark_kernel(const uint32_t *__restrict__ offsets, int64_t n_cells, int64_t n_points, int64_t n_groups,
+                  const __grid_constant__ BatchDev B, const __grid_constant__ CellsDev C, uint32_t *__restrict__ dir)
+{
+    __shared__ unsigned short s_list[CM_WARPS][512];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t group = (int64_t)blockIdx.x * CM_WARPS + warp;
+    if (group >= n_groups) return;
+    const int64_t c0 = group * 512;
+    // lane owns cells c0 + 16 lane .. + 15: 17 consecutive offsets
+    uint32_t off[17];
+#pragma unroll
+    for (int k = 0; k < 17; ++k) {
+        const int64_t c = c0 + 16 * lane + k;
+        off[k] = c < n_cells ? offsets[c] : (uint32_t)n_points;
+    }
+    uint32_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) mine |= (off[k + 1] > off[k] ? 1u : 0u) << k;
+    if (!__any_sync(0xffffffffu, mine != 0)) return;     // no point in these 512 cells
+    // exclusive prefix of the lanes' counts
+    const int cnt = __popc(mine);
+    int pre = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, pre, o);
+        if (lane >= o) pre += t;
+    }
+    const int n_occ = __shfl_sync(0xffffffffu, pre, 31);
+    int pos = pre - cnt;
+    for (uint32_t m = mine; m; m &= m - 1) {
+        const uint32_t i = 16u * (uint32_t)lane + (uint32_t)(__ffs(m) - 1);      // Z-curve position inside the group
+        uint32_t lx = 0, ly = 0, lz = 0;
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            lx |= ((i >> (3 * b)) & 1u) << b;
+            ly |= ((i >> (3 * b + 1)) & 1u) << b;
+            lz |= ((i >> (3 * b + 2)) & 1u) << b;
+        }
+        s_list[warp][pos++] = (unsigned short)(lx | (ly << 3) | (lz << 6));
+    }
+    __syncwarp();
+    const uint32_t block = (uint32_t)group;
+    const int sb[3] = {(int)(block % (uint32_t)C.bdims[0]) * 8, (int)((block / (uint32_t)C.bdims[0]) % (uint32_t)C.bdims[1]) * 8,
+                       (int)(block / ((uint32_t)C.bdims[0] * (uint32_t)C.bdims[1])) * 8};
+    for (int ci = lane; ci < n_occ; ci += 32) {
+        const uint32_t pk = s_list[warp][ci];
+        const int cc[3] = {sb[0] + (int)(pk & 7u), sb[1] + (int)((pk >> 3) & 7u), sb[2] + (int)(pk >> 6)};
+        for (int l = 0; l < B.n; ++l) {
+            int b0[3], nb[3];
+            if (l == C.finest) {
+#pragma unroll
+                for (int a = 0; a < 3; ++a) { b0[a] = cc[a]; nb[a] = 0; }
+            } else {
+                const GridDev &g = B.g[l];
+                const int shift[3] = {BRICK_XS, BRICK_YS, BRICK_ZS};
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    // saturating floor conversions; the slack covers the rounding of this map and of the two cell computations
+                    const double u0 = fma(C.beta[l][a], (double)cc[a], C.alpha[l][a]);
+                    const int k0 = max(min(__double2int_rd(u0 - 1.0e-6) - g.cell_lo[a], g.ncell[a] - 1), 0);
+                    const int k1 = max(min(__double2int_rd(u0 + C.beta[l][a] + 1.0e-6) - g.cell_lo[a], g.ncell[a] - 1), 0);
+                    b0[a] = k0 >> shift[a];
+                    nb[a] = (k1 >> shift[a]) - b0[a];            // 0 or 1: a cell is never longer than a brick of a coarser lattice
+                }
+            }
+            uint32_t *e = dir + B.dir_off[l] + ((int64_t)b0[2] * B.nby[l] + b0[1]) * B.nbx[l] + b0[0];
+            const int64_t sy = B.nbx[l], sz = (int64_t)B.nby[l] * B.nbx[l];
+            // unconditional stores (a read first would put its latency on every cell); every writer stores 1
+            for (int z = 0; z <= nb[2]; ++z)
+                for (int y = 0; y <= nb[1]; ++y)
+                    for (int x = 0; x <= nb[0]; ++x) e[z * sz + y * sy + x] = 1u;
+        }
+    }
+}
+
 int halo_wait(Mailbox *M, cudaStream_t stream);
 
 int lattices_create_batch(Lattice **out, int n_lat, const nbr_grid *grids, const void *xyz, int dtype, int64_t n,
-                          cudaStream_t stream, const double *local_lohi, const void *xyz2, int64_t n2, Mailbox *mailbox)
+                          cudaStream_t stream, const double *local_lohi, const void *xyz2, int64_t n2, Mailbox *mailbox,
+                          const CellOrderInfo *order)
 {
     // mailbox: the second part of the search cloud is what the peers pushed into this rank's halo mailbox; its
     // size stays on the device, the grids are sized for the mailbox's capacity
@@ -680,10 +752,39 @@ int lattices_create_batch(Lattice **out, int n_lat, const nbr_grid *grids, const
     const void *parts[2] = {xyz, xyz2};
     const int64_t part_n[2] = {n, n2};
     const unsigned long long *part_dev[2] = {nullptr, n2_dev};
+    // ordered cloud whose order cells are the bricks of the finest lattice of this batch: mark per occupied cell
+    int by_cells = -1;
+    static const bool no_cells = getenv("NBR_INDEX") && std::string(getenv("NBR_INDEX")) == "points";
+    if (!no_cells && order && order->valid && order->n_points == n && order->n_cells > 0)
+        for (int l = 0; l < n_lat; ++l)
+            if (grids[l].edge == order->finest && lat[l]->nbx == order->dims[0] && lat[l]->nby == order->dims[1] &&
+                lat[l]->nbz == order->dims[2])
+                by_cells = l;
+    if (by_cells >= 0)
+        for (int l = 0; l < n_lat; ++l)
+            if (grids[l].edge < order->finest) by_cells = -1;            // a finer lattice in the batch: its bricks are smaller than the cells
     for (int p = 0; p < 2; ++p) {
         // the tile's own bricks are marked while the peers' pushes are still in flight
         if (p == 1 && mailbox) NBR_TRY(halo_wait(mailbox, stream));
         if (part_n[p] <= 0) continue;
+        if (p == 0 && by_cells >= 0) {
+            CellsDev C;
+            memset(&C, 0, sizeof(C));
+            for (int a = 0; a < 3; ++a) { C.bdims[a] = order->bdims[a]; C.dims[a] = order->dims[a]; }
+            C.finest = by_cells;
+            const GridDev &f = B.g[by_cells];
+            const int span[3] = {BRICK_X, BRICK_Y, BRICK_Z};
+            for (int l = 0; l < n_lat; ++l)
+                for (int a = 0; a < 3; ++a) {
+                    C.alpha[l][a] = (f.minc[a] + (double)f.cell_lo[a] * f.edge - B.g[l].minc[a]) * B.g[l].inv_edge;
+                    C.beta[l][a] = span[a] * f.edge * B.g[l].inv_edge;
+                }
+            const int64_t n_groups = ceil_div(order->n_cells, 512);
+            cells_mark_kernel<<<(unsigned)ceil_div(n_groups, CM_WARPS), CM_WARPS * 32, 0, stream>>>(order->offsets.as<uint32_t>(), order->n_cells, n,
+                                                                                                n_groups, B, C, dir);
+            NBR_LAUNCHED();
+            continue;
+        }
         // a part whose size is only known on the device gets a capped grid that strides over its chunks
         const unsigned pt_blocks = (unsigned)std::min<int64_t>(ceil_div(part_n[p], 256 * PTS), part_dev[p] ? device_sm_count() * 8 : INT64_MAX);
         if (part_dev[p]) {

@@ -43,7 +43,7 @@ constexpr int LATTICE_BATCH = 8;
 struct Mailbox;
 int lattices_create_batch(Lattice **out, int n_lat, const nbr_grid *grids, const void *xyz, int dtype, int64_t n,
                           cudaStream_t stream, const double *local_lohi = nullptr, const void *xyz2 = nullptr,
-                          int64_t n2 = 0, Mailbox *mailbox = nullptr);
+                          int64_t n2 = 0, Mailbox *mailbox = nullptr, const CellOrderInfo *order = nullptr);
 int lattice_counts(const Lattice *L, int64_t *n_voxels, int64_t *n_bricks);
 int bbox(const void *xyz, int dtype, int64_t n, int ndim, double *lohi_dev, cudaStream_t stream);
 int grid_from_bbox(const double lo[3], const double hi[3], double edge, int ndim, nbr_grid *out);

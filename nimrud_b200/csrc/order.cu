@@ -131,6 +131,8 @@ struct CellGrid {
     int first[3];
     int dims[3];
     int bdims[3];                 // blocks of 8 x 8 x 8 cells
+    int exact;                    // cells = bricks of `g` (the finest lattice), from its own exact cell arithmetic
+    GridDev g;
 };
 
 // cells are numbered block by block (blocks of 8 x 8 x 8 cells, row-major) and along a Z-curve inside a block:
@@ -140,10 +142,18 @@ struct CellGrid {
 __device__ __forceinline__ uint32_t cell_of(const void *xyz, int dtype, int64_t i, const CellGrid &G)
 {
     uint32_t c[3];
+    if (G.exact) {
+        // the brick of the finest lattice that holds the point, bit-identical to what the lattice build computes
+        int k[3];
+        if (dtype == NBR_F32) point_cell<float>(reinterpret_cast<const float *>(xyz), i, G.g, k);
+        else point_cell<double>(reinterpret_cast<const double *>(xyz), i, G.g, k);
+        c[0] = (uint32_t)(k[0] >> BRICK_XS); c[1] = (uint32_t)(k[1] >> BRICK_YS); c[2] = (uint32_t)(k[2] >> BRICK_ZS);
+    } else {
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        const double u = (load_coord(xyz, dtype, i, 3, a) - G.origin[a]) * G.inv_cell[a];
-        c[a] = (uint32_t)clampi((int)floor(u) - G.first[a], 0, G.dims[a] - 1);
+        for (int a = 0; a < 3; ++a) {
+            const double u = (load_coord(xyz, dtype, i, 3, a) - G.origin[a]) * G.inv_cell[a];
+            c[a] = (uint32_t)clampi((int)floor(u) - G.first[a], 0, G.dims[a] - 1);
+        }
     }
     const uint32_t block = ((c[2] >> 3) * (uint32_t)G.bdims[1] + (c[1] >> 3)) * (uint32_t)G.bdims[0] + (c[0] >> 3);
     const uint32_t z9 = (uint32_t)(spread3(c[0] & 7u) | (spread3(c[1] & 7u) << 1) | (spread3(c[2] & 7u) << 2));
@@ -173,14 +183,31 @@ cell_place_kernel(int64_t n, const uint32_t *__restrict__ offsets, const uint32_
 // lohi: bounding box of the cloud (host).  origin / cell: corner and edge lengths of the cell grid to align
 // with (cells are doubled until the dense counter array fits 2^26 entries).
 int cell_order(const void *xyz, int dtype, int64_t n, const double lohi[6], const double origin[3],
-               const double cell_in[3], uint32_t *perm_out, void *sorted_xyz_out, cudaStream_t stream)
+               const double cell_in[3], uint32_t *perm_out, void *sorted_xyz_out, cudaStream_t stream,
+               const GridDev *finest, CellOrderInfo *info)
 {
+    if (info) info->valid = false;
     if (n <= 0) return NBR_OK;
     if (n >= (int64_t)1 << 32) return fail(NBR_ERR_UNSUPPORTED, "cell_order: more than 2^32 points");
     CellGrid G;
+    memset(&G, 0, sizeof(G));
     double cell[3] = {cell_in[0], cell_in[1], cell_in[2]};
     double total = -1;
-    for (int attempt = 0; attempt < 64; ++attempt) {
+    if (finest) {
+        // cells = the bricks of the finest lattice over its whole directory (every point of the cloud lies inside)
+        double cells = 512.0;
+        for (int a = 0; a < 3; ++a) {
+            G.origin[a] = origin[a];
+            G.inv_cell[a] = 1.0 / cell[a];
+            G.first[a] = 0;
+        }
+        G.dims[0] = (finest->ncell[0] + BRICK_X - 1) / BRICK_X;
+        G.dims[1] = (finest->ncell[1] + BRICK_Y - 1) / BRICK_Y;
+        G.dims[2] = (finest->ncell[2] + BRICK_Z - 1) / BRICK_Z;
+        for (int a = 0; a < 3; ++a) { G.bdims[a] = (G.dims[a] + 7) / 8; cells *= (double)G.bdims[a]; }
+        if (cells <= 67108864.0) { total = cells; G.exact = 1; G.g = *finest; }
+    }
+    for (int attempt = 0; total < 0 && attempt < 64; ++attempt) {
         double cells = 512.0;
         bool ok = true;
         for (int a = 0; a < 3; ++a) {
@@ -214,6 +241,14 @@ int cell_order(const void *xyz, int dtype, int64_t n, const double lohi[6], cons
     if (sorted_xyz_out) {
         gather_kernel<<<blocks, 256, 0, stream>>>(xyz, dtype, n, perm_out, sorted_xyz_out);
         NBR_LAUNCHED();
+    }
+    if (info && G.exact && sorted_xyz_out) {
+        info->offsets.swap(counts);
+        info->n_cells = nc;
+        info->n_points = n;
+        for (int a = 0; a < 3; ++a) { info->bdims[a] = G.bdims[a]; info->dims[a] = G.dims[a]; }
+        info->finest = finest->edge;
+        info->valid = true;
     }
     return NBR_OK;
 }

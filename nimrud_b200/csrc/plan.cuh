@@ -23,7 +23,8 @@ struct Plan {
 
 int plan_create(Plan **out, const void *search, int s_dtype, int64_t ns, const double *edges, const double *radii,
                 int n_scales, int descriptor_mask, const double *global_lohi, const double *known_local_box,
-                cudaStream_t stream, const void *search2 = nullptr, int64_t ns2 = 0, Mailbox *mailbox = nullptr);
+                cudaStream_t stream, const void *search2 = nullptr, int64_t ns2 = 0, Mailbox *mailbox = nullptr,
+                const CellOrderInfo *order = nullptr);
 // features of one batch of queries in arbitrary order -> rows [0, nq) of `out` (device)
 int plan_run(const Plan *P, const void *query, int q_dtype, int64_t nq, const double *qbox_known, void *out,
              int out_dtype, cudaStream_t stream);
