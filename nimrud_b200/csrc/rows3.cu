@@ -193,7 +193,17 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
                 const long long n2 = (long long)((__reduce_max_sync(0xffffffffu, c2) + W3) >> BRICK_ZS) - lo2 + 1;
                 staged = n0 <= R3_CAP && n1 <= R3_CAP && n2 <= R3_CAP && n0 * n1 * n2 <= R3_CAP;
                 nb0 = (int)n0; nb1 = (int)n1;
-                if (P.stats && lane == 0) atomicAdd(P.stats + li * 8 + (staged ? 0 : 1), 1ull);
+                if (P.stats) {
+                    // diagnostics: staged / direct warps, and the number of distinct anchor cells among the warp's queries
+                    const unsigned long long key = ((unsigned long long)(uint32_t)c0 << 42) ^ ((unsigned long long)(uint32_t)c1 << 21) ^ (uint32_t)c2;
+                    const uint32_t peers = __match_any_sync(0xffffffffu, key);
+                    const int leaders = __popc(__ballot_sync(0xffffffffu, (peers & lanemask_lt()) == 0));
+                    if (lane == 0) {
+                        atomicAdd(P.stats + li * 8 + (staged ? 0 : 1), 1ull);
+                        atomicAdd(P.stats + li * 8 + 2, (unsigned long long)leaders);
+                        if (leaders <= 8) atomicAdd(P.stats + li * 8 + 3, 1ull);
+                    }
+                }
                 // stage every lane's table line and (window fits) the bricks of the warp's window:
                 // brick (ix,iy,iz) -> win[((iz*nb1)+iy)*nb0+ix][32]; empty and out-of-range bricks copy slot 0 (zeros)
                 const int total = staged ? nb0 * nb1 * (int)n2 : 0;
@@ -574,8 +584,9 @@ int rows3_launch(const R3Launch *L, const void *query, int dtype, const uint32_t
         NBR_CUDA(cudaMemcpyAsync(h, stats.ptr, sizeof(h), cudaMemcpyDeviceToHost, stream));
         NBR_CUDA(cudaStreamSynchronize(stream));
         for (int l = 0; l < L->n; ++l)
-            fprintf(stderr, "[nbr rows3 stats] entry %d edge %.3g r %.3g: staged warps %llu, direct warps %llu\n", l,
-                    L->e[l].edge, L->e[l].r, h[l * 8], h[l * 8 + 1]);
+            fprintf(stderr, "[nbr rows3 stats] entry %d edge %.3g r %.3g: staged warps %llu, direct warps %llu, distinct anchor cells per warp %.2f, warps with <= 8: %.1f %%\n", l,
+                    L->e[l].edge, L->e[l].r, h[l * 8], h[l * 8 + 1], (double)h[l * 8 + 2] / (double)(h[l * 8] + h[l * 8 + 1]),
+                    100.0 * (double)h[l * 8 + 3] / (double)(h[l * 8] + h[l * 8 + 1]));
     }
     return NBR_OK;
 }

@@ -28,11 +28,16 @@ from ._util import is_torch
 # --------------------------------------------------------------------------------------------------
 # feature block
 # --------------------------------------------------------------------------------------------------
-def scaleset_features(query_cloud, search_cloud, scaleset, out_dtype=np.float32, descriptors="reference"):
+def scaleset_features(query_cloud, search_cloud, scaleset, out_dtype=np.float32, descriptors="reference",
+                      drop_empty=False):
     """
     scaleset = [(voxel_edge, [radius, ...]), ...]  ->  (N, C * total_scales) features, scale-major in the
     caller's order (C = 4 reference columns, or 26 with descriptors="extended").  every radius of a group
     shares the group's voxel lattice: one index build and one staged window per group on the device.
+
+    drop_empty=True follows the legacy driver's row rule (nimrud/prototypes/apc.py:565, 655-660: "if a point gets
+    a feature from at least one pass ... it will be represented in the index set"): returns (index, features) with
+    only the queries whose neighborhood is non-empty at one scale at least, index = their rows in query_cloud.
     """
     edges, radii = [], []
     for edge, group in scaleset:
@@ -41,9 +46,13 @@ def scaleset_features(query_cloud, search_cloud, scaleset, out_dtype=np.float32,
             radii.append(float(r))
     feats = multiscale.process_single_core(query_cloud, search_cloud, edges, radii, out_dtype=out_dtype,
                                            descriptors=descriptors)
-    if is_torch(feats):
-        return torch.nan_to_num(feats)
-    return np.nan_to_num(feats)
+    feats = torch.nan_to_num(feats) if is_torch(feats) else np.nan_to_num(feats)
+    if not drop_empty:
+        return feats
+    ncol = feats.shape[1] // max(len(radii), 1) if len(radii) else 4
+    populated = (feats[:, 0::ncol] > 0).any(1) if len(radii) else feats[:, :0].any(1)
+    index = populated.nonzero()[:, 0] if is_torch(feats) else np.nonzero(populated)[0]
+    return index, feats[index]
 
 
 # --------------------------------------------------------------------------------------------------

@@ -40,3 +40,18 @@ def test_classifier_handoff_matches_oracle_features(c_oracle):
     diff = np.abs(a["confusion_mean"] - b["confusion_mean"]).max()
     assert diff <= 0.02 * a["confusion_mean"].sum(0).max(), diff
     assert gpu["producer"].mean() > 60.0                                    # the 4 components are separable
+
+
+def test_scaleset_drop_empty_rule():
+    """legacy row rule (prototypes/apc.py:565, 655-660): a query is represented if one pass at least gave it a feature."""
+    from nimrud_b200 import learning, synth
+    cloud = synth.urban_scene(20_000, seed=3).numpy()
+    far = np.array([[1e4, 1e4, 50.0], [-500.0, 3.0, 2.0]], dtype=np.float32)
+    q = np.concatenate([cloud[:500], far])
+    scaleset = [(0.2, [0.4, 0.6]), (0.4, [1.2])]
+    full = learning.scaleset_features(q, cloud, scaleset)
+    idx, kept = learning.scaleset_features(q, cloud, scaleset, drop_empty=True)
+    assert full.shape == (502, 12)
+    assert np.array_equal(idx, np.nonzero((full[:, 0::4] > 0).any(1))[0])
+    assert 500 not in idx and 501 not in idx and len(idx) >= 490
+    assert np.array_equal(kept, full[idx])
