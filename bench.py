@@ -353,6 +353,30 @@ def run_extras(args, lib, multiscale, synth, cloud, dev):
                      "ms": ms50, "queries_per_s": q.shape[0] / (ms50 * 1e-3), "value": q.shape[0] * 3 / (ms50 * 1e-3), "unit": UNIT,
                      "indexed_lattice_build_ms": ms_build, "check": check}
     index.close()
+    del idx, d2, res
+    # ---- configs[2], raw-point variant (the legacy sspedge = 0): the same queries against the 10M unfiltered points
+    res = {}
+    ms_raw = _timed_ms(lambda: res.__setitem__("r", multiscale.knn_points(q, kcloud, 50, ks=(10, 20, 50), out_dtype=np.float32)), 2, torch)
+    idx, d2, _ = res["r"]
+    near = ((kcloud[:, :2].double() >= lo - 6.0) & (kcloud[:, :2].double() < lo + 40.0)).all(1).nonzero()[:, 0]
+    check = None
+    if sub.numel() and near.numel() >= 50:
+        dmax = d2[sub][:, -1].max().item() ** 0.5
+        qs, cl = q[sub].double(), kcloud[near].double()
+        ok_rows = checked = 0
+        for a in range(0, qs.shape[0], 128):
+            blk = qs[a:a + 128]
+            dd = ((blk[:, None, 0] - cl[None, :, 0]) ** 2 + (blk[:, None, 1] - cl[None, :, 1]) ** 2) + (blk[:, None, 2] - cl[None, :, 2]) ** 2
+            order = torch.sort(dd, dim=1, stable=True).indices[:, :50]
+            good = (idx[sub[a:a + 128]].long() == near[order]).all(1) & (d2[sub[a:a + 128]] == torch.gather(dd, 1, order)).all(1)
+            ok_rows += int(good.sum())
+            checked += int(blk.shape[0])
+        check = {"queries": checked, "identical": bool(ok_rows == checked), "margin_ok": bool(dmax < 6.0),
+                 "how": "float64 brute force on the device over the raw points around a 34 m x 34 m window, stable sort = (d2, index) order"}
+    extras["knn_raw_points"] = {"workload": "the same %d queries against the %d UNFILTERED points (search over raw points, legacy sspedge = 0), "
+                                            "k = 50 with features for k = 10 / 20 / 50; cell index built inside the call" % (q.shape[0], n),
+                                "ms": ms_raw, "queries_per_s": q.shape[0] / (ms_raw * 1e-3), "value": q.shape[0] * 3 / (ms_raw * 1e-3),
+                                "unit": UNIT, "check": check}
     return extras
 
 

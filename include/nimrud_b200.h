@@ -155,6 +155,15 @@ int nbr_knn(const nbr_lattice *lattice, const void *query_xyz, int dtype, int64_
             int out_dtype, int64_t out_row_stride, int32_t col_offset, int32_t descriptor_mask,
             void *stream);
 
+/* k nearest RAW POINTS of the search cloud (no voxel filter; the legacy pipeline's sspedge = 0,
+ * nimrud/prototypes/mso.py:277,303-308; no counterpart in nimrud/minimal).  total order (float64 squared distance,
+ * index in search_xyz).  builds its own cell index per call (cell_edge: hint for the cell size, <= 0 = automatic).
+ * outputs as nbr_knn; the feature columns use the float64 moments of the k nearest points themselves. */
+int nbr_knn_points(const void *search_xyz, int s_dtype, int64_t n_search, const void *query_xyz, int q_dtype,
+                   int64_t n_query, int32_t k, double cell_edge, int32_t *idx_out, double *d2_out,
+                   const int32_t *ks_host, int32_t n_k, void *feats_out, int out_dtype, int64_t out_row_stride,
+                   int32_t col_offset, int32_t descriptor_mask, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * whole path
  * ---------------------------------------------------------------------------------------------- */

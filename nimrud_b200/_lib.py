@@ -56,6 +56,8 @@ SIGNATURES = {
     "nbr_radius_sets": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_i64, c_f64, c_vp, c_vp, c_vp]),
     "nbr_knn": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_i64, c_i32, c_vp, c_vp, ctypes.POINTER(c_i32), c_i32,
                                c_vp, ctypes.c_int, c_i64, c_i32, c_i32, c_vp]),
+    "nbr_knn_points": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_vp, ctypes.c_int, c_i64, c_i32, c_f64, c_vp, c_vp,
+                                      ctypes.POINTER(c_i32), c_i32, c_vp, ctypes.c_int, c_i64, c_i32, c_i32, c_vp]),
     "nbr_voxel_vector_means": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_i64, c_vp, c_i32, c_vp, c_vp]),
     "nbr_radius_vector_means": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_i64, c_f64, c_vp, c_i32, c_vp, ctypes.c_int,
                                                c_i64, c_i32, c_vp]),

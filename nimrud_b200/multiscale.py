@@ -385,13 +385,52 @@ class LatticeIndex(object):
         return (idx, d2) if feats is None else (idx, d2, feats)
 
 
+def knn_points(query_cloud, search_cloud, k, ks=None, out_dtype=np.float64, descriptors="reference", cell_edge=0.0):
+    """
+    k nearest RAW points of the search cloud per query (no voxel filter; the legacy sspedge = 0), in
+    (squared distance, index) order.  returns (indices int32 (Nq,k) into search_cloud, d2 float64 (Nq,k)
+    [, features (Nq, C*len(ks))]) as CUDA tensors.
+    """
+    validate_cloud(query_cloud, "query_cloud")
+    validate_cloud(search_cloud, "search_cloud")
+    if search_cloud.shape[0] < 1:
+        raise ValueError("need at least 1 search point")
+    require_cuda()
+    q, qc = device_cloud(query_cloud)
+    s, sc = (q, qc) if search_cloud is query_cloud else device_cloud(search_cloud, q.device)
+    nq = q.shape[0]
+    idx = torch.empty((nq, k), dtype=torch.int32, device=q.device)
+    d2 = torch.empty((nq, k), dtype=torch.float64, device=q.device)
+    np_out, out_code = _out_code(out_dtype)
+    ncol, mask = _ncol(descriptors)
+    feats, ks_arr = None, None
+    if ks is not None:
+        ks_arr = np.ascontiguousarray(ks, dtype=np.int32)
+        if np.any(np.diff(ks_arr) <= 0) or ks_arr[-1] != k:
+            raise ValueError("ks must be ascending and end at k")
+        feats = torch.zeros((nq, ncol * len(ks_arr)), dtype=_TORCH_OUT[np_out], device=q.device)
+    with torch.cuda.device(q.device):
+        _lib.check(_lib.lib().nbr_knn_points(
+            ptr(s), sc, s.shape[0], ptr(q), qc, nq, int(k), float(cell_edge), ptr(idx), ptr(d2),
+            ks_arr.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)) if ks_arr is not None else None,
+            len(ks_arr) if ks_arr is not None else 0, ptr(feats), out_code, feats.shape[1] if feats is not None else 0, 0, mask,
+            stream_ptr(q.device)))
+    return (idx, d2) if feats is None else (idx, d2, feats)
+
+
 def knn_features(query_cloud, search_cloud, edge_length, ks, out_dtype=np.float64, descriptors="reference"):
     """
     multiscale kNN features (extension; BASELINE config 3): the search cloud is voxel-filtered at
     edge_length, and for each k in ks the reference's 4 columns are computed over the k nearest
     voxels, ties broken by (distance, index).  (Nq, C*len(ks)); numpy in -> numpy out.
+    edge_length = 0 searches the raw points instead (the legacy convention sspedge = 0, prototypes/mso.py:277).
     """
     ks = sorted(int(k) for k in ks)
+    if not edge_length:
+        _, _, feats = knn_points(query_cloud, search_cloud, ks[-1], ks=ks, out_dtype=out_dtype, descriptors=descriptors)
+        if is_torch(query_cloud):
+            return feats if query_cloud.is_cuda else feats.cpu()
+        return feats.cpu().numpy()
     index = LatticeIndex(search_cloud, edge_length, indexed=True)
     try:
         _, _, feats = index.knn(query_cloud, ks[-1], ks=ks, out_dtype=out_dtype, descriptors=descriptors)
