@@ -822,6 +822,16 @@ int lattices_create_batch(Lattice **out, int n_lat, const nbr_grid *grids, const
     return NBR_OK;
 }
 
+// centres of the nv unique voxels of an INDEXED lattice, np.unique order (utils/geometry.py:120-138)
+int lattice_centres(const Lattice *L, int64_t nv, double *centres, cudaStream_t stream)
+{
+    if (!L->indexed) return fail(NBR_ERR_INVALID, "lattice_centres: lattice was built without NBR_LATTICE_INDEXED");
+    if (nv <= 0) return NBR_OK;
+    centre_kernel<<<(unsigned)ceil_div(nv, 256), 256, 0, stream>>>(reinterpret_cast<const int64_t *>(L->ukeys), nv, L->gdev, centres);
+    NBR_LAUNCHED();
+    return NBR_OK;
+}
+
 int lattice_counts(const Lattice *L, int64_t *n_voxels, int64_t *n_bricks)
 {
     unsigned char host[64];

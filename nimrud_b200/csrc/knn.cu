@@ -17,7 +17,16 @@
 #include "finalize.cuh"
 #include "lattice.cuh"
 
+#include <stdlib.h>
+
+#include <string>
+
 namespace nbr {
+
+int knn_points(const void *search, int s_dtype, int64_t ns, const void *query, int q_dtype, int64_t nq, int k, double cell_edge,
+               int32_t *idx_out, double *d2_out, const int32_t *ks, int n_k, void *feats, int out_dtype, int64_t row_stride,
+               int col_offset, int descriptor_mask, cudaStream_t stream);
+int lattice_centres(const Lattice *L, int64_t nv, double *centres, cudaStream_t stream);
 
 constexpr int KNN_WARPS = 4;
 constexpr int KNN_MAX_K = 128;
@@ -300,6 +309,21 @@ int knn(const Lattice *lat, const void *query, int dtype, int64_t nq, int k, int
     if (k < 1 || k > KNN_MAX_K) return fail(NBR_ERR_UNSUPPORTED, "knn: k must be in [1, 128]");
     if (n_k < 0 || n_k > 16) return fail(NBR_ERR_UNSUPPORTED, "knn: at most 16 values of k");
     if (nq <= 0) return NBR_OK;
+    // default route: the voxel centres (np.unique order, so a centre's position IS its index) go through the point
+    // kernel of knn_points.cu -- same float64 distances on the same centres, same (d^2, index) order, measured 46 M
+    // against 35 M queries/s at k = 50 on 9.4M voxels.  NBR_KNN=bricks keeps the brick sweep below.
+    static const bool use_bricks = getenv("NBR_KNN") && std::string(getenv("NBR_KNN")) == "bricks";
+    if (!use_bricks) {
+        int64_t nv = 0;
+        NBR_TRY(lattice_counts(lat, &nv, nullptr));
+        if (nv >= 1) {
+            Scratch centres;
+            NBR_TRY(centres.alloc(sizeof(double) * 3 * (size_t)nv, stream));
+            NBR_TRY(lattice_centres(lat, nv, centres.as<double>(), stream));
+            return knn_points(centres.ptr, NBR_F64, nv, query, dtype, nq, k, 0.0, idx_out, d2_out, ks, n_k, feats, out_dtype, row_stride,
+                              col_offset, descriptor_mask, stream);
+        }
+    }
     KsParam kp;
     kp.n = feats ? n_k : 0;
     for (int i = 0; i < kp.n; ++i) {

@@ -79,16 +79,16 @@ kp_place_kernel(const void *__restrict__ xyz, int dtype, int64_t n, const uint32
 }
 
 template <typename OutT>
-__global__ void __launch_bounds__(KP_WARPS * 32)
+__global__ void __launch_bounds__(KP_WARPS * 32, 6)
 knn_points_kernel(PGrid G, const double *__restrict__ pts, const int32_t *__restrict__ orig, const uint32_t *__restrict__ offsets,
                   int64_t n_search, const void *__restrict__ query, int q_dtype, int64_t nq, int k, int32_t *__restrict__ idx_out,
                   double *__restrict__ d2_out, KpKs ks, OutT *__restrict__ feats, int64_t row_stride, int col_offset,
-                  int descriptor_mask)
+                  int descriptor_mask, int cap)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_count[KP_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    KpRec *rec = reinterpret_cast<KpRec *>(smem_raw) + (size_t)warp * KP_CAP;
+    KpRec *rec = reinterpret_cast<KpRec *>(smem_raw) + (size_t)warp * cap;       // cap records per warp (a power of two >= 4 k)
     const int ncol = (descriptor_mask & NBR_DESC_EXTENDED) ? NBR_COLS_EXTENDED : NBR_COLS_REFERENCE;
     const int64_t n_cells = (int64_t)G.dims[0] * G.dims[1] * G.dims[2];
 
@@ -100,7 +100,11 @@ knn_points_kernel(PGrid G, const double *__restrict__ pts, const int32_t *__rest
             q[a] = load_coord(query, q_dtype, qi, 3, a);
             ca[a] = (long long)fmin(fmax(floor((q[a] - G.origin[a]) * G.inv_g), -4.0e9), 4.0e9);   // not clamped to the grid
         }
-        long long W = 1;
+        // first window: the cells hold ~4 points each where the cloud is a surface and the ball of a window of half-width
+        // W has a radius of about W + 0.5 cells, i.e. about 4 pi (W + 0.5)^2 points: start where that reaches k.  (a window
+        // one step too wide costs more than an extra attempt: 343 cells against 27 + 125)
+        long long W = (long long)ceilf(sqrtf((float)k * 0.0796f) - 0.5f);
+        if (W < 1) W = 1;
         double lo2 = 0.0, hi2 = INFINITY, r2 = 0.0;
         bool ball_of_w = true;
         int n_cand = 0;
@@ -132,19 +136,21 @@ knn_points_kernel(PGrid G, const double *__restrict__ pts, const int32_t *__rest
             if (lane == 0) s_count[warp] = 0;
             __syncwarp();
             if (!empty) {
-                const int ncx = whi[0] - wlo[0] + 1, ncy = whi[1] - wlo[1] + 1, ncz = whi[2] - wlo[2] + 1;
-                const long long nc = (long long)ncx * ncy * ncz;
-                for (long long t = lane; t < nc; t += 32) {
-                    const int ix = wlo[0] + (int)(t % ncx), iy = wlo[1] + (int)((t / ncx) % ncy), iz = wlo[2] + (int)(t / ((long long)ncx * ncy));
-                    const int64_t id = ((int64_t)iz * G.dims[1] + iy) * G.dims[0] + ix;
-                    const uint32_t first = offsets[id], last = id + 1 < n_cells ? offsets[id + 1] : (uint32_t)n_search;
+                // the cells are numbered x-fastest, so the points of one x-row of the window (whi[0] - wlo[0] + 1 cells) are ONE
+                // contiguous range of the cell-ordered copy: a lane per row, two offsets per row
+                const int ncy = whi[1] - wlo[1] + 1, ncz = whi[2] - wlo[2] + 1;
+                const long long nrows = (long long)ncy * ncz;
+                for (long long t = lane; t < nrows; t += 32) {
+                    const int iz = wlo[2] + (int)(t / ncy), iy = wlo[1] + (int)(t - (long long)(iz - wlo[2]) * ncy);
+                    const int64_t id0 = ((int64_t)iz * G.dims[1] + iy) * G.dims[0] + wlo[0], id1 = id0 + (whi[0] - wlo[0]) + 1;
+                    const uint32_t first = offsets[id0], last = id1 < n_cells ? offsets[id1] : (uint32_t)n_search;
                     for (uint32_t p = first; p < last; ++p) {
                         const double dx = __dsub_rn(q[0], pts[(size_t)p * 3]), dy = __dsub_rn(q[1], pts[(size_t)p * 3 + 1]),
                                      dz = __dsub_rn(q[2], pts[(size_t)p * 3 + 2]);
                         const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
                         if (d2 <= r2) {
                             const int slot = atomicAdd(&s_count[warp], 1);
-                            if (slot < KP_CAP) {
+                            if (slot < cap) {
                                 KpRec r;
                                 r.d2 = d2; r.idx = orig[p]; r.pos = (int32_t)p;
                                 rec[slot] = r;
@@ -156,8 +162,8 @@ knn_points_kernel(PGrid G, const double *__restrict__ pts, const int32_t *__rest
             __syncwarp();
             n_cand = s_count[warp];
             __syncwarp();
-            // invariants: fewer than k points inside lo2; more than KP_CAP inside hi2
-            if (n_cand >= k && n_cand <= KP_CAP) break;
+            // invariants: fewer than k points inside lo2; more than cap inside hi2
+            if (n_cand >= k && n_cand <= cap) break;
             if (n_cand >= k) {
                 hi2 = r2;                                   // too many: shrink the ball inside the same window
                 ball_of_w = false;
@@ -175,7 +181,7 @@ knn_points_kernel(PGrid G, const double *__restrict__ pts, const int32_t *__rest
             if (!(mid > lo2 && mid < hi2)) break;           // more than KP_CAP - k points at one distance: keep the first KP_CAP found
             r2 = mid;
         }
-        if (n_cand > KP_CAP) n_cand = KP_CAP;
+        if (n_cand > cap) n_cand = cap;
         __syncwarp();
 
         // ---- bitonic sort of the records (padded with +inf to a power of two)
@@ -318,21 +324,24 @@ int knn_points(const void *search, int s_dtype, int64_t ns, const void *query, i
                                                  sorted.as<double>(), orig.as<int32_t>());
     NBR_LAUNCHED();
     // ---- queries
-    const size_t smem = sizeof(KpRec) * (size_t)KP_CAP * KP_WARPS;
+    int cap = 128;
+    while (cap < 4 * k && cap < KP_CAP) cap <<= 1;           // 128 records for k <= 32, 256 for k <= 64, 512 above
+    const size_t smem = sizeof(KpRec) * (size_t)cap * KP_WARPS;
+    const size_t smem_max = sizeof(KpRec) * (size_t)KP_CAP * KP_WARPS;
     static std::atomic<uint64_t> configured{0};
     if (first_use_on_device(configured)) {
-        NBR_CUDA(cudaFuncSetAttribute(knn_points_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        NBR_CUDA(cudaFuncSetAttribute(knn_points_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NBR_CUDA(cudaFuncSetAttribute(knn_points_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        NBR_CUDA(cudaFuncSetAttribute(knn_points_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     }
-    const int blocks = (int)std::min<int64_t>(ceil_div(nq, KP_WARPS), (int64_t)device_sm_count() * 8);
+    const int blocks = (int)std::min<int64_t>(ceil_div(nq, KP_WARPS), (int64_t)device_sm_count() * 12);
     if (out_dtype == NBR_F32)
         knn_points_kernel<float><<<blocks, KP_WARPS * 32, smem, stream>>>(G, sorted.as<double>(), orig.as<int32_t>(), counts.as<uint32_t>(), ns,
                                                                           query, q_dtype, nq, k, idx_out, d2_out, kp, (float *)feats,
-                                                                          row_stride, col_offset, descriptor_mask);
+                                                                          row_stride, col_offset, descriptor_mask, cap);
     else
         knn_points_kernel<double><<<blocks, KP_WARPS * 32, smem, stream>>>(G, sorted.as<double>(), orig.as<int32_t>(), counts.as<uint32_t>(), ns,
                                                                            query, q_dtype, nq, k, idx_out, d2_out, kp, (double *)feats,
-                                                                           row_stride, col_offset, descriptor_mask);
+                                                                           row_stride, col_offset, descriptor_mask, cap);
     NBR_LAUNCHED();
     return NBR_OK;
 }
