@@ -184,6 +184,48 @@ knn_points_kernel(PGrid G, const double *__restrict__ pts, const int32_t *__rest
         if (n_cand > cap) n_cand = cap;
         __syncwarp();
 
+        // ---- thin the candidates before sorting: the ball usually holds 2-3 k points and the sort costs n log^2 n.  a
+        // 32-bucket histogram of d^2 (lane = bucket) finds the bucket of the k-th smallest; every record up to and
+        // including that bucket stays (all ties of the k-th distance share its bucket), the rest cannot be among the k
+        if (n_cand > 64 && n_cand > k + 16) {
+            double dmax = 0.0;
+            for (int p = lane; p < n_cand; p += 32) dmax = fmax(dmax, rec[p].d2);
+#pragma unroll
+            for (int o = 16; o; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+            const double scale = dmax > 0.0 ? 32.0 / dmax : 0.0;
+            int mine = 0;                                            // records in bucket `lane`
+            for (int p0 = 0; p0 < n_cand; p0 += 32) {
+                const int p = p0 + lane;
+                const int bkt = p < n_cand ? min((int)(rec[p].d2 * scale), 31) : -1;
+#pragma unroll
+                for (int b = 0; b < 32; ++b) {
+                    const int c = __popc(__ballot_sync(0xffffffffu, bkt == b));
+                    if (lane == b) mine += c;
+                }
+            }
+            int cum = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, cum, o);
+                if (lane >= o) cum += t;
+            }
+            const int last_bucket = __ffs(__ballot_sync(0xffffffffu, cum >= k)) - 1;      // >= 0: cum reaches n_cand >= k
+            int kept = 0;
+            for (int p0 = 0; p0 < n_cand; p0 += 32) {                 // in-place compaction: writes stay behind the reads
+                const int p = p0 + lane;
+                KpRec r;
+                r.d2 = INFINITY; r.idx = 0; r.pos = 0;
+                if (p < n_cand) r = rec[p];
+                const bool keep = p < n_cand && min((int)(r.d2 * scale), 31) <= last_bucket;
+                const uint32_t m = __ballot_sync(0xffffffffu, keep);
+                __syncwarp();
+                if (keep) rec[kept + __popc(m & lanemask_lt())] = r;
+                kept += __popc(m);
+                __syncwarp();
+            }
+            n_cand = kept;
+        }
+
         // ---- bitonic sort of the records (padded with +inf to a power of two)
         int npow = 32;
         while (npow < n_cand) npow <<= 1;

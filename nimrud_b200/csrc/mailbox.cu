@@ -20,7 +20,7 @@
 //                    number of rows received (kept on the device: the lattice build reads it there).
 // a peer can only push epoch e+1 after it has seen this rank's box of epoch e+1, which this rank publishes
 // stream-ordered after every kernel of epoch e that reads the mailbox: one buffer is enough.
-// waits are bounded (NBR_MAILBOX_TIMEOUT_MS, default 20 s): a rank that never arrives raises a sticky flag
+// waits are bounded (NBR_MAILBOX_TIMEOUT_MS, default 120 s): a rank that never arrives raises a sticky flag
 // instead of hanging the GPU.
 #include <stdlib.h>
 #include <string.h>
@@ -231,8 +231,8 @@ static unsigned long long timeout_ns()
 {
     static const unsigned long long ns = [] {
         const char *e = getenv("NBR_MAILBOX_TIMEOUT_MS");
-        const double ms = e ? atof(e) : 20000.0;
-        return (unsigned long long)((ms > 0 ? ms : 20000.0) * 1e6);
+        const double ms = e ? atof(e) : 120000.0;
+        return (unsigned long long)((ms > 0 ? ms : 120000.0) * 1e6);
     }();
     return ns;
 }
