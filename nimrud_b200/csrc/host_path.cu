@@ -296,7 +296,8 @@ static int rows_to_host(const Plan *P, const void *qdev_all, int q_dtype, int64_
     const int ncol = (descriptor_mask & NBR_DESC_EXTENDED) ? NBR_COLS_EXTENDED : NBR_COLS_REFERENCE;
     const size_t cols = (size_t)ncol * n_scales;
     const size_t qrow = 3 * esize(q_dtype), wrow = cols * esize(wire), orow = cols * esize(out_dtype);
-    const int64_t batch = std::max<int64_t>(262144, (n_query + 15) / 16);
+    const char *batch_env = getenv("NBR_HOST_BATCH_ROWS");
+    const int64_t batch = batch_env && atoll(batch_env) > 0 ? (int64_t)atoll(batch_env) : std::max<int64_t>(262144, (n_query + 15) / 16);
     const int n_batches = (int)ceil_div(n_query, batch);
     constexpr int RING = 3;
     const bool out_pinned = is_pinned(out_host);

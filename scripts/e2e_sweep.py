@@ -24,6 +24,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         del host_out
 else:
     for env in ({}, {"NBR_HOST_PIECE_MB": "1"}, {"NBR_HOST_PIECE_MB": "2"}, {"NBR_HOST_PIECE_MB": "8"}, {"NBR_HOST_PIECE_MB": "16"},
-                {"NBR_HOST_THREADS": "9"}, {"NBR_HOST_THREADS": "5"}, {"NBR_HOST_THREADS": "32"}, {"NBR_HOST_WIRE": "f64"}):
+                {"NBR_HOST_THREADS": "9"}, {"NBR_HOST_THREADS": "5"}, {"NBR_HOST_THREADS": "32"}, {"NBR_HOST_WIRE": "f64"},
+                {"NBR_HOST_BATCH_ROWS": "65536"}, {"NBR_HOST_BATCH_ROWS": "131072"}):
         e = dict(os.environ); e.update(env)
         subprocess.run([sys.executable, os.path.abspath(__file__), "child", str(env)], env=e)
