@@ -6,7 +6,8 @@
 //   * WIRE FORMAT float32.  the device computes float32 rows (population is an exact small integer, the other
 //     columns carry a 1e-4 tolerance and float32 keeps 6e-8), they cross PCIe at half the bytes, and host threads
 //     widen them into the caller's float64 array while the next batch is on the wire.  NBR_HOST_WIRE=f64 sends
-//     float64 rows instead.
+//     float64 rows instead; a pinned float64 result gets NBR_HOST_DIRECT_SHARE (0.1) of every batch widened on the
+//     device and written in place, which takes that share off the host's memory bus.
 //   * PINNED RINGS.  pageable buffers (plain numpy arrays) are staged through pinned ring buffers by a pool of host
 //     threads: cloud chunks in, row batches out; pinned caller buffers are used in place.  the rings are cached
 //     for the life of the process.
@@ -285,6 +286,12 @@ int tile_step_plan(Mailbox *M, const void *xyz, int dtype, int64_t n, const doub
                    int32_t n_scales, int32_t descriptor_mask, double *boxes_host_out, Scratch &perm, Scratch &sorted, Plan **P_out,
                    cudaStream_t s);
 
+// float32 rows -> float64 rows on the device (the share of a batch that crosses the wire as float64, see rows_to_host)
+__global__ void widen_rows_kernel(const float *__restrict__ src, double *__restrict__ dst, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = (double)src[i];
+}
+
 // features of the queries qdev[0, n_query) (device, any order) against plan P -> the caller's HOST rows, in batches:
 // kernels of batch b+1 | device->host pieces of batch b | host threads moving / widening the pieces that have landed
 static int rows_to_host(const Plan *P, const void *qdev_all, int q_dtype, int64_t n_query, const double *qbox, void *out_host,
@@ -312,19 +319,29 @@ static int rows_to_host(const Plan *P, const void *qdev_all, int q_dtype, int64_
     // by piece, and the tail after the last copy is one piece, not one batch
     const char *piece_env = getenv("NBR_HOST_PIECE_MB");
     const double piece_mb = piece_env && atof(piece_env) > 0 ? atof(piece_env) : 4.0;
+    // float64 rows from float32 wire rows cost the host 4 bytes of DRAM traffic per wire byte (the DMA write, the read, the
+    // doubled write) and the host's memory, not the link, bounds the call.  when the caller's buffer is pinned, the last
+    // `share` of every batch is widened on the DEVICE and lands in the caller's rows directly (2 bytes of DRAM traffic per
+    // wire byte of twice the wire bytes): the split balances link and host memory.  same values either way (float32 results)
+    const char *share_env = getenv("NBR_HOST_DIRECT_SHARE");
+    const double share = !(widen_rows && out_pinned) ? 0.0 : (share_env ? std::min(std::max(atof(share_env), 0.0), 1.0) : 0.1);
+    const int64_t batch_direct = (int64_t)((double)batch * share);
     const size_t piece_rows = direct ? (size_t)batch : std::max<size_t>(1, (size_t)(piece_mb * (1 << 20)) / wrow);
     const int pieces_per_batch = (int)ceil_div(batch, (int64_t)piece_rows);
-    std::vector<cudaEvent_t> computed(RING, nullptr), landed((size_t)RING * pieces_per_batch, nullptr);
+    std::vector<cudaEvent_t> computed(RING, nullptr), drained(RING, nullptr), landed((size_t)RING * pieces_per_batch, nullptr);
     int rc = NBR_OK;
     cudaError_t e = cudaSuccess;
     for (auto &ev : computed)
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    for (auto &ev : drained)
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     for (auto &ev : landed)
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     {
-        Scratch o;
+        Scratch o, o64;
         void *pin[RING] = {nullptr, nullptr, nullptr};
         if (e == cudaSuccess) rc = o.alloc((size_t)std::min<int64_t>(n_query, batch * RING) * wrow, stream);
+        if (!rc && e == cudaSuccess && batch_direct > 0) rc = o64.alloc((size_t)batch_direct * RING * orow, stream);
         if (!rc && e == cudaSuccess && !direct)
             for (int k = 0; k < std::min(RING, n_batches) && !rc; ++k) rc = g_ring_out.get(k, (size_t)batch * wrow, &pin[k]);
 
@@ -340,7 +357,8 @@ static int rows_to_host(const Plan *P, const void *qdev_all, int q_dtype, int64_
                     std::this_thread::yield();
                 }
                 const int slot = b % RING;
-                const int64_t first = (int64_t)b * batch, n = std::min(batch, n_query - first);
+                const int64_t first = (int64_t)b * batch, n_all = std::min(batch, n_query - first);
+                const int64_t n = n_all - std::min(batch_direct, n_all);      // the rest arrives as float64 by itself
                 const char *src = (const char *)pin[slot];
                 char *dst = (char *)out_host + (size_t)first * orow;
                 for (int64_t r0 = 0, pc = 0; r0 < n; r0 += (int64_t)piece_rows, ++pc) {
@@ -370,20 +388,31 @@ static int rows_to_host(const Plan *P, const void *qdev_all, int q_dtype, int64_
                 if (use_consumers)
                     while (consumed[b - RING].load(std::memory_order_acquire) < n_consumers && !abort_flag.load()) std::this_thread::yield();
                 // the device slot is free once its previous copy has landed
-                const int64_t n_prev = std::min(batch, n_query - (int64_t)(b - RING) * batch);
-                e = cudaStreamWaitEvent(stream, landed[(size_t)slot * pieces_per_batch + ceil_div(n_prev, (int64_t)piece_rows) - 1], 0);
+                e = cudaStreamWaitEvent(stream, drained[slot], 0);
                 if (e != cudaSuccess) break;
             }
             rc = plan_run(P, qdev, q_dtype, n, qbox, odev, wire, stream);
             if (rc) break;
-            e = cudaEventRecord(computed[slot], stream);
+            const int64_t n_direct = std::min(batch_direct, n), n_wire = n - n_direct;
+            char *odev64 = batch_direct > 0 ? (char *)o64.ptr + (size_t)slot * batch_direct * orow : nullptr;
+            if (n_direct > 0) {
+                const size_t elems = (size_t)n_direct * cols;
+                widen_rows_kernel<<<(unsigned)std::min<size_t>(ceil_div(elems, (size_t)256), (size_t)device_sm_count() * 8), 256, 0, stream>>>(
+                    (const float *)(odev + (size_t)n_wire * wrow), (double *)odev64, elems);
+                g_launches.fetch_add(1, std::memory_order_relaxed);
+                e = cudaGetLastError();                 // no early return here: the consumers are running
+            }
+            if (e == cudaSuccess) e = cudaEventRecord(computed[slot], stream);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(copy_stream, computed[slot], 0);
-            for (int64_t r0 = 0, pc = 0; e == cudaSuccess && r0 < n; r0 += (int64_t)piece_rows, ++pc) {
-                const size_t rows = (size_t)std::min<int64_t>((int64_t)piece_rows, n - r0);
+            for (int64_t r0 = 0, pc = 0; e == cudaSuccess && r0 < n_wire; r0 += (int64_t)piece_rows, ++pc) {
+                const size_t rows = (size_t)std::min<int64_t>((int64_t)piece_rows, n_wire - r0);
                 void *dst = direct ? (void *)((char *)out_host + (size_t)(first + r0) * orow) : (void *)((char *)pin[slot] + (size_t)r0 * wrow);
                 e = cudaMemcpyAsync(dst, odev + (size_t)r0 * wrow, rows * wrow, cudaMemcpyDeviceToHost, copy_stream);
                 if (e == cudaSuccess) e = cudaEventRecord(landed[(size_t)slot * pieces_per_batch + pc], copy_stream);
             }
+            if (e == cudaSuccess && n_direct > 0)
+                e = cudaMemcpyAsync((char *)out_host + (size_t)(first + n_wire) * orow, odev64, (size_t)n_direct * orow, cudaMemcpyDeviceToHost, copy_stream);
+            if (e == cudaSuccess) e = cudaEventRecord(drained[slot], copy_stream);      // both device slots are free again
             if (e == cudaSuccess) issued[b].store(1, std::memory_order_release);
         }
         if (rc || e != cudaSuccess) abort_flag.store(1);
@@ -396,6 +425,7 @@ static int rows_to_host(const Plan *P, const void *qdev_all, int q_dtype, int64_
         cudaStreamSynchronize(stream);
     }
     for (auto ev : computed) if (ev) cudaEventDestroy(ev);
+    for (auto ev : drained) if (ev) cudaEventDestroy(ev);
     for (auto ev : landed) if (ev) cudaEventDestroy(ev);
     return rc;
 }
