@@ -206,19 +206,22 @@ static int upload(void *dev, const void *host, size_t bytes, cudaStream_t stream
         NBR_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, stream));
         return NBR_OK;
     }
-    const size_t chunk = 32u << 20;
-    cudaEvent_t freed[2] = {nullptr, nullptr};
+    // chunks through a ring of 4 pinned slots: the first chunk's copy into the ring is the pipeline's start-up cost
+    const char *chunk_env = getenv("NBR_HOST_UPLOAD_MB");
+    const size_t chunk = (size_t)(chunk_env && atof(chunk_env) > 0 ? atof(chunk_env) : 4.0) << 20;
+    constexpr int SLOTS = 4;
+    cudaEvent_t freed[SLOTS] = {nullptr, nullptr, nullptr, nullptr};
     int rc = NBR_OK;
-    for (int k = 0; k < 2 && !rc; ++k)
+    for (int k = 0; k < SLOTS && !rc; ++k)
         if (cudaEventCreateWithFlags(&freed[k], cudaEventDisableTiming) != cudaSuccess) rc = fail(NBR_ERR_CUDA, "upload: cudaEventCreate");
     size_t at = 0;
     for (int it = 0; !rc && at < bytes; ++it) {
-        const int slot = it & 1;
+        const int slot = it % SLOTS;
         const size_t len = std::min(chunk, bytes - at);
         void *pin = nullptr;
         rc = g_ring_in.get(slot, chunk, &pin);
         if (rc) break;
-        if (it >= 2 && cudaEventSynchronize(freed[slot]) != cudaSuccess) { rc = fail(NBR_ERR_CUDA, "upload: event"); break; }
+        if (it >= SLOTS && cudaEventSynchronize(freed[slot]) != cudaSuccess) { rc = fail(NBR_ERR_CUDA, "upload: event"); break; }
         const char *src = (const char *)host + at;
         HostPool::get().run([&](int part, int parts) {
             size_t first, count;
@@ -230,7 +233,7 @@ static int upload(void *dev, const void *host, size_t bytes, cudaStream_t stream
             rc = fail(NBR_ERR_CUDA, "upload: cudaMemcpyAsync");
         at += len;
     }
-    for (int k = 0; k < 2; ++k)
+    for (int k = 0; k < SLOTS; ++k)
         if (freed[k]) { cudaEventSynchronize(freed[k]); cudaEventDestroy(freed[k]); }
     return rc;
 }
