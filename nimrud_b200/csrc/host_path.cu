@@ -208,7 +208,7 @@ static int upload(void *dev, const void *host, size_t bytes, cudaStream_t stream
     }
     // chunks through a ring of 4 pinned slots: the first chunk's copy into the ring is the pipeline's start-up cost
     const char *chunk_env = getenv("NBR_HOST_UPLOAD_MB");
-    const size_t chunk = (size_t)(chunk_env && atof(chunk_env) > 0 ? atof(chunk_env) : 4.0) << 20;
+    const size_t chunk = std::max<size_t>(1u << 20, (size_t)((chunk_env && atof(chunk_env) > 0 ? atof(chunk_env) : 4.0) * (double)(1u << 20)));
     constexpr int SLOTS = 4;
     cudaEvent_t freed[SLOTS] = {nullptr, nullptr, nullptr, nullptr};
     int rc = NBR_OK;
