@@ -325,9 +325,14 @@ static int rows_to_host(const Plan *P, const void *qdev_all, int q_dtype, int64_
     // float64 rows from float32 wire rows cost the host 4 bytes of DRAM traffic per wire byte (the DMA write, the read, the
     // doubled write) and the host's memory, not the link, bounds the call.  when the caller's buffer is pinned, the last
     // `share` of every batch is widened on the DEVICE and lands in the caller's rows directly (2 bytes of DRAM traffic per
-    // wire byte of twice the wire bytes): the split balances link and host memory.  same values either way (float32 results)
-    const char *share_env = getenv("NBR_HOST_DIRECT_SHARE");
-    const double share = !(widen_rows && out_pinned) ? 0.0 : (share_env ? std::min(std::max(atof(share_env), 0.0), 1.0) : 0.1);
+    // wire byte of twice the wire bytes): the split balances link and host memory.  same values either way (float32 results).
+    // the ranks of a node share the host's cores and memory bus but each has its own link, so the share grows with
+    // LOCAL_WORLD_SIZE (measured, 10M points x 5 scales per rank: 1 rank 24.2 -> 23.2 ms at 0.1; 2 ranks 37.0 -> 31.2 ms at
+    // 0.5; 4 ranks 69.1 -> 42.9 ms and 8 ranks 165 -> 148 ms at 1.0)
+    const char *share_env = getenv("NBR_HOST_DIRECT_SHARE"), *lws_env = getenv("LOCAL_WORLD_SIZE");
+    const int local_ranks = lws_env ? atoi(lws_env) : 1;
+    const double share_default = local_ranks <= 1 ? 0.1 : (local_ranks == 2 ? 0.4 : 1.0);
+    const double share = !(widen_rows && out_pinned) ? 0.0 : (share_env ? std::min(std::max(atof(share_env), 0.0), 1.0) : share_default);
     const int64_t batch_direct = (int64_t)((double)batch * share);
     const size_t piece_rows = direct ? (size_t)batch : std::max<size_t>(1, (size_t)(piece_mb * (1 << 20)) / wrow);
     const int pieces_per_batch = (int)ceil_div(batch, (int64_t)piece_rows);
