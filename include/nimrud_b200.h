@@ -38,6 +38,7 @@ extern "C" {
 #define NBR_ERR_CUDA 4
 #define NBR_ERR_UNSUPPORTED 5
 #define NBR_ERR_OUT_OF_BOUNDS 6  /* reference: ValueError, utils/geometry.py:96-97                */
+#define NBR_ERR_CAPACITY 7       /* nbr_tile_step_gather: the gather buffers are too small; grow them and call again */
 
 #define NBR_F32 0
 #define NBR_F64 1
@@ -285,6 +286,35 @@ int nbr_multiscale_features_tile_mb(const void *sorted_xyz, const uint32_t *perm
 int nbr_tile_step(nbr_mailbox *mailbox, const void *xyz, int dtype, int64_t n, const double *edges_host,
                   const double *radii_host, int32_t n_scales, void *out, int out_dtype, int32_t descriptor_mask,
                   double *boxes_host_out, int64_t *n_voxels_host, void *stream);
+
+/* FEATURE ALL-GATHER WITHOUT A COLLECTIVE CALL (north_star: "final feature all-gather"; no reference counterpart, the
+ * reference is one process).  every rank owns a GATHER BUFFER for the rows of all ranks in rank order (cudaMalloc'ed by
+ * nbr_mailbox_gather_alloc, mapped by the peers like the mailbox: nbr_mailbox_gather_ipc_handle ->
+ * nbr_mailbox_gather_connect_ipc, or nbr_mailbox_gather_connect_local inside one process).  (re)allocation is
+ * collective on the caller's side: every rank allocates the same size, the handles are exchanged, everybody connects, and
+ * only then the next step runs.  nbr_tile_step_gather is nbr_tile_step whose fused feature kernel stores every finished
+ * row into the buffer of EVERY rank (remote stores over NVLink from the kernel's own write-out; scale sets the 7x7x7
+ * kernel does not cover alone are computed into the own buffer and pushed as peer copies), followed by a stream-ordered
+ * signal + wait: when the call's work on `stream` is done, nbr_mailbox_gather_ptr() holds the rows of all ranks.
+ * row_offsets_host[world + 1]: first row of every rank's share.  NBR_ERR_CAPACITY (on every rank alike, after the step's
+ * halo exchange has completed): the buffers are too small for sum n rows; grow them collectively and call again. */
+int nbr_mailbox_gather_alloc(nbr_mailbox *mailbox, uint64_t bytes);
+int nbr_mailbox_gather_ipc_handle(const nbr_mailbox *mailbox, void *handle_out_64);
+int nbr_mailbox_gather_connect_ipc(nbr_mailbox *mailbox, int32_t peer, const void *handle_64, uint64_t bytes);
+int nbr_mailbox_gather_connect_local(nbr_mailbox *mailbox, int32_t peer, const nbr_mailbox *peer_mailbox);
+void *nbr_mailbox_gather_ptr(const nbr_mailbox *mailbox, uint64_t *bytes_out);
+/* step-wise form: nbr_multiscale_features_tile_mb with rows [row_offset, row_offset + n) of every gather buffer as the
+ * output (total_rows = rows of all ranks), and the signal + wait as a call of its own */
+int nbr_multiscale_features_tile_mb_gather(const void *sorted_xyz, const uint32_t *perm, int dtype, int64_t n,
+                                           nbr_mailbox *mailbox, const double *local_lohi_host,
+                                           const double *global_lohi_host, const double *edges_host,
+                                           const double *radii_host, int32_t n_scales, int out_dtype,
+                                           int32_t descriptor_mask, int64_t row_offset, int64_t total_rows,
+                                           int64_t *n_voxels_host, void *stream);
+int nbr_gather_finish(nbr_mailbox *mailbox, void *stream);
+int nbr_tile_step_gather(nbr_mailbox *mailbox, const void *xyz, int dtype, int64_t n, const double *edges_host,
+                         const double *radii_host, int32_t n_scales, int out_dtype, int32_t descriptor_mask,
+                         double *boxes_host_out, int64_t *n_voxels_host, int64_t *row_offsets_host, void *stream);
 
 /* nbr_tile_step with HOST buffers (the tile goes up, the rows come down in batches whose copies overlap the kernels;
  * float32 on the wire, widened by host threads for out_dtype NBR_F64, like nbr_multiscale_features_host). */

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NIMRUD_B200_LIB") or os.path.join(HERE, "lib", "libnimrud_b200.so")   # env: A/B builds
 
 OK = 0
-ERR_INVALID, ERR_TOO_FEW_POINTS, ERR_ADDRESS_BITS, ERR_CUDA, ERR_UNSUPPORTED, ERR_OUT_OF_BOUNDS = 1, 2, 3, 4, 5, 6
+ERR_INVALID, ERR_TOO_FEW_POINTS, ERR_ADDRESS_BITS, ERR_CUDA, ERR_UNSUPPORTED, ERR_OUT_OF_BOUNDS, ERR_CAPACITY = 1, 2, 3, 4, 5, 6, 7
 F32, F64 = 0, 1
 DESC_REFERENCE, DESC_EXTENDED = 0, 1
 LATTICE_INDEXED = 1
@@ -89,6 +89,17 @@ SIGNATURES = {
                                                        c_i32, c_vp, ctypes.c_int, c_i32, ctypes.POINTER(c_i64), c_vp]),
     "nbr_tile_step": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_i64, ctypes.POINTER(c_f64), ctypes.POINTER(c_f64), c_i32, c_vp,
                                      ctypes.c_int, c_i32, ctypes.POINTER(c_f64), ctypes.POINTER(c_i64), c_vp]),
+    "nbr_mailbox_gather_alloc": (ctypes.c_int, [c_vp, ctypes.c_uint64]),
+    "nbr_mailbox_gather_ipc_handle": (ctypes.c_int, [c_vp, c_vp]),
+    "nbr_mailbox_gather_connect_ipc": (ctypes.c_int, [c_vp, c_i32, c_vp, ctypes.c_uint64]),
+    "nbr_mailbox_gather_connect_local": (ctypes.c_int, [c_vp, c_i32, c_vp]),
+    "nbr_mailbox_gather_ptr": (c_vp, [c_vp, ctypes.POINTER(ctypes.c_uint64)]),
+    "nbr_multiscale_features_tile_mb_gather": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_i64, c_vp, ctypes.POINTER(c_f64),
+                                                              ctypes.POINTER(c_f64), ctypes.POINTER(c_f64), ctypes.POINTER(c_f64),
+                                                              c_i32, ctypes.c_int, c_i32, c_i64, c_i64, ctypes.POINTER(c_i64), c_vp]),
+    "nbr_gather_finish": (ctypes.c_int, [c_vp, c_vp]),
+    "nbr_tile_step_gather": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_i64, ctypes.POINTER(c_f64), ctypes.POINTER(c_f64), c_i32,
+                                            ctypes.c_int, c_i32, ctypes.POINTER(c_f64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), c_vp]),
     "nbr_tile_step_host": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_i64, ctypes.POINTER(c_f64), ctypes.POINTER(c_f64), c_i32, c_vp,
                                           ctypes.c_int, c_i32, ctypes.POINTER(c_f64)]),
     "nbr_multiscale_features": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_vp, ctypes.c_int, c_i64,
@@ -137,6 +148,8 @@ def check(rc):
         raise ValueError(msg)
     if rc == ERR_UNSUPPORTED:
         raise NotImplementedError(msg)
+    if rc == ERR_CAPACITY:
+        raise RuntimeError(msg)
     raise RuntimeError("nimrud_b200 CUDA error: " + msg)
 
 

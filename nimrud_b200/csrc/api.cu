@@ -285,8 +285,11 @@ int plan_create(Plan **out, const void *search, int s_dtype, int64_t ns, const d
 
 // features of one batch of queries that is already in a coherent order: row i of `sorted` is query
 // perm[i] (perm == NULL: identity) and its features go to row perm[i] of `out`
+// dests (feature all-gather, nbr_tile_step_gather): `out` is this rank's share of its own gather buffer; the rows also
+// go to the same place in every peer's buffer -- from inside the fused kernel when one launch owns whole rows, otherwise
+// as peer copies of the finished share
 int plan_run_sorted(const Plan *P, const void *sorted, int q_dtype, const uint32_t *perm, int64_t nq, void *out,
-                    int out_dtype, cudaStream_t stream)
+                    int out_dtype, cudaStream_t stream, const RowDests *dests = nullptr)
 {
     if (out_dtype != NBR_F32 && out_dtype != NBR_F64) return fail(NBR_ERR_INVALID, "multiscale_features: bad out_dtype");
     if (nq <= 0 || P->n_scales == 0) return NBR_OK;
@@ -306,6 +309,7 @@ int plan_run_sorted(const Plan *P, const void *sorted, int q_dtype, const uint32
     R3Launch r3, r5;
     memset(&r3, 0, sizeof(r3));
     memset(&r5, 0, sizeof(r5));
+    bool only_rows3 = true;                   // every scale so far is an entry of the pending rows3 launch
     for (auto &g : P->groups) {
         std::vector<double> rr;
         std::vector<int> cc;
@@ -314,13 +318,15 @@ int plan_run_sorted(const Plan *P, const void *sorted, int q_dtype, const uint32
             int rc = NBR_OK;
             if (rows3_entry(g.lat, P->radii[s], s * ncol, r3.n ? &r3.e[r3.n - 1] : nullptr, &E, &r3.tq, stream, &rc)) {
                 r3.e[r3.n++] = E;
-                if (r3.n == R3_MAX_ENTRIES) {
+                if (r3.n == R3_MAX_ENTRIES && P->n_scales > R3_MAX_ENTRIES) {
                     NBR_TRY(rows3_launch(&r3, sorted, q_dtype, perm, nq, out, out_dtype, row_stride, P->descriptor_mask, stream));
                     r3.n = 0;
+                    only_rows3 = false;
                 }
                 continue;
             }
             NBR_TRY(rc);
+            only_rows3 = false;
             if (rows5_entry(g.lat, P->radii[s], s * ncol, r5.n ? &r5.e[r5.n - 1] : nullptr, &E, &r5.tq, stream, &rc)) {
                 r5.e[r5.n++] = E;
                 if (r5.n == R3_MAX_ENTRIES) {
@@ -343,9 +349,20 @@ int plan_run_sorted(const Plan *P, const void *sorted, int q_dtype, const uint32
             if (launch.n_lat == RW_MAX_LATTICES) NBR_TRY(flush());
         }
     }
-    NBR_TRY(rows3_launch(&r3, sorted, q_dtype, perm, nq, out, out_dtype, row_stride, P->descriptor_mask, stream));
+    static const bool peer_copies = getenv("NBR_GATHER") && std::string(getenv("NBR_GATHER")) == "copy";
+    const bool fused = dests && dests->n > 1 && only_rows3 && !peer_copies && ((uintptr_t)out & 15) == 0 &&
+                       rows3_owns_rows(r3.n, row_stride, out_dtype, P->descriptor_mask);
+    NBR_TRY(rows3_launch(&r3, sorted, q_dtype, perm, nq, out, out_dtype, row_stride, P->descriptor_mask, stream, fused ? dests : nullptr));
     NBR_TRY(rows5_launch(&r5, sorted, q_dtype, perm, nq, out, out_dtype, row_stride, P->descriptor_mask, stream));
-    return flush();
+    NBR_TRY(flush());
+    if (dests && !fused) {
+        const size_t row_bytes = (size_t)row_stride * (out_dtype == NBR_F32 ? 4 : 8);
+        for (int d = 0; d < dests->n; ++d)
+            if (d != dests->self)
+                NBR_CUDA(cudaMemcpyAsync(dests->base[d] + (size_t)dests->row_offset * row_bytes, out, (size_t)nq * row_bytes,
+                                         cudaMemcpyDefault, stream));
+    }
+    return NBR_OK;
 }
 
 // corner of brick (0,0,0) of the lattice with edge `finest` that plan_create would build for this box
@@ -590,6 +607,57 @@ extern "C" int nbr_multiscale_features_tile_mb(const void *sorted_xyz, const uin
     return rc;
 }
 
+// destinations of a rank's rows: its place (rank order) in the gather buffer of every rank.  NBR_ERR_CAPACITY if one
+// of the buffers cannot hold `total` rows
+static int gather_dests(const Mailbox *M, int64_t row_offset, int64_t total, size_t row_bytes, RowDests *D)
+{
+    memset(D, 0, sizeof(*D));
+    D->n = M->world;
+    D->self = M->rank;
+    D->row_offset = row_offset;
+    for (int r = 0; r < M->world; ++r) {
+        D->base[r] = M->gather_peer[r];
+        if ((!D->base[r] && total > 0 && row_bytes > 0) || (size_t)total * row_bytes > M->gather_peer_bytes[r])
+            return fail(NBR_ERR_CAPACITY, "feature gather: the gather buffers are too small for the rows of all ranks");
+    }
+    return NBR_OK;
+}
+
+// nbr_multiscale_features_tile_mb whose rows go to rows [row_offset, row_offset + n) of every rank's gather buffer
+// (step-wise form of nbr_tile_step_gather; the caller finishes the step with nbr_gather_finish, or -- several tiles on
+// one device in one process -- relies on stream order)
+extern "C" int nbr_multiscale_features_tile_mb_gather(const void *sorted_xyz, const uint32_t *perm, int dtype, int64_t n,
+                                                      nbr_mailbox *mailbox, const double *local_lohi_host,
+                                                      const double *global_lohi_host, const double *edges_host,
+                                                      const double *radii_host, int32_t n_scales, int out_dtype,
+                                                      int32_t descriptor_mask, int64_t row_offset, int64_t total_rows,
+                                                      int64_t *n_voxels_host, void *stream)
+{
+    if (!mailbox || !local_lohi_host || !global_lohi_host || (n > 0 && (!sorted_xyz || !perm)) || row_offset < 0 || total_rows < row_offset + n)
+        return fail(NBR_ERR_INVALID, "nbr_multiscale_features_tile_mb_gather: bad argument");
+    NBR_TRY(check_cloud_dtype(dtype, "nbr_multiscale_features_tile_mb_gather"));
+    if (out_dtype != NBR_F32 && out_dtype != NBR_F64) return fail(NBR_ERR_INVALID, "nbr_multiscale_features_tile_mb_gather: bad out_dtype");
+    Mailbox *M = reinterpret_cast<Mailbox *>(mailbox);
+    if (n <= 0 || n_scales <= 0) return halo_wait(M, (cudaStream_t)stream);
+    const int ncol = (descriptor_mask & NBR_DESC_EXTENDED) ? NBR_COLS_EXTENDED : NBR_COLS_REFERENCE;
+    const size_t row_bytes = (size_t)ncol * n_scales * (out_dtype == NBR_F32 ? 4 : 8);
+    RowDests D;
+    NBR_TRY(gather_dests(M, row_offset, total_rows, row_bytes, &D));
+    Plan *P = nullptr;
+    NBR_TRY(plan_create(&P, sorted_xyz, dtype, n, edges_host, radii_host, n_scales, descriptor_mask, global_lohi_host,
+                        local_lohi_host, (cudaStream_t)stream, nullptr, 0, M));
+    int rc = plan_run_sorted(P, sorted_xyz, dtype, perm, n, D.base[M->rank] + (size_t)row_offset * row_bytes, out_dtype, (cudaStream_t)stream, &D);
+    if (rc == NBR_OK && n_voxels_host) rc = plan_voxel_counts(P, n_voxels_host);
+    delete P;
+    return rc;
+}
+
+extern "C" int nbr_gather_finish(nbr_mailbox *mailbox, void *stream)
+{
+    if (!mailbox) return fail(NBR_ERR_INVALID, "nbr_gather_finish: null argument");
+    return gather_finish(reinterpret_cast<Mailbox *>(mailbox), (cudaStream_t)stream);
+}
+
 // one whole step of a rank in ONE call: box table (the step's only host synchronisation) -> halo push -> query
 // order of the tile -> lattices from tile + mailbox -> features.  nothing but C++ runs between the synchronisation
 // and the next launches, so the GPU idles for microseconds there, not for an interpreter's worth of time.
@@ -641,6 +709,45 @@ int tile_step_plan(Mailbox *M, const void *xyz, int dtype, int64_t n, const doub
                        &order);
 }
 }  // namespace nbr
+
+// nbr_tile_step whose rows land in the gather buffer of EVERY rank (rank order): the feature all-gather without a
+// collective call.  row_offsets_host[world + 1]: first row of every rank's share
+extern "C" int nbr_tile_step_gather(nbr_mailbox *mailbox, const void *xyz, int dtype, int64_t n, const double *edges_host,
+                                    const double *radii_host, int32_t n_scales, int out_dtype, int32_t descriptor_mask,
+                                    double *boxes_host_out, int64_t *n_voxels_host, int64_t *row_offsets_host, void *stream)
+{
+    Mailbox *M = reinterpret_cast<Mailbox *>(mailbox);
+    if (!M || n < 0 || n_scales < 0 || (n_scales > 0 && (!edges_host || !radii_host)) || (n > 0 && !xyz))
+        return fail(NBR_ERR_INVALID, "nbr_tile_step_gather: bad argument");
+    NBR_TRY(check_cloud_dtype(dtype, "nbr_tile_step_gather"));
+    if (out_dtype != NBR_F32 && out_dtype != NBR_F64) return fail(NBR_ERR_INVALID, "nbr_tile_step_gather: bad out_dtype");
+    cudaStream_t s = (cudaStream_t)stream;
+    Scratch perm, sorted;
+    Plan *P = nullptr;
+    double boxes[MB_MAX_WORLD][8];
+    NBR_TRY(tile_step_plan(M, xyz, dtype, n, edges_host, radii_host, n_scales, descriptor_mask, &boxes[0][0], perm, sorted, &P, s));
+    if (boxes_host_out) memcpy(boxes_host_out, boxes, sizeof(double) * 8 * M->world);
+    const int ncol = (descriptor_mask & NBR_DESC_EXTENDED) ? NBR_COLS_EXTENDED : NBR_COLS_REFERENCE;
+    const size_t row_bytes = (size_t)ncol * n_scales * (out_dtype == NBR_F32 ? 4 : 8);
+    RowDests D;
+    int64_t total = 0, mine = 0;
+    for (int r = 0; r < M->world; ++r) {
+        if (r == M->rank) mine = total;
+        if (row_offsets_host) row_offsets_host[r] = total;
+        total += (int64_t)boxes[r][6];
+    }
+    if (row_offsets_host) row_offsets_host[M->world] = total;
+    // every rank sees the same box table and the buffers have one size, so a capacity error is raised on every rank or
+    // on none; the step's halo exchange is complete by now (tile_step_plan), nothing is left half-done for the peers
+    int rc = gather_dests(M, mine, total, row_bytes, &D);
+    if (!rc && P && (int64_t)boxes[M->rank][6] != n) rc = fail(NBR_ERR_INVALID, "nbr_tile_step_gather: box table and tile disagree");
+    if (!rc && P)
+        rc = plan_run_sorted(P, sorted.ptr, dtype, perm.as<uint32_t>(), n, D.base[M->rank] + (size_t)D.row_offset * row_bytes, out_dtype, s, &D);
+    if (!rc && P && n_voxels_host) rc = plan_voxel_counts(P, n_voxels_host);
+    delete P;
+    if (!rc) rc = gather_finish(M, s);
+    return rc;
+}
 
 extern "C" int nbr_tile_step(nbr_mailbox *mailbox, const void *xyz, int dtype, int64_t n, const double *edges_host,
                              const double *radii_host, int32_t n_scales, void *out, int out_dtype,

@@ -227,6 +227,31 @@ __global__ void halo_wait_kernel(MailboxHeader *H, int rank, int world, unsigned
     }
 }
 
+// feature all-gather, last step: lane d tells peer d that this rank's rows of the epoch are in its buffer (the kernels
+// that wrote them are earlier on this stream; the system-scope fence + release make them visible before the flag), then
+// waits for peer d's flag in this rank's own header.  signal first, wait second: no rank waits for a rank that waits
+__global__ void gather_signal_wait_kernel(MailboxHeader *H, PeerHeaders P, int rank, int world, unsigned long long epoch,
+                                          unsigned long long *host_status, unsigned long long timeout_ns)
+{
+    const int d = threadIdx.x;
+    bool ok = true;
+    if (d < world && d != rank) {
+        __threadfence_system();
+        st_release_sys(&P.h[d]->gather_done[rank], epoch);
+        const unsigned long long t0 = global_ns();
+        while (ld_acquire_sys(&H->gather_done[d]) < epoch) {
+            if (global_ns() - t0 > timeout_ns) { ok = false; break; }
+            __nanosleep(200);
+        }
+    }
+    const bool all_ok = __all_sync(0xffffffffu, ok);
+    if (threadIdx.x == 0 && !all_ok) {
+        H->timeout = 1;
+        host_status[0] = 1ull;
+        __threadfence_system();
+    }
+}
+
 static unsigned long long timeout_ns()
 {
     static const unsigned long long ns = [] {
@@ -237,11 +262,25 @@ static unsigned long long timeout_ns()
     return ns;
 }
 
+void Mailbox::gather_release()
+{
+    for (int d = 0; d < MB_MAX_WORLD; ++d) {
+        if (gather_opened[d] && gather_peer[d]) cudaIpcCloseMemHandle(gather_peer[d]);
+        gather_peer[d] = nullptr;
+        gather_peer_bytes[d] = 0;
+        gather_opened[d] = false;
+    }
+    if (gather_base) cudaFree(gather_base);
+    gather_base = nullptr;
+    gather_bytes = 0;
+}
+
 Mailbox::~Mailbox()
 {
     int cur = 0;
     cudaGetDevice(&cur);
     cudaSetDevice(device);
+    gather_release();
     for (int d = 0; d < MB_MAX_WORLD; ++d)
         if (opened[d] && peer[d]) cudaIpcCloseMemHandle(peer[d]);
     if (base) cudaFree(base);
@@ -262,9 +301,89 @@ int halo_wait(Mailbox *M, cudaStream_t stream)
     return NBR_OK;
 }
 
+int gather_finish(Mailbox *M, cudaStream_t stream)
+{
+    if (M->world <= 1) return NBR_OK;
+    PhaseTimer tw(PHASE_HALO_WAIT, stream);
+    PeerHeaders P;
+    for (int d = 0; d < MB_MAX_WORLD; ++d) P.h[d] = reinterpret_cast<MailboxHeader *>(M->peer[d]);
+    unsigned long long *status = reinterpret_cast<unsigned long long *>(M->host_boxes + 8 * MB_MAX_WORLD);
+    gather_signal_wait_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<MailboxHeader *>(M->base), P, M->rank, M->world, M->epoch, status,
+                                                    timeout_ns());
+    NBR_LAUNCHED();
+    return NBR_OK;
+}
+
 }  // namespace nbr
 
 using namespace nbr;
+
+// ---- gather buffers: one per rank, sized for the rows of every rank; (re)allocation is collective on the caller's side
+// (every rank allocates, exchanges the handles, connects, and only then runs the next step)
+extern "C" int nbr_mailbox_gather_alloc(nbr_mailbox *mb, uint64_t bytes)
+{
+    Mailbox *M = reinterpret_cast<Mailbox *>(mb);
+    if (!M) return fail(NBR_ERR_INVALID, "nbr_mailbox_gather_alloc: null argument");
+    int cur = 0;
+    NBR_CUDA(cudaGetDevice(&cur));
+    NBR_CUDA(cudaSetDevice(M->device));
+    cudaDeviceSynchronize();
+    M->gather_release();
+    cudaError_t e = bytes ? cudaMalloc(&M->gather_base, bytes) : cudaSuccess;
+    cudaSetDevice(cur);
+    if (e != cudaSuccess) { M->gather_base = nullptr; return fail(NBR_ERR_CUDA, std::string("nbr_mailbox_gather_alloc: ") + cudaGetErrorString(e)); }
+    M->gather_bytes = bytes;
+    M->gather_peer[M->rank] = M->gather_base;
+    M->gather_peer_bytes[M->rank] = bytes;
+    return NBR_OK;
+}
+
+extern "C" int nbr_mailbox_gather_ipc_handle(const nbr_mailbox *mb, void *handle_out_64)
+{
+    const Mailbox *M = reinterpret_cast<const Mailbox *>(mb);
+    if (!M || !handle_out_64 || !M->gather_base) return fail(NBR_ERR_INVALID, "nbr_mailbox_gather_ipc_handle: no gather buffer");
+    cudaIpcMemHandle_t h;
+    NBR_CUDA(cudaIpcGetMemHandle(&h, M->gather_base));
+    memcpy(handle_out_64, &h, 64);
+    return NBR_OK;
+}
+
+extern "C" int nbr_mailbox_gather_connect_ipc(nbr_mailbox *mb, int32_t peer, const void *handle_64, uint64_t bytes)
+{
+    Mailbox *M = reinterpret_cast<Mailbox *>(mb);
+    if (!M || !handle_64 || peer < 0 || peer >= M->world || peer == M->rank)
+        return fail(NBR_ERR_INVALID, "nbr_mailbox_gather_connect_ipc: bad argument");
+    if (M->gather_opened[peer] && M->gather_peer[peer]) cudaIpcCloseMemHandle(M->gather_peer[peer]);
+    M->gather_peer[peer] = nullptr;
+    M->gather_opened[peer] = false;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle_64, 64);
+    void *p = nullptr;
+    NBR_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    M->gather_peer[peer] = reinterpret_cast<unsigned char *>(p);
+    M->gather_peer_bytes[peer] = bytes;
+    M->gather_opened[peer] = true;
+    return NBR_OK;
+}
+
+extern "C" int nbr_mailbox_gather_connect_local(nbr_mailbox *mb, int32_t peer, const nbr_mailbox *peer_mb)
+{
+    Mailbox *M = reinterpret_cast<Mailbox *>(mb);
+    const Mailbox *Q = reinterpret_cast<const Mailbox *>(peer_mb);
+    if (!M || !Q || peer < 0 || peer >= M->world || peer == M->rank || Q->rank != peer || !Q->gather_base)
+        return fail(NBR_ERR_INVALID, "nbr_mailbox_gather_connect_local: bad argument");
+    M->gather_peer[peer] = Q->gather_base;           // peer access between the devices was enabled by nbr_mailbox_connect_local
+    M->gather_peer_bytes[peer] = Q->gather_bytes;
+    M->gather_opened[peer] = false;
+    return NBR_OK;
+}
+
+extern "C" void *nbr_mailbox_gather_ptr(const nbr_mailbox *mb, uint64_t *bytes_out)
+{
+    const Mailbox *M = reinterpret_cast<const Mailbox *>(mb);
+    if (bytes_out) *bytes_out = M ? (uint64_t)M->gather_bytes : 0;
+    return M ? M->gather_base : nullptr;
+}
 
 extern "C" int nbr_mailbox_create(nbr_mailbox **out, int32_t rank, int32_t world, int dtype, int64_t capacity_rows)
 {

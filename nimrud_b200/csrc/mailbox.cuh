@@ -19,6 +19,7 @@ struct MailboxHeader {
     unsigned long long overflow;                     // sticky: rows dropped because the mailbox was full
     unsigned long long timeout;                      // sticky: a wait gave up
     unsigned long long blocks_done;                  // push kernel: blocks finished (the last one signals)
+    unsigned long long gather_done[MB_MAX_WORLD];    // epoch of the last finished row gather of every peer (gather buffers)
 };
 static_assert(sizeof(MailboxHeader) <= MB_HEADER_BYTES, "mailbox header");
 
@@ -32,9 +33,29 @@ struct Mailbox {
     unsigned long long epoch = 0;
     double *box_dev = nullptr;                       // this rank's bounding box (device, 8 doubles)
     double *host_boxes = nullptr;                    // pinned: [MB_MAX_WORLD][8] boxes, then 8 status words
+    // feature all-gather through peer stores: every rank owns a buffer for the rows of ALL ranks (rank order), mapped
+    // by the others like the mailbox itself; the feature kernel writes every finished row into all of them
+    unsigned char *gather_base = nullptr;
+    size_t gather_bytes = 0;
+    unsigned char *gather_peer[MB_MAX_WORLD] = {nullptr};
+    size_t gather_peer_bytes[MB_MAX_WORLD] = {0};
+    bool gather_opened[MB_MAX_WORLD] = {false};
+    void gather_release();
     ~Mailbox();
     const void *rows() const { return base + MB_HEADER_BYTES; }
     const unsigned long long *count_dev() const { return &reinterpret_cast<const MailboxHeader *>(base)->count; }
 };
+
+// destinations of finished feature rows (rows3.cu): row q of this launch goes to base[d] + (row_offset + q) * row bytes
+struct RowDests {
+    unsigned char *base[MB_MAX_WORLD];
+    long long row_offset;
+    int n;
+    int self;                     // index of this rank's own buffer
+};
+
+int halo_wait(Mailbox *M, cudaStream_t stream);
+// signals "my rows of this epoch are in your buffer" to every peer, then waits for every peer's signal
+int gather_finish(Mailbox *M, cudaStream_t stream);
 
 }  // namespace nbr

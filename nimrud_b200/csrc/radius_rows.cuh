@@ -54,8 +54,10 @@ struct R3Launch {
 };
 bool rows3_entry(const Lattice *lat, double radius, int col, const R3Entry *prev, R3Entry *E, int *tq_io,
                  cudaStream_t stream, int *rc);
+struct RowDests;
 int rows3_launch(const R3Launch *L, const void *query, int dtype, const uint32_t *perm, int64_t nq, void *out,
-                 int out_dtype, int64_t row_stride, int descriptor_mask, cudaStream_t stream);
+                 int out_dtype, int64_t row_stride, int descriptor_mask, cudaStream_t stream, const RowDests *dests = nullptr);
+bool rows3_owns_rows(int n_entries, int64_t row_stride, int out_dtype, int descriptor_mask);
 
 // same for 11x11x11 windows (rows5.cu): r/e + 0.5 < 6
 bool rows5_entry(const Lattice *lat, double radius, int col, const R3Entry *prev, R3Entry *E, int *tq_io,

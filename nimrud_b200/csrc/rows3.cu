@@ -20,6 +20,7 @@
 #include "finalize.cuh"
 #include "lattice.cuh"
 #include "radius_rows.cuh"
+#include "mailbox.cuh"
 
 #include <stdlib.h>
 
@@ -113,10 +114,14 @@ __device__ __noinline__ bool r3_exact_in(const R3Entry &E, double qx, double qy,
     return s <= __dmul_rn(E.r, E.r);
 }
 
-template <typename OutT, bool EXT>
+// MULTI: the finished rows are the rank's share of a feature all-gather -- every row is stored into the gather buffer of
+// EVERY rank (D.base[d], peer-mapped over NVLink) at its place in rank order, so the exchange rides on the kernel's own
+// write-out instead of following it as a collective
+template <typename OutT, bool EXT, bool MULTI>
 __global__ void __launch_bounds__(R3_WARPS * 32, R3_BLOCKS_N)
 rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query, int dtype,
-             const uint32_t *__restrict__ perm, int64_t nq, OutT *__restrict__ out, int64_t row_stride, int stage_rows)
+             const uint32_t *__restrict__ perm, int64_t nq, OutT *__restrict__ out, int64_t row_stride, int stage_rows,
+             const __grid_constant__ RowDests D)
 {
     // dynamic shared memory, per warp: brick window | table lines | output rows (when the launch owns whole rows)
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -499,7 +504,11 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
                 if (row_active) {
                     const uint4 v = *reinterpret_cast<const uint4 *>(rows + r * row_bytes + cidx * 16);
                     // streaming store: the rows are never read again, they should not push bricks and tables out of L2
-                    __stcs(reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(out) + row_q * (long long)row_bytes + cidx * 16), v);
+                    if (MULTI) {
+                        const long long at = (D.row_offset + row_q) * (long long)row_bytes + cidx * 16;
+                        for (int d = 0; d < D.n; ++d) __stcs(reinterpret_cast<uint4 *>(D.base[d] + at), v);
+                    } else
+                        __stcs(reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(out) + row_q * (long long)row_bytes + cidx * 16), v);
                 }
                 r += r_step; cidx += c_step;
                 if (cidx >= cpr) { cidx -= cpr; r += 1; }
@@ -544,8 +553,19 @@ bool rows3_entry(const Lattice *lat, double radius, int col, const R3Entry *prev
     return *rc == NBR_OK;
 }
 
+// true if a launch of n_entries entries assembles whole rows in shared memory (the condition of the MULTI write-out)
+bool rows3_owns_rows(int n_entries, int64_t row_stride, int out_dtype, int descriptor_mask)
+{
+    static const bool no_stage = getenv("NBR_NO_ROW_STAGING") != nullptr;
+    const bool ext = (descriptor_mask & NBR_DESC_EXTENDED) != 0;
+    const int ncol = ext ? NBR_COLS_EXTENDED : NBR_COLS_REFERENCE;
+    const size_t row_bytes = (size_t)row_stride * (out_dtype == NBR_F32 ? 4 : 8);
+    return !no_stage && !ext && n_entries > 0 && n_entries <= R3_MAX_ENTRIES && (int64_t)n_entries * ncol == row_stride &&
+           row_bytes <= R3_MAX_ROW_BYTES && row_bytes % 16 == 0;
+}
+
 int rows3_launch(const R3Launch *L, const void *query, int dtype, const uint32_t *perm, int64_t nq, void *out,
-                 int out_dtype, int64_t row_stride, int descriptor_mask, cudaStream_t stream)
+                 int out_dtype, int64_t row_stride, int descriptor_mask, cudaStream_t stream, const RowDests *dests)
 {
     if (nq <= 0 || L->n <= 0) return NBR_OK;
     R3Launch copy = *L;
@@ -565,18 +585,29 @@ int rows3_launch(const R3Launch *L, const void *query, int dtype, const uint32_t
     static const bool no_stage = getenv("NBR_NO_ROW_STAGING") != nullptr;
     const int stage_rows = !no_stage && (int64_t)L->n * ncol == row_stride && row_bytes <= R3_MAX_ROW_BYTES && row_bytes % 16 == 0 &&
                            ((uintptr_t)out & 15) == 0;
+    if (dests && (!stage_rows || ext)) return fail(NBR_ERR_UNSUPPORTED, "rows3_launch: rows for several destinations need a launch that owns whole rows");
+    RowDests D;
+    memset(&D, 0, sizeof(D));
+    if (dests) {
+        D = *dests;
+        for (int d = 0; d < D.n; ++d)
+            if (((uintptr_t)D.base[d] & 15) != 0) return fail(NBR_ERR_INVALID, "rows3_launch: destination rows must be 16-byte aligned");
+    }
     const size_t smem = (size_t)R3_WARPS * (R3_WIN_BYTES + R3_TAB_BYTES + (stage_rows ? 32 * row_bytes : 0));
     static std::atomic<uint64_t> configured{0};
     if (first_use_on_device(configured)) {
         const int max_smem = R3_WARPS * (R3_WIN_BYTES + R3_TAB_BYTES + 32 * R3_MAX_ROW_BYTES);
-        NBR_CUDA(cudaFuncSetAttribute(rows3_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        NBR_CUDA(cudaFuncSetAttribute(rows3_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        NBR_CUDA(cudaFuncSetAttribute(rows3_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        NBR_CUDA(cudaFuncSetAttribute(rows3_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        NBR_CUDA(cudaFuncSetAttribute(rows3_kernel<float, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        NBR_CUDA(cudaFuncSetAttribute(rows3_kernel<float, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        NBR_CUDA(cudaFuncSetAttribute(rows3_kernel<double, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        NBR_CUDA(cudaFuncSetAttribute(rows3_kernel<double, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        NBR_CUDA(cudaFuncSetAttribute(rows3_kernel<float, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        NBR_CUDA(cudaFuncSetAttribute(rows3_kernel<double, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     }
-#define R3_GO(T, X) rows3_kernel<T, X><<<blocks, R3_WARPS * 32, smem, stream>>>(copy, query, dtype, perm, nq, (T *)out, row_stride, stage_rows)
-    if (out_dtype == NBR_F32) { if (ext) R3_GO(float, true); else R3_GO(float, false); }
-    else                      { if (ext) R3_GO(double, true); else R3_GO(double, false); }
+#define R3_GO(T, X, M) rows3_kernel<T, X, M><<<blocks, R3_WARPS * 32, smem, stream>>>(copy, query, dtype, perm, nq, (T *)out, row_stride, stage_rows, D)
+    if (dests) { if (out_dtype == NBR_F32) R3_GO(float, false, true); else R3_GO(double, false, true); }
+    else if (out_dtype == NBR_F32) { if (ext) R3_GO(float, true, false); else R3_GO(float, false, false); }
+    else                           { if (ext) R3_GO(double, true, false); else R3_GO(double, false, false); }
 #undef R3_GO
     NBR_LAUNCHED();
     if (want_stats) {

@@ -33,6 +33,18 @@ def worker(rank, world, port, tmp):
     feats_nccl = nd.process_tile(mine.cuda().contiguous(), EDGES, RADII, gather=True, out_dtype=np.float32)
     os.environ.pop("NBR_HALO")
     assert torch.equal(feats, feats_nccl)
+    # the all-gather through peer stores from inside the feature kernel (nbr_tile_step_gather), twice (the second step
+    # reuses the buffers), and with a scale set the 7x7x7 kernel does not cover alone (peer copies of the finished share)
+    for _ in range(2):
+        peer = nd.process_tile(mine.cuda().contiguous(), EDGES, RADII, gather="peer", out_dtype=np.float32)
+        assert torch.equal(peer, feats)
+    mixed_e, mixed_r = (0.2, 0.2, 0.4), (0.6, 1.0, 1.2)
+    a = nd.process_tile(mine.cuda().contiguous(), mixed_e, mixed_r, gather=True, out_dtype=np.float32)
+    b = nd.process_tile(mine.cuda().contiguous(), mixed_e, mixed_r, gather="peer", out_dtype=np.float32)
+    assert torch.equal(a, b)
+    b64 = nd.process_tile(mine.cuda().contiguous(), EDGES, RADII, gather="peer", out_dtype=np.float64)
+    a64 = nd.process_tile(mine.cuda().contiguous(), EDGES, RADII, gather=True, out_dtype=np.float64)
+    assert b64.dtype == torch.float64 and torch.equal(a64, b64)
     # host buffers (nbr_tile_step_host): float32 on the wire, widened on the host
     local = nd.process_tile(mine.cuda().contiguous(), EDGES, RADII, out_dtype=np.float32)
     host_rows = nd.process_tile_host(mine.numpy(), EDGES, RADII, out_dtype=np.float64)

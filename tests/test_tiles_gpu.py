@@ -74,6 +74,43 @@ def test_tiles_in_one_process_match_unpartitioned(scene, nx, ny):
     assert seam_rows > 1000            # the comparison covered queries that need the halo
 
 
+@pytest.mark.parametrize("mode", ["fused", "copy"])
+def test_rows_gathered_by_the_feature_kernel(scene, mode):
+    """the feature all-gather through peer stores: every tile's kernel writes its rows into the gather buffer of EVERY
+    tile (here: four buffers on one device); each buffer must hold the unpartitioned rows in tile order.  "copy" is
+    the path of scale sets the 7x7x7 kernel does not cover alone (rows into the own buffer, then peer copies)."""
+    from nimrud_b200 import distributed as nd
+    cloud, whole = scene
+    idx = split_tiles(cloud, 2, 2)
+    tiles = [cloud[i].contiguous() for i in idx]
+    order = torch.cat(idx)
+    if mode == "copy":
+        edges, radii = (0.2, 0.2, 0.4), (0.6, 1.0, 1.2)        # 7x7x7 and 11x11x11 windows in one call
+        from nimrud_b200 import multiscale
+        ref = multiscale.process_single_core(cloud, cloud, edges, radii, out_dtype=np.float32)[order]
+    else:
+        edges, radii, ref = EDGES, RADII, whole[order]
+    launches0 = _launches()
+    outs = nd.process_tiles_local(tiles, edges, radii, out_dtype=np.float32, gather=True)
+    assert len(outs) == 4 and _launches() > launches0
+    for o in outs:
+        assert o.shape == ref.shape and torch.equal(o, ref)
+    # float64 rows, uneven tiles with an empty one
+    tiles3 = [tiles[0], tiles[1][:0], torch.cat([tiles[1], tiles[2], tiles[3]])]
+    order3 = torch.cat([idx[0], idx[1], idx[2], idx[3]])
+    outs = nd.process_tiles_local(tiles3, edges, radii, out_dtype=np.float64, gather=True)
+    if mode == "fused":
+        from nimrud_b200 import multiscale
+        ref64 = multiscale.process_single_core(cloud, cloud, edges, radii, out_dtype=np.float64)[order3]
+        for o in outs:
+            assert o.dtype == torch.float64 and torch.equal(o, ref64)
+
+
+def _launches():
+    from nimrud_b200 import _lib
+    return int(_lib.lib().nbr_kernel_launches())
+
+
 def test_empty_and_single_point_tiles(scene):
     from nimrud_b200 import distributed as nd
     cloud, whole = scene
