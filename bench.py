@@ -519,11 +519,11 @@ def gpu_arm(args, rank, world, local_rank):
     with_gather, seam = None, None
     if world > 1:
         g_steps = max(1, min(args.steps, 5))
-        gathered = nd.process_tile(cloud, EDGES, RADII, out=out, gather=True)
+        gathered = nd.process_tile(cloud, EDGES, RADII, out=out, gather="nccl")
         barrier()
         ev0.record()
         for _ in range(g_steps):
-            gathered = nd.process_tile(cloud, EDGES, RADII, out=out, gather=True)
+            gathered = nd.process_tile(cloud, EDGES, RADII, out=out, gather="nccl")
         ev1.record()
         barrier()
         t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
@@ -533,15 +533,17 @@ def gpu_arm(args, rank, world, local_rank):
                        "gathered_bytes_per_rank": int(gathered.numel() * gathered.element_size()),
                        "how": "all_gather_into_tensor of the (n, 20) float32 rows into one preallocated (N*n, 20) result on every rank"}
         same = bool(torch.equal(gathered[rank * n:(rank + 1) * n], out))
-        # the same result without a collective call: the fused feature kernel stores every finished row into the gather
-        # buffer of every rank over NVLink (process_tile(gather="peer") -> nbr_tile_step_gather)
-        peer = nd.process_tile(cloud, EDGES, RADII, gather="peer")
+        # the same result without a collective call: the fused feature kernel stores every finished row into a staging
+        # buffer of every other rank over NVLink, the receivers put the rows in place (process_tile(gather=True) ->
+        # nbr_tile_step_gather)
+        peer_out = torch.empty_like(gathered)
+        peer = nd.process_tile(cloud, EDGES, RADII, gather="peer", out_all=peer_out)
         peer_same = bool(torch.equal(peer, gathered))
         del gathered
         barrier()
         ev0.record()
         for _ in range(g_steps):
-            peer = nd.process_tile(cloud, EDGES, RADII, gather="peer")
+            peer = nd.process_tile(cloud, EDGES, RADII, gather="peer", out_all=peer_out)
         ev1.record()
         barrier()
         t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
@@ -552,10 +554,11 @@ def gpu_arm(args, rank, world, local_rank):
         with_gather["ms_per_step"] = p_ms
         with_gather["value"] = world * n * ns / (p_ms * 1e-3)
         with_gather["identical_to_nccl_gather"] = peer_same
-        with_gather["how"] = "rows stored into the (N*n, 20) float32 gather buffer of every rank by the feature kernel itself " \
-                             "(peer-mapped memory over NVLink, stream-ordered signal + wait, no collective call); nccl_*: the " \
-                             "same step followed by all_gather_into_tensor into a preallocated result"
-        del peer
+        with_gather["how"] = "finished rows stored into a staging buffer of every other rank by the feature kernel itself " \
+                             "(peer-mapped memory over NVLink, a warp's 32 rows as one contiguous piece + row numbers), " \
+                             "stream-ordered signal + wait, receivers put the rows in place in the preallocated (N*n, 20) " \
+                             "float32 result; no collective call.  nccl_*: the same step followed by all_gather_into_tensor"
+        del peer, peer_out
         seam = seam_check(nd, multiscale, dist, cloud, out, EDGES, RADII, rank, world)
         if seam is not None:
             seam["gathered_rows_match_local"] = same

@@ -288,33 +288,40 @@ int nbr_tile_step(nbr_mailbox *mailbox, const void *xyz, int dtype, int64_t n, c
                   double *boxes_host_out, int64_t *n_voxels_host, void *stream);
 
 /* FEATURE ALL-GATHER WITHOUT A COLLECTIVE CALL (north_star: "final feature all-gather"; no reference counterpart, the
- * reference is one process).  every rank owns a GATHER BUFFER for the rows of all ranks in rank order (cudaMalloc'ed by
- * nbr_mailbox_gather_alloc, mapped by the peers like the mailbox: nbr_mailbox_gather_ipc_handle ->
- * nbr_mailbox_gather_connect_ipc, or nbr_mailbox_gather_connect_local inside one process).  (re)allocation is
- * collective on the caller's side: every rank allocates the same size, the handles are exchanged, everybody connects, and
- * only then the next step runs.  nbr_tile_step_gather is nbr_tile_step whose fused feature kernel stores every finished
- * row into the buffer of EVERY rank (remote stores over NVLink from the kernel's own write-out; scale sets the 7x7x7
- * kernel does not cover alone are computed into the own buffer and pushed as peer copies), followed by a stream-ordered
- * signal + wait: when the call's work on `stream` is done, nbr_mailbox_gather_ptr() holds the rows of all ranks.
- * row_offsets_host[world + 1]: first row of every rank's share.  NBR_ERR_CAPACITY (on every rank alike, after the step's
- * halo exchange has completed): the buffers are too small for sum n rows; grow them collectively and call again. */
+ * reference is one process).  every rank owns a STAGING BUFFER (cudaMalloc'ed by nbr_mailbox_gather_alloc, mapped by the
+ * peers like the mailbox: nbr_mailbox_gather_ipc_handle -> nbr_mailbox_gather_connect_ipc, or
+ * nbr_mailbox_gather_connect_local inside one process) of at least nbr_gather_staging_bytes(rows of all ranks, row
+ * bytes).  (re)allocation is collective on the caller's side: every rank allocates the same size, the handles are
+ * exchanged, everybody connects, and only then the next step runs.
+ * nbr_tile_step_gather is nbr_tile_step with the all-gather inside: the fused feature kernel writes each finished row
+ * to its place in out_all AND -- in processing order, a warp's 32 rows as one contiguous piece, with the row numbers --
+ * into the staging buffer of every other rank (remote stores over NVLink from the kernel's own write-out; scale sets
+ * the 7x7x7 kernel does not cover alone are pushed after their kernels); a stream-ordered signal + wait follows, then
+ * the staged rows of the peers are put in place.  when the call's work on `stream` is done, out_all (ordinary device
+ * memory, out_rows_capacity rows) holds the rows of all ranks in rank order, every share in its tile's own order.
+ * row_offsets_host[world + 1]: first row of every rank's share.  NBR_ERR_CAPACITY (after the step's halo exchange has
+ * completed, on every rank alike if the ranks pass results of one size): staging buffers or result too small for
+ * sum n rows; row_offsets_host is valid, grow them collectively and call again. */
 int nbr_mailbox_gather_alloc(nbr_mailbox *mailbox, uint64_t bytes);
 int nbr_mailbox_gather_ipc_handle(const nbr_mailbox *mailbox, void *handle_out_64);
 int nbr_mailbox_gather_connect_ipc(nbr_mailbox *mailbox, int32_t peer, const void *handle_64, uint64_t bytes);
 int nbr_mailbox_gather_connect_local(nbr_mailbox *mailbox, int32_t peer, const nbr_mailbox *peer_mailbox);
 void *nbr_mailbox_gather_ptr(const nbr_mailbox *mailbox, uint64_t *bytes_out);
-/* step-wise form: nbr_multiscale_features_tile_mb with rows [row_offset, row_offset + n) of every gather buffer as the
- * output (total_rows = rows of all ranks), and the signal + wait as a call of its own */
+uint64_t nbr_gather_staging_bytes(int64_t total_rows, int64_t row_bytes);
+/* step-wise form: nbr_multiscale_features_tile_mb with the staging writes (this rank's rows are rows [row_offset,
+ * row_offset + n) of total_rows), then the signal + wait, then the staged rows into out_all */
 int nbr_multiscale_features_tile_mb_gather(const void *sorted_xyz, const uint32_t *perm, int dtype, int64_t n,
                                            nbr_mailbox *mailbox, const double *local_lohi_host,
                                            const double *global_lohi_host, const double *edges_host,
-                                           const double *radii_host, int32_t n_scales, int out_dtype,
+                                           const double *radii_host, int32_t n_scales, void *out_all, int out_dtype,
                                            int32_t descriptor_mask, int64_t row_offset, int64_t total_rows,
                                            int64_t *n_voxels_host, void *stream);
 int nbr_gather_finish(nbr_mailbox *mailbox, void *stream);
+int nbr_gather_unpermute(nbr_mailbox *mailbox, const int64_t *row_offsets_host, int64_t row_bytes, void *out_all, void *stream);
 int nbr_tile_step_gather(nbr_mailbox *mailbox, const void *xyz, int dtype, int64_t n, const double *edges_host,
-                         const double *radii_host, int32_t n_scales, int out_dtype, int32_t descriptor_mask,
-                         double *boxes_host_out, int64_t *n_voxels_host, int64_t *row_offsets_host, void *stream);
+                         const double *radii_host, int32_t n_scales, void *out_all, int64_t out_rows_capacity,
+                         int out_dtype, int32_t descriptor_mask, double *boxes_host_out, int64_t *n_voxels_host,
+                         int64_t *row_offsets_host, void *stream);
 
 /* nbr_tile_step with HOST buffers (the tile goes up, the rows come down in batches whose copies overlap the kernels;
  * float32 on the wire, widened by host threads for out_dtype NBR_F64, like nbr_multiscale_features_host). */

@@ -96,10 +96,13 @@ SIGNATURES = {
     "nbr_mailbox_gather_ptr": (c_vp, [c_vp, ctypes.POINTER(ctypes.c_uint64)]),
     "nbr_multiscale_features_tile_mb_gather": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_i64, c_vp, ctypes.POINTER(c_f64),
                                                               ctypes.POINTER(c_f64), ctypes.POINTER(c_f64), ctypes.POINTER(c_f64),
-                                                              c_i32, ctypes.c_int, c_i32, c_i64, c_i64, ctypes.POINTER(c_i64), c_vp]),
+                                                              c_i32, c_vp, ctypes.c_int, c_i32, c_i64, c_i64, ctypes.POINTER(c_i64), c_vp]),
     "nbr_gather_finish": (ctypes.c_int, [c_vp, c_vp]),
-    "nbr_tile_step_gather": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_i64, ctypes.POINTER(c_f64), ctypes.POINTER(c_f64), c_i32,
-                                            ctypes.c_int, c_i32, ctypes.POINTER(c_f64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), c_vp]),
+    "nbr_gather_unpermute": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i64), c_i64, c_vp, c_vp]),
+    "nbr_gather_staging_bytes": (ctypes.c_uint64, [c_i64, c_i64]),
+    "nbr_tile_step_gather": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_i64, ctypes.POINTER(c_f64), ctypes.POINTER(c_f64), c_i32, c_vp,
+                                            c_i64, ctypes.c_int, c_i32, ctypes.POINTER(c_f64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64),
+                                            c_vp]),
     "nbr_tile_step_host": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_i64, ctypes.POINTER(c_f64), ctypes.POINTER(c_f64), c_i32, c_vp,
                                           ctypes.c_int, c_i32, ctypes.POINTER(c_f64)]),
     "nbr_multiscale_features": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_vp, ctypes.c_int, c_i64,

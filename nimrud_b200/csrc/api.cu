@@ -285,9 +285,9 @@ int plan_create(Plan **out, const void *search, int s_dtype, int64_t ns, const d
 
 // features of one batch of queries that is already in a coherent order: row i of `sorted` is query
 // perm[i] (perm == NULL: identity) and its features go to row perm[i] of `out`
-// dests (feature all-gather, nbr_tile_step_gather): `out` is this rank's share of its own gather buffer; the rows also
-// go to the same place in every peer's buffer -- from inside the fused kernel when one launch owns whole rows, otherwise
-// as peer copies of the finished share
+// dests (feature all-gather, nbr_tile_step_gather): `out` is this rank's share of the result; the rows also go to every
+// peer's staging buffer -- from inside the fused kernel when one launch owns whole rows, otherwise as a push of the
+// finished share
 int plan_run_sorted(const Plan *P, const void *sorted, int q_dtype, const uint32_t *perm, int64_t nq, void *out,
                     int out_dtype, cudaStream_t stream, const RowDests *dests = nullptr)
 {
@@ -349,19 +349,14 @@ int plan_run_sorted(const Plan *P, const void *sorted, int q_dtype, const uint32
             if (launch.n_lat == RW_MAX_LATTICES) NBR_TRY(flush());
         }
     }
-    static const bool peer_copies = getenv("NBR_GATHER") && std::string(getenv("NBR_GATHER")) == "copy";
+    const char *gather_env = getenv("NBR_GATHER");
+    const bool peer_copies = gather_env && std::string(gather_env) == "copy";
     const bool fused = dests && dests->n > 1 && only_rows3 && !peer_copies && ((uintptr_t)out & 15) == 0 &&
                        rows3_owns_rows(r3.n, row_stride, out_dtype, P->descriptor_mask);
     NBR_TRY(rows3_launch(&r3, sorted, q_dtype, perm, nq, out, out_dtype, row_stride, P->descriptor_mask, stream, fused ? dests : nullptr));
     NBR_TRY(rows5_launch(&r5, sorted, q_dtype, perm, nq, out, out_dtype, row_stride, P->descriptor_mask, stream));
     NBR_TRY(flush());
-    if (dests && !fused) {
-        const size_t row_bytes = (size_t)row_stride * (out_dtype == NBR_F32 ? 4 : 8);
-        for (int d = 0; d < dests->n; ++d)
-            if (d != dests->self)
-                NBR_CUDA(cudaMemcpyAsync(dests->base[d] + (size_t)dests->row_offset * row_bytes, out, (size_t)nq * row_bytes,
-                                         cudaMemcpyDefault, stream));
-    }
+    if (dests && !fused) NBR_TRY(gather_push_rows(dests, out, nq, (size_t)row_stride * (out_dtype == NBR_F32 ? 4 : 8), stream));
     return NBR_OK;
 }
 
@@ -607,33 +602,37 @@ extern "C" int nbr_multiscale_features_tile_mb(const void *sorted_xyz, const uin
     return rc;
 }
 
-// destinations of a rank's rows: its place (rank order) in the gather buffer of every rank.  NBR_ERR_CAPACITY if one
-// of the buffers cannot hold `total` rows
+// destinations of a rank's rows in the staging buffers of the peers (rows [row_offset, ...) of `total`).
+// NBR_ERR_CAPACITY if one of the buffers cannot hold `total` rows and their row numbers
 static int gather_dests(const Mailbox *M, int64_t row_offset, int64_t total, size_t row_bytes, RowDests *D)
 {
     memset(D, 0, sizeof(*D));
     D->n = M->world;
     D->self = M->rank;
     D->row_offset = row_offset;
+    if (row_bytes % 16 != 0) return fail(NBR_ERR_UNSUPPORTED, "feature gather: rows must be multiples of 16 bytes");
+    const size_t need = gather_bytes_needed(total, row_bytes), perm_at = gather_perm_offset(total, row_bytes);
     for (int r = 0; r < M->world; ++r) {
+        if (M->world > 1 && total > 0 && (!M->gather_peer[r] || need > M->gather_peer_bytes[r]))
+            return fail(NBR_ERR_CAPACITY, "feature gather: the staging buffers are too small for the rows of all ranks");
         D->base[r] = M->gather_peer[r];
-        if ((!D->base[r] && total > 0 && row_bytes > 0) || (size_t)total * row_bytes > M->gather_peer_bytes[r])
-            return fail(NBR_ERR_CAPACITY, "feature gather: the gather buffers are too small for the rows of all ranks");
+        D->perm[r] = M->gather_peer[r] ? reinterpret_cast<uint32_t *>(M->gather_peer[r] + perm_at) : nullptr;
     }
     return NBR_OK;
 }
 
-// nbr_multiscale_features_tile_mb whose rows go to rows [row_offset, row_offset + n) of every rank's gather buffer
-// (step-wise form of nbr_tile_step_gather; the caller finishes the step with nbr_gather_finish, or -- several tiles on
-// one device in one process -- relies on stream order)
+// nbr_multiscale_features_tile_mb whose rows also go to the staging buffer of every other rank (step-wise form of
+// nbr_tile_step_gather: the caller finishes with nbr_gather_finish -- or, several tiles on one device in one process,
+// relies on stream order -- and nbr_gather_unpermute).  out_all: the result for the rows of ALL ranks
 extern "C" int nbr_multiscale_features_tile_mb_gather(const void *sorted_xyz, const uint32_t *perm, int dtype, int64_t n,
                                                       nbr_mailbox *mailbox, const double *local_lohi_host,
                                                       const double *global_lohi_host, const double *edges_host,
-                                                      const double *radii_host, int32_t n_scales, int out_dtype,
+                                                      const double *radii_host, int32_t n_scales, void *out_all, int out_dtype,
                                                       int32_t descriptor_mask, int64_t row_offset, int64_t total_rows,
                                                       int64_t *n_voxels_host, void *stream)
 {
-    if (!mailbox || !local_lohi_host || !global_lohi_host || (n > 0 && (!sorted_xyz || !perm)) || row_offset < 0 || total_rows < row_offset + n)
+    if (!mailbox || !local_lohi_host || !global_lohi_host || (n > 0 && (!sorted_xyz || !perm || !out_all)) || row_offset < 0 ||
+        total_rows < row_offset + n)
         return fail(NBR_ERR_INVALID, "nbr_multiscale_features_tile_mb_gather: bad argument");
     NBR_TRY(check_cloud_dtype(dtype, "nbr_multiscale_features_tile_mb_gather"));
     if (out_dtype != NBR_F32 && out_dtype != NBR_F64) return fail(NBR_ERR_INVALID, "nbr_multiscale_features_tile_mb_gather: bad out_dtype");
@@ -646,7 +645,8 @@ extern "C" int nbr_multiscale_features_tile_mb_gather(const void *sorted_xyz, co
     Plan *P = nullptr;
     NBR_TRY(plan_create(&P, sorted_xyz, dtype, n, edges_host, radii_host, n_scales, descriptor_mask, global_lohi_host,
                         local_lohi_host, (cudaStream_t)stream, nullptr, 0, M));
-    int rc = plan_run_sorted(P, sorted_xyz, dtype, perm, n, D.base[M->rank] + (size_t)row_offset * row_bytes, out_dtype, (cudaStream_t)stream, &D);
+    int rc = plan_run_sorted(P, sorted_xyz, dtype, perm, n, (unsigned char *)out_all + (size_t)row_offset * row_bytes, out_dtype,
+                             (cudaStream_t)stream, &D);
     if (rc == NBR_OK && n_voxels_host) rc = plan_voxel_counts(P, n_voxels_host);
     delete P;
     return rc;
@@ -656,6 +656,12 @@ extern "C" int nbr_gather_finish(nbr_mailbox *mailbox, void *stream)
 {
     if (!mailbox) return fail(NBR_ERR_INVALID, "nbr_gather_finish: null argument");
     return gather_finish(reinterpret_cast<Mailbox *>(mailbox), (cudaStream_t)stream);
+}
+
+extern "C" int nbr_gather_unpermute(nbr_mailbox *mailbox, const int64_t *row_offsets_host, int64_t row_bytes, void *out_all, void *stream)
+{
+    if (!mailbox || !row_offsets_host || row_bytes < 0 || !out_all) return fail(NBR_ERR_INVALID, "nbr_gather_unpermute: bad argument");
+    return gather_unpermute(reinterpret_cast<Mailbox *>(mailbox), row_offsets_host, (size_t)row_bytes, out_all, (cudaStream_t)stream);
 }
 
 // one whole step of a rank in ONE call: box table (the step's only host synchronisation) -> halo push -> query
@@ -710,14 +716,17 @@ int tile_step_plan(Mailbox *M, const void *xyz, int dtype, int64_t n, const doub
 }
 }  // namespace nbr
 
-// nbr_tile_step whose rows land in the gather buffer of EVERY rank (rank order): the feature all-gather without a
-// collective call.  row_offsets_host[world + 1]: first row of every rank's share
+// nbr_tile_step with the feature all-gather inside: out_all receives the rows of ALL ranks (rank order, every share in
+// its tile's own order).  the fused kernel stores every finished row into the staging buffers of the peers as it goes,
+// a stream-ordered signal + wait follows, then the staged rows of the peers are put in place.
+// row_offsets_host[world + 1]: first row of every rank's share
 extern "C" int nbr_tile_step_gather(nbr_mailbox *mailbox, const void *xyz, int dtype, int64_t n, const double *edges_host,
-                                    const double *radii_host, int32_t n_scales, int out_dtype, int32_t descriptor_mask,
-                                    double *boxes_host_out, int64_t *n_voxels_host, int64_t *row_offsets_host, void *stream)
+                                    const double *radii_host, int32_t n_scales, void *out_all, int64_t out_rows_capacity,
+                                    int out_dtype, int32_t descriptor_mask, double *boxes_host_out, int64_t *n_voxels_host,
+                                    int64_t *row_offsets_host, void *stream)
 {
     Mailbox *M = reinterpret_cast<Mailbox *>(mailbox);
-    if (!M || n < 0 || n_scales < 0 || (n_scales > 0 && (!edges_host || !radii_host)) || (n > 0 && !xyz))
+    if (!M || n < 0 || n_scales < 0 || (n_scales > 0 && (!edges_host || !radii_host)) || (n > 0 && !xyz) || out_rows_capacity < 0)
         return fail(NBR_ERR_INVALID, "nbr_tile_step_gather: bad argument");
     NBR_TRY(check_cloud_dtype(dtype, "nbr_tile_step_gather"));
     if (out_dtype != NBR_F32 && out_dtype != NBR_F64) return fail(NBR_ERR_INVALID, "nbr_tile_step_gather: bad out_dtype");
@@ -730,22 +739,26 @@ extern "C" int nbr_tile_step_gather(nbr_mailbox *mailbox, const void *xyz, int d
     const int ncol = (descriptor_mask & NBR_DESC_EXTENDED) ? NBR_COLS_EXTENDED : NBR_COLS_REFERENCE;
     const size_t row_bytes = (size_t)ncol * n_scales * (out_dtype == NBR_F32 ? 4 : 8);
     RowDests D;
-    int64_t total = 0, mine = 0;
-    for (int r = 0; r < M->world; ++r) {
-        if (r == M->rank) mine = total;
-        if (row_offsets_host) row_offsets_host[r] = total;
-        total += (int64_t)boxes[r][6];
-    }
-    if (row_offsets_host) row_offsets_host[M->world] = total;
-    // every rank sees the same box table and the buffers have one size, so a capacity error is raised on every rank or
-    // on none; the step's halo exchange is complete by now (tile_step_plan), nothing is left half-done for the peers
-    int rc = gather_dests(M, mine, total, row_bytes, &D);
+    int64_t offs[MB_MAX_WORLD + 1];
+    offs[0] = 0;
+    for (int r = 0; r < M->world; ++r) offs[r + 1] = offs[r] + (int64_t)boxes[r][6];
+    const int64_t total = offs[M->world];
+    if (row_offsets_host) std::copy(offs, offs + M->world + 1, row_offsets_host);
+    // every rank sees the same box table and the staging buffers have one size, so a capacity error of the STAGING
+    // buffers is raised on every rank or on none; the step's halo exchange is complete by now (tile_step_plan),
+    // nothing is left half-done for the peers.  the result's capacity is the caller's own business: ranks that pass
+    // differently sized results would disagree here, so it is checked last and reported the same way
+    int rc = gather_dests(M, offs[M->rank], total, row_bytes, &D);
+    if (!rc && (out_rows_capacity < total || (total > 0 && row_bytes > 0 && !out_all)))
+        rc = fail(NBR_ERR_CAPACITY, "nbr_tile_step_gather: the result holds fewer rows than all ranks produce");
     if (!rc && P && (int64_t)boxes[M->rank][6] != n) rc = fail(NBR_ERR_INVALID, "nbr_tile_step_gather: box table and tile disagree");
     if (!rc && P)
-        rc = plan_run_sorted(P, sorted.ptr, dtype, perm.as<uint32_t>(), n, D.base[M->rank] + (size_t)D.row_offset * row_bytes, out_dtype, s, &D);
+        rc = plan_run_sorted(P, sorted.ptr, dtype, perm.as<uint32_t>(), n, (unsigned char *)out_all + (size_t)offs[M->rank] * row_bytes,
+                             out_dtype, s, &D);
     if (!rc && P && n_voxels_host) rc = plan_voxel_counts(P, n_voxels_host);
     delete P;
     if (!rc) rc = gather_finish(M, s);
+    if (!rc) rc = gather_unpermute(M, offs, row_bytes, out_all, s);
     return rc;
 }
 

@@ -252,6 +252,54 @@ __global__ void gather_signal_wait_kernel(MailboxHeader *H, PeerHeaders P, int r
     }
 }
 
+// fallback of the fused write-out (scale sets the 7x7x7 kernel does not cover alone): the rank's finished rows, in
+// tile order, go to every peer's staging buffer as they are; their row numbers are the identity
+__global__ void gather_push_rows_kernel(const uint4 *__restrict__ rows, size_t n_pieces, int64_t n_rows, RowDests D, size_t row_bytes)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x, first = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (size_t i = first; i < n_pieces; i += stride) {
+        const uint4 v = rows[i];
+        for (int d = 0; d < D.n; ++d)
+            if (d != D.self) __stcs(reinterpret_cast<uint4 *>(D.base[d] + (size_t)D.row_offset * row_bytes) + i, v);
+    }
+    for (size_t i = first; i < (size_t)n_rows; i += stride)
+        for (int d = 0; d < D.n; ++d)
+            if (d != D.self) D.perm[d][D.row_offset + i] = (uint32_t)i;
+}
+
+struct UnpermuteDev {
+    long long off[MB_MAX_WORLD + 1];       // first row of every rank's share
+    int world, self;
+};
+
+// staged rows -> their places: a warp takes 32 consecutive staged rows (one contiguous read), looks up their row
+// numbers and stores each row as 16-byte pieces into its place of the result (local scattered stores: cheap)
+__global__ void gather_unpermute_kernel(const unsigned char *__restrict__ staged, const uint32_t *__restrict__ perm, UnpermuteDev U,
+                                        int cpr, unsigned char *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const long long total = U.off[U.world], row_bytes = 16ll * cpr;
+    const long long n_groups = (total + 31) >> 5;
+    for (long long grp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; grp < n_groups; grp += ((long long)gridDim.x * blockDim.x) >> 5) {
+        const long long g = grp * 32 + lane;
+        long long dst = -1;                                   // destination row of staged row g; -1: not staged (own share, tail)
+        if (g < total && !(g >= U.off[U.self] && g < U.off[U.self + 1])) {
+            int r = 0;
+            while (g >= U.off[r + 1]) ++r;
+            dst = U.off[r] + (long long)perm[g];
+        }
+        if (!__any_sync(0xffffffffu, dst >= 0)) continue;
+        for (int p = lane; p < 32 * cpr; p += 32) {
+            const int row = p / cpr, c = p - row * cpr;
+            const long long d = __shfl_sync(0xffffffffu, dst, row);
+            if (d >= 0) {
+                const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(staged + (grp * 32 + row) * row_bytes) + c);
+                __stcs(reinterpret_cast<uint4 *>(out + d * row_bytes) + c, v);
+            }
+        }
+    }
+}
+
 static unsigned long long timeout_ns()
 {
     static const unsigned long long ns = [] {
@@ -310,6 +358,35 @@ int gather_finish(Mailbox *M, cudaStream_t stream)
     unsigned long long *status = reinterpret_cast<unsigned long long *>(M->host_boxes + 8 * MB_MAX_WORLD);
     gather_signal_wait_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<MailboxHeader *>(M->base), P, M->rank, M->world, M->epoch, status,
                                                     timeout_ns());
+    NBR_LAUNCHED();
+    return NBR_OK;
+}
+
+int gather_push_rows(const RowDests *D, const void *rows, int64_t n, size_t row_bytes, cudaStream_t stream)
+{
+    if (n <= 0 || D->n <= 1) return NBR_OK;
+    if (row_bytes % 16 != 0 || ((uintptr_t)rows & 15) != 0) return fail(NBR_ERR_UNSUPPORTED, "feature gather: rows must be multiples of 16 bytes");
+    const size_t pieces = (size_t)n * row_bytes / 16;
+    const unsigned blocks = (unsigned)std::min<size_t>(ceil_div(pieces, (size_t)256), (size_t)device_sm_count() * 8);
+    gather_push_rows_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint4 *>(rows), pieces, n, *D, row_bytes);
+    NBR_LAUNCHED();
+    return NBR_OK;
+}
+
+int gather_unpermute(const Mailbox *M, const int64_t *row_offsets, size_t row_bytes, void *out_all, cudaStream_t stream)
+{
+    if (M->world <= 1) return NBR_OK;
+    const int64_t total = row_offsets[M->world];
+    if (total - (row_offsets[M->rank + 1] - row_offsets[M->rank]) <= 0 || row_bytes == 0) return NBR_OK;
+    if (row_bytes % 16 != 0 || ((uintptr_t)out_all & 15) != 0) return fail(NBR_ERR_UNSUPPORTED, "feature gather: rows must be multiples of 16 bytes");
+    UnpermuteDev U;
+    memset(&U, 0, sizeof(U));
+    for (int r = 0; r <= M->world; ++r) U.off[r] = row_offsets[r];
+    U.world = M->world;
+    U.self = M->rank;
+    const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(ceil_div(total, (int64_t)32), (int64_t)8), (int64_t)device_sm_count() * 8);
+    gather_unpermute_kernel<<<blocks, 256, 0, stream>>>(M->gather_base, reinterpret_cast<const uint32_t *>(M->gather_base + gather_perm_offset(total, row_bytes)),
+                                                        U, (int)(row_bytes / 16), reinterpret_cast<unsigned char *>(out_all));
     NBR_LAUNCHED();
     return NBR_OK;
 }
@@ -376,6 +453,11 @@ extern "C" int nbr_mailbox_gather_connect_local(nbr_mailbox *mb, int32_t peer, c
     M->gather_peer_bytes[peer] = Q->gather_bytes;
     M->gather_opened[peer] = false;
     return NBR_OK;
+}
+
+extern "C" uint64_t nbr_gather_staging_bytes(int64_t total_rows, int64_t row_bytes)
+{
+    return total_rows < 0 || row_bytes < 0 ? 0 : (uint64_t)gather_bytes_needed(total_rows, (size_t)row_bytes);
 }
 
 extern "C" void *nbr_mailbox_gather_ptr(const nbr_mailbox *mb, uint64_t *bytes_out)

@@ -114,9 +114,10 @@ __device__ __noinline__ bool r3_exact_in(const R3Entry &E, double qx, double qy,
     return s <= __dmul_rn(E.r, E.r);
 }
 
-// MULTI: the finished rows are the rank's share of a feature all-gather -- every row is stored into the gather buffer of
-// EVERY rank (D.base[d], peer-mapped over NVLink) at its place in rank order, so the exchange rides on the kernel's own
-// write-out instead of following it as a collective
+// MULTI: the finished rows are the rank's share of a feature all-gather -- besides its place in the rank's own result,
+// every row is stored into the staging buffer of every OTHER rank (D.base[d], peer-mapped over NVLink) in processing
+// order (a warp's 32 rows are one contiguous piece) together with its row number, so the exchange rides on the
+// kernel's own write-out instead of following it as a collective; the receivers put the rows in place (mailbox.cu)
 template <typename OutT, bool EXT, bool MULTI>
 __global__ void __launch_bounds__(R3_WARPS * 32, R3_BLOCKS_N)
 rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query, int dtype,
@@ -504,15 +505,19 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
                 if (row_active) {
                     const uint4 v = *reinterpret_cast<const uint4 *>(rows + r * row_bytes + cidx * 16);
                     // streaming store: the rows are never read again, they should not push bricks and tables out of L2
+                    __stcs(reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(out) + row_q * (long long)row_bytes + cidx * 16), v);
                     if (MULTI) {
-                        const long long at = (D.row_offset + row_q) * (long long)row_bytes + cidx * 16;
-                        for (int d = 0; d < D.n; ++d) __stcs(reinterpret_cast<uint4 *>(D.base[d] + at), v);
-                    } else
-                        __stcs(reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(out) + row_q * (long long)row_bytes + cidx * 16), v);
+                        const long long at = (D.row_offset + grp * 32) * (long long)row_bytes + (long long)gp * 16;
+                        for (int d = 0; d < D.n; ++d)
+                            if (d != D.self) __stcs(reinterpret_cast<uint4 *>(D.base[d] + at), v);
+                    }
                 }
                 r += r_step; cidx += c_step;
                 if (cidx >= cpr) { cidx -= cpr; r += 1; }
             }
+            if (MULTI && active)
+                for (int d = 0; d < D.n; ++d)
+                    if (d != D.self) D.perm[d][D.row_offset + slot_i] = (uint32_t)qi;
             __syncwarp();
         }
 #endif
@@ -591,7 +596,8 @@ int rows3_launch(const R3Launch *L, const void *query, int dtype, const uint32_t
     if (dests) {
         D = *dests;
         for (int d = 0; d < D.n; ++d)
-            if (((uintptr_t)D.base[d] & 15) != 0) return fail(NBR_ERR_INVALID, "rows3_launch: destination rows must be 16-byte aligned");
+            if (d != D.self && (((uintptr_t)D.base[d] & 15) != 0 || !D.base[d] || !D.perm[d]))
+                return fail(NBR_ERR_INVALID, "rows3_launch: destination rows must be 16-byte aligned");
     }
     const size_t smem = (size_t)R3_WARPS * (R3_WIN_BYTES + R3_TAB_BYTES + (stage_rows ? 32 * row_bytes : 0));
     static std::atomic<uint64_t> configured{0};

@@ -213,15 +213,6 @@ def default_capacity(n_local):
     return int(env) if env else max(4 << 20, int(n_local))
 
 
-class _DeviceView(object):
-    """__cuda_array_interface__ over library-owned device memory (keeps the owner alive)."""
-
-    def __init__(self, ptr_value, shape, np_dtype, owner):
-        self.owner = owner
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": np.dtype(np_dtype).str, "data": (ptr_value, False),
-                                         "version": 2, "strides": None}
-
-
 class HaloMailbox(object):
     """this rank's mailbox and its view of the peers' (one per (group, device, dtype); reused by every step)."""
 
@@ -235,6 +226,7 @@ class HaloMailbox(object):
             _lib.check(_lib.lib().nbr_mailbox_create(ctypes.byref(handle), self.rank, self.world, self.code, self.capacity))
         self.handle = handle
         self.boxes = np.zeros((self.world, 8), dtype=np.float64)
+        self.cache = {}
 
     def ipc_handle(self):
         from . import _lib
@@ -271,7 +263,7 @@ class HaloMailbox(object):
                         _lib.check(_lib.lib().nbr_mailbox_connect_local(a.handle, b.rank, b.handle))
         return boxes
 
-    # ---- gather buffers (feature all-gather through peer stores)
+    # ---- staging buffers of the feature all-gather through peer stores
     def gather_bytes(self):
         from . import _lib
         nbytes = ctypes.c_uint64(0)
@@ -285,7 +277,7 @@ class HaloMailbox(object):
         return bytes(buf.raw)
 
     def ensure_gather(self, nbytes, group=None):
-        """collective: every rank's gather buffer holds at least nbytes (the same value on every rank) and is mapped by
+        """collective: every rank's staging buffer holds at least nbytes (the same value on every rank) and is mapped by
         every peer.  a no-op when the buffers are large enough already."""
         from . import _lib
         nbytes = int(nbytes)
@@ -319,22 +311,6 @@ class HaloMailbox(object):
             for b in mailboxes:
                 if a is not b:
                     _lib.check(_lib.lib().nbr_mailbox_gather_connect_local(a.handle, b.rank, b.handle))
-
-    def gathered(self, rows, cols, np_dtype):
-        """(rows, cols) tensor over this rank's gather buffer: the rows of every rank, rank order.  a VIEW: the next
-        gathered step of this mailbox overwrites it."""
-        from . import _lib
-        nbytes = ctypes.c_uint64(0)
-        base = _lib.lib().nbr_mailbox_gather_ptr(self.handle, ctypes.byref(nbytes))
-        np_dtype = np.dtype(np_dtype)
-        if rows * cols * np_dtype.itemsize > nbytes.value:
-            raise ValueError("the gather buffer is smaller than the requested view")
-        if rows * cols == 0:
-            from .multiscale import _TORCH_OUT
-            return torch.zeros((rows, cols), dtype=_TORCH_OUT[np_dtype.type], device=self.device)
-        holder = _DeviceView(int(base), (int(rows), int(cols)), np_dtype, self)
-        with torch.cuda.device(self.device):
-            return torch.as_tensor(holder, device=self.device)
 
     def status(self):
         """{timeout, dropped, pushed}: valid after the device was synchronised."""
@@ -492,32 +468,47 @@ def _process_tile_cuda(cloud, edge_lengths, radii, out, out_dtype, group, voxel_
     return out, mb.boxes
 
 
-def _process_tile_gather(cloud, edge_lengths, radii, out_dtype, group, voxel_counts=None):
-    """nbr_tile_step_gather: the tile step whose rows land in every rank's gather buffer.  the buffers are sized from the
-    box table: the first step (and any step whose tiles outgrow them) reports NBR_ERR_CAPACITY on every rank alike, the
-    buffers are re-made collectively and the step is repeated."""
+def _process_tile_gather(cloud, edge_lengths, radii, out_all, out_dtype, group, voxel_counts=None):
+    """nbr_tile_step_gather: the tile step with the feature all-gather inside.  staging buffers and result are sized from
+    the box table: the first step (and any step whose tiles outgrow them) reports NBR_ERR_CAPACITY on every rank alike,
+    the buffers are re-made collectively and the step is repeated."""
     from . import _lib
     from ._util import ptr, stream_ptr
-    from .multiscale import _out_code
+    from .multiscale import _out_code, _TORCH_OUT
     np_out, out_code = _out_code(out_dtype)
     n = int(cloud.shape[0])
     cols = 4 * len(radii)
+    row_bytes = cols * np.dtype(np_out).itemsize
     mb = _group_mailbox(cloud, group)
     edges_arr, edges_p = _lib.f64_array(list(edge_lengths))
     radii_arr, radii_p = _lib.f64_array(list(radii))
     offsets = np.zeros(mb.world + 1, dtype=np.int64)
+    given = out_all is not None
+    if given and (out_all.dim() != 2 or out_all.shape[1] != cols or out_all.dtype != _TORCH_OUT[np_out] or not out_all.is_cuda
+                  or not out_all.is_contiguous()):
+        raise ValueError("out has the wrong shape, dtype or device")
+    key = ("gather_total", cols, np.dtype(np_out).str)
+    total = mb.cache.get(key, 0)
     for attempt in range(2):
+        res = out_all if given else torch.empty((total, cols), dtype=_TORCH_OUT[np_out], device=cloud.device)
         with torch.cuda.device(cloud.device):
             rc = _lib.lib().nbr_tile_step_gather(
-                mb.handle, ptr(cloud) if n else None, mb.code, n, edges_p, radii_p, len(radii), out_code, 0,
+                mb.handle, ptr(cloud) if n else None, mb.code, n, edges_p, radii_p, len(radii),
+                ptr(res) if res.numel() else None, int(res.shape[0]), out_code, 0,
                 mb.boxes.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
                 voxel_counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)) if voxel_counts is not None and n else None,
                 offsets.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), stream_ptr(cloud.device))
         if rc != _lib.ERR_CAPACITY or attempt == 1:
             _lib.check(rc)
             break
-        mb.ensure_gather(int(offsets[-1]) * cols * np.dtype(np_out).itemsize, group)
-    return mb.gathered(int(offsets[-1]), cols, np_out)
+        total = int(offsets[-1])
+        mb.cache[key] = total
+        if given and out_all.shape[0] < total:
+            raise ValueError("out holds %d rows, the ranks produce %d" % (out_all.shape[0], total))
+        mb.ensure_gather(int(_lib.lib().nbr_gather_staging_bytes(total, row_bytes)), group)
+    total = int(offsets[-1])
+    mb.cache[key] = total
+    return res[:total]
 
 
 def process_tile_host(cloud, edge_lengths, radii, out=None, out_dtype=np.float64, device=None, group=None, mailbox=None):
@@ -564,8 +555,8 @@ def process_tiles_local(clouds, edge_lengths, radii, out_dtype=np.float32, mailb
     multi-process run, every step issued for all tiles before the next one.  returns the list of per-tile
     feature tensors (rows in each tile's own order).  with one device this is also a way to process a cloud
     tile by tile; the single-GPU tests use it to prove tile + halo == unpartitioned.
-    gather=True: every tile's rows are stored into the gather buffer of EVERY tile by the feature kernel itself (the
-    peer-store all-gather of process_tile(gather="peer")); returns one (sum n, 4*S) view per tile, all equal.
+    gather=True: every tile's rows also go into the staging buffer of every other tile from inside the feature kernel
+    (the peer-store all-gather of process_tile(gather=True)); returns one (sum n, 4*S) tensor per tile, all equal.
     """
     from .multiscale import _out_code
     assert len(edge_lengths) == len(radii), "edge_lengths and radii should be equal-length sequences."
@@ -588,34 +579,38 @@ def process_tiles_local(clouds, edge_lengths, radii, out_dtype=np.float32, mailb
         if gather:
             from . import _lib
             from ._util import ptr, stream_ptr
+            from .multiscale import _TORCH_OUT
             devices = [c.device for c in clouds]
             one_device = len(set(devices)) == 1
             if not one_device and len(set(devices)) != world:
                 raise ValueError("gather=True needs all tiles on one device or every tile on its own")
             sizes = [int(c.shape[0]) for c in clouds]
-            offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+            offs = np.ascontiguousarray(np.concatenate([[0], np.cumsum(sizes)]), dtype=np.int64)
             cols = 4 * len(radii)
-            HaloMailbox.ensure_gather_local(mailboxes, int(offs[-1]) * cols * np.dtype(np_out).itemsize)
-            f64p = ctypes.POINTER(ctypes.c_double)
+            row_bytes = cols * np.dtype(np_out).itemsize
+            HaloMailbox.ensure_gather_local(mailboxes, int(_lib.lib().nbr_gather_staging_bytes(int(offs[-1]), row_bytes)))
+            f64p, i64p = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)
             edges_arr, edges_p = _lib.f64_array(list(edge_lengths))
             radii_arr, radii_p = _lib.f64_array(list(radii))
-            for mb, c, (h, glob, mine, local, origin) in zip(mailboxes, clouds, geo):
+            outs = [torch.empty((int(offs[-1]), cols), dtype=_TORCH_OUT[np_out], device=c.device) for c in clouds]
+            for mb, c, res, (h, glob, mine, local, origin) in zip(mailboxes, clouds, outs, geo):
                 with torch.cuda.device(c.device):
                     stream = torch.cuda.current_stream(c.device)
                     perm, ordered = _order_tile(c, mine, origin, float(min(edge_lengths)), stream)
                     n = int(c.shape[0])
                     _lib.check(_lib.lib().nbr_multiscale_features_tile_mb_gather(
                         ptr(ordered) if n else None, ptr(perm) if n else None, mb.code, n, mb.handle, local.ctypes.data_as(f64p),
-                        glob.ctypes.data_as(f64p), edges_p, radii_p, len(radii), out_code, 0, int(offs[mb.rank]), int(offs[-1]),
-                        None, stream_ptr(c.device)))
+                        glob.ctypes.data_as(f64p), edges_p, radii_p, len(radii), ptr(res), out_code, 0, int(offs[mb.rank]),
+                        int(offs[-1]), None, stream_ptr(c.device)))
             if not one_device:
                 # one tile per device: signal + wait on every device (on ONE device the launches are stream-ordered and a
                 # waiting kernel would only block the tiles behind it)
                 for mb in mailboxes:
                     with torch.cuda.device(mb.device):
                         _lib.check(_lib.lib().nbr_gather_finish(mb.handle, stream_ptr(mb.device)))
-            for mb in mailboxes:
-                outs.append(mb.gathered(int(offs[-1]), cols, np_out))
+            for mb, res in zip(mailboxes, outs):
+                with torch.cuda.device(mb.device):
+                    _lib.check(_lib.lib().nbr_gather_unpermute(mb.handle, offs.ctypes.data_as(i64p), row_bytes, ptr(res), stream_ptr(mb.device)))
         for mb, c, (h, glob, mine, local, origin) in zip(mailboxes, clouds, geo) if not gather else ():
             with torch.cuda.device(c.device):
                 stream = torch.cuda.current_stream(c.device)
@@ -628,8 +623,6 @@ def process_tiles_local(clouds, edge_lengths, radii, out_dtype=np.float32, mailb
             st = mb.status()
             if st["timeout"] or st["dropped"]:
                 raise RuntimeError("halo mailbox of tile %d: %s" % (mb.rank, st))
-        if gather and own:
-            outs = [o.clone() for o in outs]           # the views die with the mailboxes
         return outs
     finally:
         if own:
@@ -643,14 +636,15 @@ def _use_mailboxes(cloud):
 
 
 def process_tile(cloud, edge_lengths, radii, out=None, out_dtype=np.float32, gather=False, group=None,
-                 compute=None, voxel_counts=None):
+                 compute=None, voxel_counts=None, out_all=None):
     """
     features of this rank's tile (n_local, 4*S).  `cloud`: (n_local, 3) tensor on this rank's device; a rank may
     hold an empty tile (it still takes part in every collective step).
-    gather=True: returns the rows of every rank, concatenated in rank order, on every rank (NCCL all-gather into a
-    fresh tensor).  gather="peer": the same rows without a collective call -- the fused feature kernel stores every
-    finished row into the gather buffer of every rank over NVLink (nbr_tile_step_gather); the result is a VIEW of this
-    rank's buffer, valid until the next gather="peer" step of the same group (clone it to keep it).
+    gather=True: returns the rows of every rank, concatenated in rank order, on every rank.  on the CUDA mailbox path
+    the all-gather happens without a collective call: the fused feature kernel stores every finished row into a
+    staging buffer of every other rank over NVLink while it computes, the receivers put the rows in place
+    (nbr_tile_step_gather; NBR_GATHER=nccl or gather="nccl": features, then an NCCL all-gather).  out_all: optional
+    preallocated (>= sum n, 4*S) tensor for the rows of all ranks (peer-store path).
     compute(query, search, edges, radii, (lo, hi) numpy, out_dtype, out) -> features; default = CUDA path.
     voxel_counts: optional int64 numpy array (S,) receiving the unique voxels per scale of this rank's lattices
     (tile + halo; mailbox path only, forces a synchronisation).
@@ -658,10 +652,11 @@ def process_tile(cloud, edge_lengths, radii, out=None, out_dtype=np.float32, gat
     assert len(edge_lengths) == len(radii), "edge_lengths and radii should be equal-length sequences."
     world = dist.get_world_size(group)
     sizes = None
-    if gather == "peer":
-        if compute is not None or not _use_mailboxes(cloud) or world > 16:
-            raise ValueError('gather="peer" needs the CUDA mailbox path')
-        return _process_tile_gather(cloud, edge_lengths, radii, out_dtype, group, voxel_counts)
+    mailbox_path = compute is None and _use_mailboxes(cloud) and world <= 16
+    if gather == "peer" and not mailbox_path:
+        raise ValueError('gather="peer" needs the CUDA mailbox path')
+    if gather and gather != "nccl" and mailbox_path and (gather == "peer" or os.environ.get("NBR_GATHER", "peer") != "nccl"):
+        return _process_tile_gather(cloud, edge_lengths, radii, out_all, out_dtype, group, voxel_counts)
     if compute is None and _use_mailboxes(cloud) and world <= 16:
         feats, boxes = _process_tile_cuda(cloud, edge_lengths, radii, out, out_dtype, group, voxel_counts)
         sizes = [int(v) for v in boxes[:, 6]]

@@ -39,12 +39,15 @@ def worker(rank, world, port, tmp):
         peer = nd.process_tile(mine.cuda().contiguous(), EDGES, RADII, gather="peer", out_dtype=np.float32)
         assert torch.equal(peer, feats)
     mixed_e, mixed_r = (0.2, 0.2, 0.4), (0.6, 1.0, 1.2)
-    a = nd.process_tile(mine.cuda().contiguous(), mixed_e, mixed_r, gather=True, out_dtype=np.float32)
+    a = nd.process_tile(mine.cuda().contiguous(), mixed_e, mixed_r, gather="nccl", out_dtype=np.float32)
     b = nd.process_tile(mine.cuda().contiguous(), mixed_e, mixed_r, gather="peer", out_dtype=np.float32)
     assert torch.equal(a, b)
     b64 = nd.process_tile(mine.cuda().contiguous(), EDGES, RADII, gather="peer", out_dtype=np.float64)
-    a64 = nd.process_tile(mine.cuda().contiguous(), EDGES, RADII, gather=True, out_dtype=np.float64)
+    a64 = nd.process_tile(mine.cuda().contiguous(), EDGES, RADII, gather="nccl", out_dtype=np.float64)
     assert b64.dtype == torch.float64 and torch.equal(a64, b64)
+    keep = torch.empty((N + 7, 20), dtype=torch.float32, device="cuda")
+    got = nd.process_tile(mine.cuda().contiguous(), EDGES, RADII, gather=True, out_all=keep)
+    assert got.data_ptr() == keep.data_ptr() and torch.equal(got, feats)
     # host buffers (nbr_tile_step_host): float32 on the wire, widened on the host
     local = nd.process_tile(mine.cuda().contiguous(), EDGES, RADII, out_dtype=np.float32)
     host_rows = nd.process_tile_host(mine.numpy(), EDGES, RADII, out_dtype=np.float64)
