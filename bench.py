@@ -551,13 +551,18 @@ def gpu_arm(args, rank, world, local_rank):
         p_ms = float(t.item()) / g_steps
         with_gather["nccl_ms_per_step"] = g_ms
         with_gather["nccl_value"] = with_gather["value"]
-        with_gather["ms_per_step"] = p_ms
-        with_gather["value"] = world * n * ns / (p_ms * 1e-3)
+        with_gather["peer_ms_per_step"] = p_ms
+        with_gather["peer_value"] = world * n * ns / (p_ms * 1e-3)
+        # ms_per_step / value: what process_tile(gather=True) does by default at this world size
+        with_gather["default"] = "peer" if world <= 4 else "nccl"
+        if world <= 4:
+            with_gather["ms_per_step"] = p_ms
+            with_gather["value"] = with_gather["peer_value"]
         with_gather["identical_to_nccl_gather"] = peer_same
-        with_gather["how"] = "finished rows stored into a staging buffer of every other rank by the feature kernel itself " \
+        with_gather["how"] = "peer: finished rows stored into a staging buffer of every other rank by the feature kernel itself " \
                              "(peer-mapped memory over NVLink, a warp's 32 rows as one contiguous piece + row numbers), " \
                              "stream-ordered signal + wait, receivers put the rows in place in the preallocated (N*n, 20) " \
-                             "float32 result; no collective call.  nccl_*: the same step followed by all_gather_into_tensor"
+                             "float32 result; no collective call.  nccl: the same step followed by all_gather_into_tensor"
         del peer, peer_out
         seam = seam_check(nd, multiscale, dist, cloud, out, EDGES, RADII, rank, world)
         if seam is not None:

@@ -273,11 +273,16 @@ struct UnpermuteDev {
 };
 
 // staged rows -> their places: a warp takes 32 consecutive staged rows (one contiguous read), looks up their row
-// numbers and stores each row as 16-byte pieces into its place of the result (local scattered stores: cheap)
+// numbers and stores each row as 16-byte pieces into its place of the result.  the stores are random 80-byte accesses:
+// the kernel lives on memory-level parallelism, so all pieces of a group are loaded before the first one is stored
+// (CPR = 16-byte pieces per row, compile-time for the common row sizes; measured 0.92 ms per 10M rows with one load in
+// flight per warp)
+template <int CPR>
 __global__ void gather_unpermute_kernel(const unsigned char *__restrict__ staged, const uint32_t *__restrict__ perm, UnpermuteDev U,
-                                        int cpr, unsigned char *__restrict__ out)
+                                        int cpr_arg, unsigned char *__restrict__ out)
 {
     const int lane = threadIdx.x & 31;
+    const int cpr = CPR > 0 ? CPR : cpr_arg;
     const long long total = U.off[U.world], row_bytes = 16ll * cpr;
     const long long n_groups = (total + 31) >> 5;
     for (long long grp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; grp < n_groups; grp += ((long long)gridDim.x * blockDim.x) >> 5) {
@@ -289,12 +294,26 @@ __global__ void gather_unpermute_kernel(const unsigned char *__restrict__ staged
             dst = U.off[r] + (long long)perm[g];
         }
         if (!__any_sync(0xffffffffu, dst >= 0)) continue;
-        for (int p = lane; p < 32 * cpr; p += 32) {
-            const int row = p / cpr, c = p - row * cpr;
-            const long long d = __shfl_sync(0xffffffffu, dst, row);
-            if (d >= 0) {
-                const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(staged + (grp * 32 + row) * row_bytes) + c);
-                __stcs(reinterpret_cast<uint4 *>(out + d * row_bytes) + c, v);
+        const unsigned char *src = staged + grp * 32 * row_bytes;
+        if (CPR > 0) {
+            uint4 v[CPR > 0 ? CPR : 1];
+            long long d[CPR > 0 ? CPR : 1];
+            int c[CPR > 0 ? CPR : 1];
+#pragma unroll
+            for (int t = 0; t < CPR; ++t) {
+                const int p = lane + 32 * t, row = p / CPR;
+                c[t] = p - row * CPR;
+                d[t] = __shfl_sync(0xffffffffu, dst, row);
+                if (d[t] >= 0) v[t] = __ldcs(reinterpret_cast<const uint4 *>(src) + p);
+            }
+#pragma unroll
+            for (int t = 0; t < CPR; ++t)
+                if (d[t] >= 0) __stcs(reinterpret_cast<uint4 *>(out + d[t] * row_bytes) + c[t], v[t]);
+        } else {
+            for (int p = lane; p < 32 * cpr; p += 32) {
+                const int row = p / cpr, c = p - row * cpr;
+                const long long d = __shfl_sync(0xffffffffu, dst, row);
+                if (d >= 0) __stcs(reinterpret_cast<uint4 *>(out + d * row_bytes) + c, __ldcs(reinterpret_cast<const uint4 *>(src) + p));
             }
         }
     }
@@ -385,8 +404,12 @@ int gather_unpermute(const Mailbox *M, const int64_t *row_offsets, size_t row_by
     U.world = M->world;
     U.self = M->rank;
     const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(ceil_div(total, (int64_t)32), (int64_t)8), (int64_t)device_sm_count() * 8);
-    gather_unpermute_kernel<<<blocks, 256, 0, stream>>>(M->gather_base, reinterpret_cast<const uint32_t *>(M->gather_base + gather_perm_offset(total, row_bytes)),
-                                                        U, (int)(row_bytes / 16), reinterpret_cast<unsigned char *>(out_all));
+    const uint32_t *perm = reinterpret_cast<const uint32_t *>(M->gather_base + gather_perm_offset(total, row_bytes));
+    const int cpr = (int)(row_bytes / 16);
+    unsigned char *dst = reinterpret_cast<unsigned char *>(out_all);
+    if (cpr == 5) gather_unpermute_kernel<5><<<blocks, 256, 0, stream>>>(M->gather_base, perm, U, cpr, dst);           // 5 scales, float32
+    else if (cpr == 10) gather_unpermute_kernel<10><<<blocks, 256, 0, stream>>>(M->gather_base, perm, U, cpr, dst);    // 5 scales, float64
+    else gather_unpermute_kernel<0><<<blocks, 256, 0, stream>>>(M->gather_base, perm, U, cpr, dst);
     NBR_LAUNCHED();
     return NBR_OK;
 }

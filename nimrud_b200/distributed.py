@@ -643,8 +643,9 @@ def process_tile(cloud, edge_lengths, radii, out=None, out_dtype=np.float32, gat
     gather=True: returns the rows of every rank, concatenated in rank order, on every rank.  on the CUDA mailbox path
     the all-gather happens without a collective call: the fused feature kernel stores every finished row into a
     staging buffer of every other rank over NVLink while it computes, the receivers put the rows in place
-    (nbr_tile_step_gather; NBR_GATHER=nccl or gather="nccl": features, then an NCCL all-gather).  out_all: optional
-    preallocated (>= sum n, 4*S) tensor for the rows of all ranks (peer-store path).
+    (nbr_tile_step_gather; the default up to 4 ranks, gather="peer" / NBR_GATHER=peer forces it; gather="nccl" /
+    NBR_GATHER=nccl: features, then an NCCL all-gather).  out_all: optional preallocated (>= sum n, 4*S) tensor for
+    the rows of all ranks (peer-store path).
     compute(query, search, edges, radii, (lo, hi) numpy, out_dtype, out) -> features; default = CUDA path.
     voxel_counts: optional int64 numpy array (S,) receiving the unique voxels per scale of this rank's lattices
     (tile + halo; mailbox path only, forces a synchronisation).
@@ -655,7 +656,10 @@ def process_tile(cloud, edge_lengths, radii, out=None, out_dtype=np.float32, gat
     mailbox_path = compute is None and _use_mailboxes(cloud) and world <= 16
     if gather == "peer" and not mailbox_path:
         raise ValueError('gather="peer" needs the CUDA mailbox path')
-    if gather and gather != "nccl" and mailbox_path and (gather == "peer" or os.environ.get("NBR_GATHER", "peer") != "nccl"):
+    # default: the peer-store gather up to 4 ranks.  its receivers put (N - 1) n rows in place with random 80-byte
+    # writes (0.9 ms per 10M rows, DRAM-bound); from 8 ranks on that costs what riding on the kernel saves
+    auto = os.environ.get("NBR_GATHER", "peer" if world <= 4 else "nccl")
+    if gather and gather != "nccl" and mailbox_path and (gather == "peer" or auto in ("peer", "fused", "copy")):
         return _process_tile_gather(cloud, edge_lengths, radii, out_all, out_dtype, group, voxel_counts)
     if compute is None and _use_mailboxes(cloud) and world <= 16:
         feats, boxes = _process_tile_cuda(cloud, edge_lengths, radii, out, out_dtype, group, voxel_counts)

@@ -7,10 +7,11 @@ from nimrud_b200 import distributed as nd, synth
 EDGES = (0.1, 0.2, 0.4, 0.8, 1.6); RADII = (0.3, 0.6, 1.2, 2.4, 4.8)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
 world = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+gather = len(sys.argv) > 3 and sys.argv[3] == "gather"
 extent = math.sqrt(n / 40.0)
 tiles = [synth.urban_scene(n, seed=20 + r, device="cuda", origin=((r % 2) * extent, (r // 2) * extent)) for r in range(world)]
 mbs = nd.HaloMailbox.local_set(world, ["cuda"] * world, torch.float32, n)
 for it in range(3):
-    outs = nd.process_tiles_local(tiles, EDGES, RADII, mailboxes=mbs)
+    outs = nd.process_tiles_local(tiles, EDGES, RADII, mailboxes=mbs, gather=gather)
     torch.cuda.synchronize()
 print("ok", [float(o[:, 0].mean()) for o in outs])
