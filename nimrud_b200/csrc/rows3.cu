@@ -47,6 +47,9 @@ namespace nbr {
 #ifndef R3_TMA_ROWS
 #define R3_TMA_ROWS 0               // 1: finished rows leave shared memory as 80-byte bulk copies (TMA, UBLKCP) instead of through registers. measured: 4.128 vs 4.091 ms (10M tiny copies per step are bound by the engine's small-copy rate)
 #endif
+#ifndef R3_TMA_PEER
+#define R3_TMA_PEER 1               // MULTI launches: a warp's 32 finished rows leave for every peer as ONE bulk copy (TMA, UBLKCP: 2560 contiguous bytes) instead of 5 16-byte stores per lane and peer
+#endif
 #ifndef R3_PIPELINE
 #define R3_PIPELINE 0               // stage entry li + 1 before the eigen-solve of entry li
 #endif
@@ -158,6 +161,11 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
         OutT *dst_row = stage_rows ? reinterpret_cast<OutT *>(rows + lane * row_bytes) : out + qi * row_stride;
 #if R3_TMA_ROWS
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous group's rows have been read out of the buffer
+#elif R3_TMA_PEER
+        if (MULTI) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the copies to the peers have read the previous group's rows
+            __syncwarp();
+        }
 #endif
 
         // state of the current lattice (kept across entries that share it)
@@ -495,6 +503,22 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
 #else
         if (stage_rows) {
             // row buffer -> global: consecutive lanes write consecutive 16-byte pieces of a row
+#if R3_TMA_PEER
+            if (MULTI) {
+                // the warp's rows are one contiguous piece of shared memory and one contiguous piece of every peer's
+                // staging buffer: lane d hands them to the bulk-copy engine for peer d (the right granularity for it:
+                // 2.5 KB per copy, not one 80-byte row).  generic-proxy writes are fenced for the async proxy first
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                const long long left = (long long)nq - (long long)grp * 32, n_rows = left < 32 ? left : 32;
+                if (lane < D.n && lane != D.self) {
+                    const uint32_t src_addr = (uint32_t)__cvta_generic_to_shared(rows);
+                    unsigned char *gdst = D.base[lane] + (D.row_offset + grp * 32) * (long long)row_bytes;
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(src_addr), "r"((uint32_t)(n_rows * row_bytes)) : "memory");
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+#endif
             __syncwarp();
             // piece gp = lane + 32 t is piece cidx of row r; (r, cidx) advance by (32 / cpr, 32 % cpr) per trip
             const int pieces = 32 * cpr;
@@ -506,7 +530,7 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
                     const uint4 v = *reinterpret_cast<const uint4 *>(rows + r * row_bytes + cidx * 16);
                     // streaming store: the rows are never read again, they should not push bricks and tables out of L2
                     __stcs(reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(out) + row_q * (long long)row_bytes + cidx * 16), v);
-                    if (MULTI) {
+                    if (MULTI && !R3_TMA_PEER) {
                         const long long at = (D.row_offset + grp * 32) * (long long)row_bytes + (long long)gp * 16;
                         for (int d = 0; d < D.n; ++d)
                             if (d != D.self) __stcs(reinterpret_cast<uint4 *>(D.base[d] + at), v);
@@ -524,6 +548,8 @@ rows3_kernel(const __grid_constant__ R3Launch P, const void *__restrict__ query,
     }
 #if R3_TMA_ROWS
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");          // the last rows have left before the block retires
+#elif R3_TMA_PEER
+    if (MULTI) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 #endif
 }
 
