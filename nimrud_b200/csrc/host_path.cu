@@ -6,8 +6,8 @@
 //   * WIRE FORMAT float32.  the device computes float32 rows (population is an exact small integer, the other
 //     columns carry a 1e-4 tolerance and float32 keeps 6e-8), they cross PCIe at half the bytes, and host threads
 //     widen them into the caller's float64 array while the next batch is on the wire.  NBR_HOST_WIRE=f64 sends
-//     float64 rows instead; a pinned float64 result gets NBR_HOST_DIRECT_SHARE (0.1) of every batch widened on the
-//     device and written in place, which takes that share off the host's memory bus.
+//     float64 rows instead; with a pinned float64 result a batch whose turn comes while the host threads are behind is
+//     widened on the DEVICE and written in place (rows_to_host: routes), which takes it off the host's memory bus.
 //   * PINNED RINGS.  pageable buffers (plain numpy arrays) are staged through pinned ring buffers by a pool of host
 //     threads: cloud chunks in, row batches out; pinned caller buffers are used in place.  the rings are cached
 //     for the life of the process.
@@ -20,6 +20,7 @@
 #include <sys/mman.h>
 
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -322,26 +323,29 @@ static int rows_to_host(const Plan *P, const void *qdev_all, int q_dtype, int64_
     // by piece, and the tail after the last copy is one piece, not one batch
     const char *piece_env = getenv("NBR_HOST_PIECE_MB");
     const double piece_mb = piece_env && atof(piece_env) > 0 ? atof(piece_env) : 4.0;
-    // float64 rows from float32 wire rows cost the host 4 bytes of DRAM traffic per wire byte (the DMA write, the read, the
-    // doubled write) and the host's memory, not the link, bounds the call.  when the caller's buffer is pinned, the last
-    // `share` of every batch is widened on the DEVICE and lands in the caller's rows directly (2 bytes of DRAM traffic per
-    // wire byte of twice the wire bytes): the split balances link and host memory.  same values either way (float32 results).
-    // the ranks of a node share the host's cores and memory bus but each has its own link, so the share grows with
-    // LOCAL_WORLD_SIZE (measured, 10M points x 5 scales per rank: 1 rank 24.2 -> 23.2 ms at 0.1; 2 ranks 37.0 -> 31.2 ms at
-    // 0.5; 4 ranks 69.1 -> 42.9 ms and 8 ranks 165 -> 148 ms at 1.0)
-    const char *share_env = getenv("NBR_HOST_DIRECT_SHARE"), *lws_env = getenv("LOCAL_WORLD_SIZE");
-    const int local_ranks = lws_env ? atoi(lws_env) : 1;
-    const double share_default = local_ranks <= 1 ? 0.1 : (local_ranks == 2 ? 0.4 : 1.0);
-    const double share = !(widen_rows && out_pinned) ? 0.0 : (share_env ? std::min(std::max(atof(share_env), 0.0), 1.0) : share_default);
-    const int64_t batch_direct = (int64_t)((double)batch * share);
+    // ROUTES of a batch of float64 rows into a PINNED result.  "wire": float32 over the link into the pinned ring, widened
+    // by the host threads (4 bytes of host DRAM traffic per wire byte: the DMA write, the read, the doubled write).
+    // "device": widened on the device, float64 straight into the caller's rows (twice the link bytes, no host work).
+    // which one is cheaper depends on what the box is short of -- host memory / cores (one rank: 24.2 ms all-wire, 23.2
+    // with a tenth on the device route; 4 ranks on a box with fast links: 69 ms all-wire, 43 ms all-device) or link
+    // bandwidth (4 ranks on a box with 65 GB/s for all links: all-device 95 ms) -- so the route is chosen per batch, when
+    // its rows exist: wire if the pinned slot it needs is drained; device if that slot's rows have LANDED but the host
+    // threads are still behind; if the slot's rows have not even landed the link is the bottleneck and the batch waits
+    // for it.  NBR_HOST_WIDEN=host / device pins the route.  same values either way (float32 results).
+    enum { ROUTE_AUTO, ROUTE_WIRE, ROUTE_DEVICE };
+    const char *widen_env = getenv("NBR_HOST_WIDEN");
+    int route_mode = ROUTE_WIRE;
+    if (widen_rows && out_pinned)
+        route_mode = !widen_env ? ROUTE_AUTO : (std::string(widen_env) == "device" ? ROUTE_DEVICE : (std::string(widen_env) == "host" ? ROUTE_WIRE : ROUTE_AUTO));
     const size_t piece_rows = direct ? (size_t)batch : std::max<size_t>(1, (size_t)(piece_mb * (1 << 20)) / wrow);
     const int pieces_per_batch = (int)ceil_div(batch, (int64_t)piece_rows);
-    std::vector<cudaEvent_t> computed(RING, nullptr), drained(RING, nullptr), landed((size_t)RING * pieces_per_batch, nullptr);
+    // computed[s]: the kernels of the batch in device slot s are done; freed[s]: the slot's rows have been read
+    std::vector<cudaEvent_t> computed(RING, nullptr), freed(RING, nullptr), landed((size_t)RING * pieces_per_batch, nullptr);
     int rc = NBR_OK;
     cudaError_t e = cudaSuccess;
     for (auto &ev : computed)
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-    for (auto &ev : drained)
+    for (auto &ev : freed)
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     for (auto &ev : landed)
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
@@ -349,79 +353,120 @@ static int rows_to_host(const Plan *P, const void *qdev_all, int q_dtype, int64_
         Scratch o, o64;
         void *pin[RING] = {nullptr, nullptr, nullptr};
         if (e == cudaSuccess) rc = o.alloc((size_t)std::min<int64_t>(n_query, batch * RING) * wrow, stream);
-        if (!rc && e == cudaSuccess && batch_direct > 0) rc = o64.alloc((size_t)batch_direct * RING * orow, stream);
-        if (!rc && e == cudaSuccess && !direct)
+        if (!rc && e == cudaSuccess && route_mode != ROUTE_WIRE) rc = o64.alloc((size_t)std::min<int64_t>(n_query, batch * RING) * orow, stream);
+        if (!rc && e == cudaSuccess && !direct && route_mode != ROUTE_DEVICE)
             for (int k = 0; k < std::min(RING, n_batches) && !rc; ++k) rc = g_ring_out.get(k, (size_t)batch * wrow, &pin[k]);
 
-        // ---- consumers: every host thread walks the pieces in order, waits for the piece's event and moves its
-        // stripe of the piece from the pinned ring into the caller's rows (widening if asked)
-        std::vector<std::atomic<int>> issued(n_batches), consumed(n_batches);
-        for (int b = 0; b < n_batches; ++b) { issued[b].store(0); consumed[b].store(0); }
+        // ---- consumers: every host thread walks the batches in order; a wire batch's pieces are awaited one by one and
+        // the thread's stripe of each goes from the pinned ring into the caller's rows (widening if asked)
+        // route[b]: 0 not routed yet, 1 + p wire through pinned slot p, -1 device route (nothing to do for the host)
+        std::vector<std::atomic<int>> route(n_batches), consumed(n_batches);
+        for (int b = 0; b < n_batches; ++b) { route[b].store(0); consumed[b].store(0); }
         std::atomic<int> abort_flag{0};
+        const auto nap = [] { std::this_thread::sleep_for(std::chrono::microseconds(20)); };
         const std::function<void(int, int)> consumer = [&](int part, int parts) {
             for (int b = 0; b < n_batches; ++b) {
-                while (!issued[b].load(std::memory_order_acquire)) {
+                int r;
+                while ((r = route[b].load(std::memory_order_acquire)) == 0) {
                     if (abort_flag.load(std::memory_order_relaxed)) return;
-                    std::this_thread::yield();
+                    nap();
                 }
-                const int slot = b % RING;
-                const int64_t first = (int64_t)b * batch, n_all = std::min(batch, n_query - first);
-                const int64_t n = n_all - std::min(batch_direct, n_all);      // the rest arrives as float64 by itself
-                const char *src = (const char *)pin[slot];
-                char *dst = (char *)out_host + (size_t)first * orow;
-                for (int64_t r0 = 0, pc = 0; r0 < n; r0 += (int64_t)piece_rows, ++pc) {
-                    const size_t rows = (size_t)std::min<int64_t>((int64_t)piece_rows, n - r0);
-                    if (cudaEventSynchronize(landed[(size_t)slot * pieces_per_batch + pc]) != cudaSuccess) { abort_flag.store(1); return; }
-                    size_t a, c;
-                    part_range(rows * cols, 1, part, parts, &a, &c);
-                    if (!c) continue;
-                    a += (size_t)r0 * cols;
-                    if (widen_rows) widen((const float *)src + a, (double *)dst + a, c);
-                    else memcpy(dst + a * esize(out_dtype), src + a * esize(out_dtype), c * esize(out_dtype));
+                if (r > 0) {
+                    const int slot = r - 1;
+                    const int64_t first = (int64_t)b * batch, n = std::min(batch, n_query - first);
+                    const char *src = (const char *)pin[slot];
+                    char *dst = (char *)out_host + (size_t)first * orow;
+                    for (int64_t r0 = 0, pc = 0; r0 < n; r0 += (int64_t)piece_rows, ++pc) {
+                        const size_t rows = (size_t)std::min<int64_t>((int64_t)piece_rows, n - r0);
+                        if (cudaEventSynchronize(landed[(size_t)slot * pieces_per_batch + pc]) != cudaSuccess) { abort_flag.store(1); return; }
+                        size_t a, c;
+                        part_range(rows * cols, 1, part, parts, &a, &c);
+                        if (!c) continue;
+                        a += (size_t)r0 * cols;
+                        if (widen_rows) widen((const float *)src + a, (double *)dst + a, c);
+                        else memcpy(dst + a * esize(out_dtype), src + a * esize(out_dtype), c * esize(out_dtype));
+                    }
                 }
                 consumed[b].fetch_add(1, std::memory_order_release);
             }
         };
-        const bool use_consumers = !rc && e == cudaSuccess && !direct;
+        const bool use_consumers = !rc && e == cudaSuccess && !direct && route_mode != ROUTE_DEVICE;
         const int n_consumers = std::max(1, HostPool::get().workers());
         if (use_consumers) HostPool::get().start(consumer);
 
-        for (int b = 0; !rc && e == cudaSuccess && b < n_batches; ++b) {
-            const int slot = b % RING;
-            const int64_t first = (int64_t)b * batch, n = std::min(batch, n_query - first);
-            const char *qdev = (const char *)qdev_all + (size_t)first * qrow;
+        int wire_count = 0, device_count = 0;
+        int pin_user[RING] = {-1, -1, -1};                      // the batch that went through pinned slot p last
+        // hands batch j (computed into device slot j % RING) to the copy stream
+        const auto ship = [&](int j) {
+            const int slot = j % RING;
+            const int64_t first = (int64_t)j * batch, n = std::min(batch, n_query - first);
             char *odev = (char *)o.ptr + (size_t)slot * batch * wrow;
-            if (b >= RING) {
-                // the pinned slot is free once every host thread has drained batch b - RING
-                if (use_consumers)
-                    while (consumed[b - RING].load(std::memory_order_acquire) < n_consumers && !abort_flag.load()) std::this_thread::yield();
-                // the device slot is free once its previous copy has landed
-                e = cudaStreamWaitEvent(stream, drained[slot], 0);
+            if (direct) {
+                e = cudaStreamWaitEvent(copy_stream, computed[slot], 0);
+                if (e == cudaSuccess) e = cudaMemcpyAsync((char *)out_host + (size_t)first * orow, odev, (size_t)n * wrow, cudaMemcpyDeviceToHost, copy_stream);
+                if (e == cudaSuccess) e = cudaEventRecord(freed[slot], copy_stream);
+                return;
+            }
+            const int p = wire_count % RING;
+            bool to_device = route_mode == ROUTE_DEVICE;
+            if (route_mode == ROUTE_AUTO) {
+                e = cudaEventSynchronize(computed[slot]);          // decide when the rows exist, not when they are queued
+                while (e == cudaSuccess && !abort_flag.load(std::memory_order_relaxed)) {
+                    const int w = pin_user[p];
+                    if (w < 0 || consumed[w].load(std::memory_order_acquire) >= n_consumers) break;
+                    const int64_t n_w = std::min(batch, n_query - (int64_t)w * batch);
+                    const cudaError_t q = cudaEventQuery(landed[(size_t)p * pieces_per_batch + ceil_div(n_w, (int64_t)piece_rows) - 1]);
+                    if (q == cudaSuccess) { to_device = true; break; }        // landed, not drained: the host is behind
+                    if (q != cudaErrorNotReady) { e = q; break; }
+                    nap();                                                     // not landed: the link is behind
+                }
+            } else if (route_mode == ROUTE_WIRE) {
+                const int w = pin_user[p];
+                if (w >= 0 && use_consumers)
+                    while (consumed[w].load(std::memory_order_acquire) < n_consumers && !abort_flag.load(std::memory_order_relaxed)) nap();
+            }
+            if (e != cudaSuccess) return;
+            e = cudaStreamWaitEvent(copy_stream, computed[slot], 0);
+            if (to_device) {
+                // everything of this route is ordered on the copy stream: the float64 slot's previous copy is ahead of
+                // the kernel that overwrites it
+                char *odev64 = (char *)o64.ptr + (size_t)(device_count % RING) * batch * orow;
+                ++device_count;
+                const size_t elems = (size_t)n * cols;
+                if (e == cudaSuccess) {
+                    widen_rows_kernel<<<(unsigned)std::min<size_t>(ceil_div(elems, (size_t)256), (size_t)device_sm_count() * 8), 256, 0, copy_stream>>>(
+                        (const float *)odev, (double *)odev64, elems);
+                    g_launches.fetch_add(1, std::memory_order_relaxed);
+                    e = cudaGetLastError();                 // no early return here: the consumers are running
+                }
+                if (e == cudaSuccess) e = cudaEventRecord(freed[slot], copy_stream);
+                if (e == cudaSuccess) e = cudaMemcpyAsync((char *)out_host + (size_t)first * orow, odev64, (size_t)n * orow, cudaMemcpyDeviceToHost, copy_stream);
+                if (e == cudaSuccess) route[j].store(-1, std::memory_order_release);
+            } else {
+                ++wire_count;
+                pin_user[p] = j;
+                for (int64_t r0 = 0, pc = 0; e == cudaSuccess && r0 < n; r0 += (int64_t)piece_rows, ++pc) {
+                    const size_t rows = (size_t)std::min<int64_t>((int64_t)piece_rows, n - r0);
+                    e = cudaMemcpyAsync((char *)pin[p] + (size_t)r0 * wrow, odev + (size_t)r0 * wrow, rows * wrow, cudaMemcpyDeviceToHost, copy_stream);
+                    if (e == cudaSuccess) e = cudaEventRecord(landed[(size_t)p * pieces_per_batch + pc], copy_stream);
+                }
+                if (e == cudaSuccess) e = cudaEventRecord(freed[slot], copy_stream);
+                if (e == cudaSuccess) route[j].store(1 + p, std::memory_order_release);
+            }
+        };
+
+        // trip b launches the kernels of batch b, then ships batch b - 1 (whose route may have to wait for its rows)
+        for (int b = 0; !rc && e == cudaSuccess && b <= n_batches; ++b) {
+            if (b < n_batches) {
+                const int slot = b % RING;
+                const int64_t first = (int64_t)b * batch, n = std::min(batch, n_query - first);
+                if (b >= RING) e = cudaStreamWaitEvent(stream, freed[slot], 0);     // recorded when batch b - RING was shipped
                 if (e != cudaSuccess) break;
+                rc = plan_run(P, (const char *)qdev_all + (size_t)first * qrow, q_dtype, n, qbox, (char *)o.ptr + (size_t)slot * batch * wrow, wire, stream);
+                if (rc) break;
+                e = cudaEventRecord(computed[slot], stream);
             }
-            rc = plan_run(P, qdev, q_dtype, n, qbox, odev, wire, stream);
-            if (rc) break;
-            const int64_t n_direct = std::min(batch_direct, n), n_wire = n - n_direct;
-            char *odev64 = batch_direct > 0 ? (char *)o64.ptr + (size_t)slot * batch_direct * orow : nullptr;
-            if (n_direct > 0) {
-                const size_t elems = (size_t)n_direct * cols;
-                widen_rows_kernel<<<(unsigned)std::min<size_t>(ceil_div(elems, (size_t)256), (size_t)device_sm_count() * 8), 256, 0, stream>>>(
-                    (const float *)(odev + (size_t)n_wire * wrow), (double *)odev64, elems);
-                g_launches.fetch_add(1, std::memory_order_relaxed);
-                e = cudaGetLastError();                 // no early return here: the consumers are running
-            }
-            if (e == cudaSuccess) e = cudaEventRecord(computed[slot], stream);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(copy_stream, computed[slot], 0);
-            for (int64_t r0 = 0, pc = 0; e == cudaSuccess && r0 < n_wire; r0 += (int64_t)piece_rows, ++pc) {
-                const size_t rows = (size_t)std::min<int64_t>((int64_t)piece_rows, n_wire - r0);
-                void *dst = direct ? (void *)((char *)out_host + (size_t)(first + r0) * orow) : (void *)((char *)pin[slot] + (size_t)r0 * wrow);
-                e = cudaMemcpyAsync(dst, odev + (size_t)r0 * wrow, rows * wrow, cudaMemcpyDeviceToHost, copy_stream);
-                if (e == cudaSuccess) e = cudaEventRecord(landed[(size_t)slot * pieces_per_batch + pc], copy_stream);
-            }
-            if (e == cudaSuccess && n_direct > 0)
-                e = cudaMemcpyAsync((char *)out_host + (size_t)(first + n_wire) * orow, odev64, (size_t)n_direct * orow, cudaMemcpyDeviceToHost, copy_stream);
-            if (e == cudaSuccess) e = cudaEventRecord(drained[slot], copy_stream);      // both device slots are free again
-            if (e == cudaSuccess) issued[b].store(1, std::memory_order_release);
+            if (b >= 1 && e == cudaSuccess) ship(b - 1);
         }
         if (rc || e != cudaSuccess) abort_flag.store(1);
         if (use_consumers) HostPool::get().wait();
@@ -431,9 +476,10 @@ static int rows_to_host(const Plan *P, const void *qdev_all, int q_dtype, int64_
         if (!rc && e != cudaSuccess) rc = fail(NBR_ERR_CUDA, std::string("host path: ") + cudaGetErrorString(e));
         cudaStreamSynchronize(copy_stream);
         cudaStreamSynchronize(stream);
+        if (getenv("NBR_HOST_STATS")) fprintf(stderr, "[nbr host path] %d batches: %d wire, %d device route\n", n_batches, wire_count, device_count);
     }
+    for (auto ev : freed) if (ev) cudaEventDestroy(ev);
     for (auto ev : computed) if (ev) cudaEventDestroy(ev);
-    for (auto ev : drained) if (ev) cudaEventDestroy(ev);
     for (auto ev : landed) if (ev) cudaEventDestroy(ev);
     return rc;
 }

@@ -1,6 +1,6 @@
-"""dev tool: float64 host-buffer call with different shares of device-widened rows (NBR_HOST_DIRECT_SHARE)."""
+"""dev tool: float64 host-buffer call with the three routes of a pinned result (NBR_HOST_WIDEN = auto / host / device)."""
 import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for share in ("0", "0.05", "0.1", "0.15", "0.2", "0.1", "0"):
-    e = dict(os.environ); e["NBR_HOST_DIRECT_SHARE"] = share
-    subprocess.run([sys.executable, os.path.join(ROOT, "scripts/e2e_sweep.py"), "child", "share " + share], env=e)
+for mode in ("auto", "host", "device", "auto"):
+    e = dict(os.environ); e["NBR_HOST_WIDEN"] = mode; e["NBR_HOST_STATS"] = "1"
+    subprocess.run([sys.executable, os.path.join(ROOT, "scripts/e2e_sweep.py"), "child", "widen " + mode], env=e)

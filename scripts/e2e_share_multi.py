@@ -1,4 +1,5 @@
-"""dev tool (torchrun, one rank per GPU): host-buffer tile step with different shares of device-widened float64 rows."""
+"""dev tool (torchrun, one rank per GPU): host-buffer tile step with the routes of a pinned float64 result
+(NBR_HOST_WIDEN = auto / host / device, given as arguments)."""
 import math, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, torch.distributed as dist
@@ -14,7 +15,7 @@ cloud = synth.urban_scene(n, seed=20 + rank, device=dev, origin=((rank % 2) * ex
 host_in = cloud.cpu().pin_memory()
 host_out = torch.empty((n, 20), dtype=torch.float64).pin_memory()
 for share in sys.argv[1:]:
-    os.environ["NBR_HOST_DIRECT_SHARE"] = share
+    os.environ["NBR_HOST_WIDEN"] = share
     nd.process_tile_host(host_in, EDGES, RADII, out=host_out, out_dtype=np.float64, device=dev)
     dist.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -24,6 +25,6 @@ for share in sys.argv[1:]:
     t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print("world %d share %s: %.1f ms per step, %.3f G point*scales/s" % (world, share, t.item() / 3 * 1e3, world * n * 5 * 3 / t.item() / 1e9), flush=True)
+        print("world %d route %s: %.1f ms per step, %.3f G point*scales/s" % (world, share, t.item() / 3 * 1e3, world * n * 5 * 3 / t.item() / 1e9), flush=True)
 nd.release_mailboxes()
 dist.destroy_process_group()
