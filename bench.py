@@ -495,7 +495,8 @@ def gpu_arm(args, rank, world, local_rank):
             del host_out
         e2e = {"value": results["f64"][0], "unit": UNIT, "h2d_bytes_per_step": int(host_in.numel() * 4),
                "d2h_bytes_per_step": int(results["f32"][1]), "out_dtype": "float64 (drop-in default)",
-               "wire": "float32 rows over PCIe, widened to float64 by host threads inside the call",
+               "wire": "float32 rows over PCIe, widened to float64 by host threads inside the call; batches whose turn comes while "
+                       "the host threads are behind are widened on the device and land as float64 (pinned result)",
                "value_float32_out": results["f32"][0], "d2h_bytes_per_step_float32_out": int(results["f32"][1]),
                "steps": e2e_steps, "timer": "host wall clock around the synchronous host-buffer call"}
         if world == 1:
