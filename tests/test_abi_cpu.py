@@ -83,6 +83,20 @@ def test_argument_validation_needs_no_gpu():
         multiscale.process_single_core(np.random.rand(10, 4), pts, [0.1], [0.5])
 
 
+def test_gather_staging_layout_host_only():
+    """staging buffer of the feature all-gather: rows, then (256-byte aligned) one uint32 row number per row"""
+    lib = _lib.lib()
+    assert lib.nbr_gather_staging_bytes(0, 80) == 0
+    assert lib.nbr_gather_staging_bytes(1, 80) == 256 + 4
+    assert lib.nbr_gather_staging_bytes(16, 80) == 1280 + 64                 # 1280 is a multiple of 256 already
+    assert lib.nbr_gather_staging_bytes(80_000_000, 80) == 6_400_000_000 + 320_000_000
+    assert lib.nbr_gather_staging_bytes(-1, 80) == 0
+    # null / bad arguments fail before any CUDA call
+    assert lib.nbr_tile_step_gather(None, None, _lib.F32, 0, None, None, 0, None, 0, _lib.F32, 0, None, None, None, None) == _lib.ERR_INVALID
+    assert lib.nbr_gather_finish(None, None) == _lib.ERR_INVALID
+    assert lib.nbr_gather_unpermute(None, None, 80, None, None) == _lib.ERR_INVALID
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
 def test_no_cpu_fallback():
     from nimrud_b200 import geometry, multiscale

@@ -57,6 +57,11 @@ def worker(rank, world, port, tmp):
     assert torch.equal(g_lo, torch.from_numpy(cloud.astype(np.float64).min(0)))
     assert torch.equal(g_hi, torch.from_numpy(cloud.astype(np.float64).max(0)))
     feats = nd.process_tile(mine, EDGES, RADII, gather=True, compute=anchored_oracle)
+    try:
+        nd.process_tile(mine, EDGES, RADII, gather="peer", compute=anchored_oracle)      # peer stores need the CUDA path
+        raise AssertionError("gather='peer' on CPU tensors must be refused")
+    except ValueError:
+        pass
     if rank == 0:
         np.save(os.path.join(tmp, "gathered.npy"), feats.numpy())
     dist.barrier()
