@@ -258,6 +258,10 @@ int nbr_multiscale_features_tile(const void *sorted_xyz, const uint32_t *perm, i
 typedef struct nbr_mailbox nbr_mailbox;
 int nbr_mailbox_create(nbr_mailbox **out, int32_t rank, int32_t world, int dtype, int64_t capacity_rows);
 void nbr_mailbox_destroy(nbr_mailbox *mailbox);
+/* closes this rank's mappings of the peers' allocations (staging_only != 0: only the gather staging buffers).  memory that
+ * another process maps must not be freed: before teardown or a collective re-allocation every rank disconnects, the ranks
+ * meet at a barrier, then the owners free (nimrud_b200/distributed.py: release_mailboxes, HaloMailbox.ensure_gather). */
+int nbr_mailbox_disconnect(nbr_mailbox *mailbox, int32_t staging_only);
 int nbr_mailbox_ipc_handle(const nbr_mailbox *mailbox, void *handle_out_64);
 int nbr_mailbox_connect_ipc(nbr_mailbox *mailbox, int32_t peer, const void *handle_64);
 int nbr_mailbox_connect_local(nbr_mailbox *mailbox, int32_t peer, const nbr_mailbox *peer_mailbox);

@@ -72,6 +72,7 @@ SIGNATURES = {
                                                     c_i32, c_vp, ctypes.c_int, c_i32, ctypes.POINTER(c_i64), c_vp]),
     "nbr_mailbox_create": (ctypes.c_int, [ctypes.POINTER(c_vp), c_i32, c_i32, ctypes.c_int, c_i64]),
     "nbr_mailbox_destroy": (None, [c_vp]),
+    "nbr_mailbox_disconnect": (ctypes.c_int, [c_vp, c_i32]),
     "nbr_mailbox_ipc_handle": (ctypes.c_int, [c_vp, c_vp]),
     "nbr_mailbox_connect_ipc": (ctypes.c_int, [c_vp, c_i32, c_vp]),
     "nbr_mailbox_connect_local": (ctypes.c_int, [c_vp, c_i32, c_vp]),

@@ -296,13 +296,14 @@ __global__ void gather_unpermute_kernel(const unsigned char *__restrict__ staged
         if (!__any_sync(0xffffffffu, dst >= 0)) continue;
         const unsigned char *src = staged + grp * 32 * row_bytes;
         if (CPR > 0) {
-            uint4 v[CPR > 0 ? CPR : 1];
-            long long d[CPR > 0 ? CPR : 1];
-            int c[CPR > 0 ? CPR : 1];
+            constexpr int K = CPR > 0 ? CPR : 1;
+            uint4 v[K];
+            long long d[K];
+            int c[K];
 #pragma unroll
             for (int t = 0; t < CPR; ++t) {
-                const int p = lane + 32 * t, row = p / CPR;
-                c[t] = p - row * CPR;
+                const int p = lane + 32 * t, row = p / K;
+                c[t] = p - row * K;
                 d[t] = __shfl_sync(0xffffffffu, dst, row);
                 if (d[t] >= 0) v[t] = __ldcs(reinterpret_cast<const uint4 *>(src) + p);
             }
@@ -516,6 +517,33 @@ extern "C" int nbr_mailbox_create(nbr_mailbox **out, int32_t rank, int32_t world
 }
 
 extern "C" void nbr_mailbox_destroy(nbr_mailbox *mb) { delete reinterpret_cast<Mailbox *>(mb); }
+
+// closes this rank's mappings of the PEERS' allocations (mailboxes and staging buffers; staging_only != 0: only those).
+// exported memory must not be freed while another process still maps it: before a collective re-allocation or
+// teardown every rank disconnects, the ranks meet at a barrier, and only then the owners free
+extern "C" int nbr_mailbox_disconnect(nbr_mailbox *mb, int32_t staging_only)
+{
+    Mailbox *M = reinterpret_cast<Mailbox *>(mb);
+    if (!M) return fail(NBR_ERR_INVALID, "nbr_mailbox_disconnect: null argument");
+    int cur = 0;
+    NBR_CUDA(cudaGetDevice(&cur));
+    NBR_CUDA(cudaSetDevice(M->device));
+    cudaDeviceSynchronize();
+    for (int d = 0; d < MB_MAX_WORLD; ++d) {
+        if (d == M->rank) continue;
+        if (M->gather_opened[d] && M->gather_peer[d]) cudaIpcCloseMemHandle(M->gather_peer[d]);
+        M->gather_peer[d] = nullptr;
+        M->gather_peer_bytes[d] = 0;
+        M->gather_opened[d] = false;
+        if (!staging_only) {
+            if (M->opened[d] && M->peer[d]) cudaIpcCloseMemHandle(M->peer[d]);
+            M->peer[d] = nullptr;
+            M->opened[d] = false;
+        }
+    }
+    cudaSetDevice(cur);
+    return NBR_OK;
+}
 
 extern "C" int nbr_mailbox_ipc_handle(const nbr_mailbox *mb, void *handle_out_64)
 {

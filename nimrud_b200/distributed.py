@@ -285,7 +285,9 @@ class HaloMailbox(object):
             return
         nbytes = max(nbytes, 256)
         torch.cuda.synchronize(self.device)
-        dist.barrier(group)                                  # nobody still writes into the buffers that are freed now
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().nbr_mailbox_disconnect(self.handle, 1))
+        dist.barrier(group)                                  # nobody writes into or maps the buffers that are freed now
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().nbr_mailbox_gather_alloc(self.handle, nbytes))
             infos = [None] * self.world
@@ -382,8 +384,17 @@ def _group_mailbox(cloud, group):
 
 
 def release_mailboxes():
-    """collective: free the cached mailboxes (call before destroy_process_group)."""
-    for mb in list(_mailboxes.values()):
+    """collective: free the cached mailboxes (call before destroy_process_group).  every rank first closes its mappings
+    of the peers' memory, the ranks meet, then the owners free."""
+    from . import _lib
+    boxes = list(_mailboxes.values())
+    for mb in boxes:
+        if getattr(mb, "handle", None):
+            with torch.cuda.device(mb.device):
+                _lib.check(_lib.lib().nbr_mailbox_disconnect(mb.handle, 0))
+    if boxes and dist.is_available() and dist.is_initialized():
+        dist.barrier()
+    for mb in boxes:
         mb.close()
     _mailboxes.clear()
 
