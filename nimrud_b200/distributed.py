@@ -646,6 +646,24 @@ def _use_mailboxes(cloud):
             and os.environ.get("NBR_HALO", "mailbox") != "nccl")
 
 
+def gather_mode(gather, world, mailbox_path, env=None):
+    """how process_tile gathers: None (no gather), "peer" (rows stored into the peers' staging buffers by the feature
+    kernel) or "nccl" (all-gather after the kernel).  default: peer stores up to 4 ranks -- the receivers put (N - 1) n
+    rows in place with random 80-byte writes (0.9 ms per 10M rows, DRAM-bound); from 8 ranks on that costs what riding on
+    the kernel saves.  NBR_GATHER=peer|nccl|copy overrides the default, gather="peer"|"nccl" overrides both."""
+    if not gather:
+        return None
+    if gather == "peer":
+        if not mailbox_path:
+            raise ValueError('gather="peer" needs the CUDA mailbox path')
+        return "peer"
+    if gather == "nccl" or not mailbox_path:
+        return "nccl"
+    env = os.environ.get("NBR_GATHER") if env is None else env
+    auto = env if env else ("peer" if world <= 4 else "nccl")
+    return "peer" if auto in ("peer", "fused", "copy") else "nccl"
+
+
 def process_tile(cloud, edge_lengths, radii, out=None, out_dtype=np.float32, gather=False, group=None,
                  compute=None, voxel_counts=None, out_all=None):
     """
@@ -665,13 +683,17 @@ def process_tile(cloud, edge_lengths, radii, out=None, out_dtype=np.float32, gat
     world = dist.get_world_size(group)
     sizes = None
     mailbox_path = compute is None and _use_mailboxes(cloud) and world <= 16
-    if gather == "peer" and not mailbox_path:
-        raise ValueError('gather="peer" needs the CUDA mailbox path')
-    # default: the peer-store gather up to 4 ranks.  its receivers put (N - 1) n rows in place with random 80-byte
-    # writes (0.9 ms per 10M rows, DRAM-bound); from 8 ranks on that costs what riding on the kernel saves
-    auto = os.environ.get("NBR_GATHER", "peer" if world <= 4 else "nccl")
-    if gather and gather != "nccl" and mailbox_path and (gather == "peer" or auto in ("peer", "fused", "copy")):
-        return _process_tile_gather(cloud, edge_lengths, radii, out_all, out_dtype, group, voxel_counts)
+    if gather_mode(gather, world, mailbox_path) == "peer":
+        res = _process_tile_gather(cloud, edge_lengths, radii, out_all, out_dtype, group, voxel_counts)
+        if out is not None:
+            # the rows of this rank's tile are a slice of the gathered result; a caller that also wants them in `out`
+            # gets a copy
+            n = int(cloud.shape[0])
+            first = int(sum(int(v) for v in _group_mailbox(cloud, group).boxes[:dist.get_rank(group), 6]))
+            if tuple(out.shape) != (n, res.shape[1]) or out.dtype != res.dtype or out.device != res.device:
+                raise ValueError("out has the wrong shape, dtype or device")
+            out.copy_(res[first:first + n])
+        return res
     if compute is None and _use_mailboxes(cloud) and world <= 16:
         feats, boxes = _process_tile_cuda(cloud, edge_lengths, radii, out, out_dtype, group, voxel_counts)
         sizes = [int(v) for v in boxes[:, 6]]

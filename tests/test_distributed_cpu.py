@@ -81,6 +81,20 @@ def test_tile_plus_halo_equals_unpartitioned(tmp_path):
     assert np.array_equal(got, ref)          # bit for bit: same voxels, same neighbor sets
 
 
+def test_gather_mode_rule():
+    """which transport the final feature all-gather takes (no collective needed to decide)"""
+    from nimrud_b200.distributed import gather_mode
+    assert gather_mode(False, 8, True, env="") is None
+    assert gather_mode(True, 2, True, env="") == "peer" and gather_mode(True, 4, True, env="") == "peer"
+    assert gather_mode(True, 8, True, env="") == "nccl"                 # the receivers' placement pass outweighs the overlap
+    assert gather_mode(True, 8, True, env="peer") == "peer" and gather_mode(True, 2, True, env="nccl") == "nccl"
+    assert gather_mode(True, 2, True, env="copy") == "peer"             # the push-kernel form of the peer path
+    assert gather_mode("nccl", 2, True, env="peer") == "nccl" and gather_mode("peer", 8, True, env="nccl") == "peer"
+    assert gather_mode(True, 2, False, env="peer") == "nccl"            # CPU tensors / custom compute: collective gather
+    with pytest.raises(ValueError):
+        gather_mode("peer", 2, False, env="")
+
+
 def test_halo_width_rule():
     from nimrud_b200 import distributed as nd
     assert nd.halo_width((0.1, 1.6), (0.3, 4.8)) >= 4.8 + 0.8
